@@ -1,0 +1,77 @@
+// g4d_common.cuh -- constants, device-side camera, small helpers shared by every kernel.
+// Every behavioural constant of the rasterizer lives here: changing one changes pixels.
+#pragma once
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#endif
+#include <stdint.h>
+
+#include "../../include/g4d.h"
+
+#if defined(__CUDACC__)
+#define G4D_HD __host__ __device__ __forceinline__
+#define G4D_D __device__ __forceinline__
+#else
+#define G4D_HD inline
+#define G4D_D inline
+#endif
+
+namespace g4d {
+
+constexpr int kTile = 16;                 // BLOCK_X = BLOCK_Y (A: 16x16 pixel tiles)
+constexpr int kTilePixels = kTile * kTile;
+constexpr int kShCoeffs = 16;             // coefficient slots per Gaussian ([N,16,3])
+constexpr float kNearCull = 0.2f;         // A.1 step 2
+constexpr float kWEps = 0.0000001f;       // A.1 step 3
+constexpr float kGuardBand = 1.3f;        // A.1 step 5
+constexpr float kDilation = 0.3f;         // A.1 step 5
+constexpr float kMinDiscriminant = 0.1f;  // A.1 step 7
+constexpr float kAlphaMax = 0.99f;        // A.3
+constexpr float kAlphaMin = 1.0f / 255.0f;
+constexpr float kTransmittanceStop = 0.0001f;
+constexpr float kDet2Eps = 0.0000001f;    // A.4 regularised 1/(det^2+eps)
+
+constexpr float kSH0 = 0.28209479177387814f;
+constexpr float kSH1 = 0.4886025119029199f;
+// degree-2 / degree-3 constants: /root/reference/utils/sh_utils.py:26-43
+#define G4D_SH2_0 1.0925484305920792f
+#define G4D_SH2_1 -1.0925484305920792f
+#define G4D_SH2_2 0.31539156525252005f
+#define G4D_SH2_3 -1.0925484305920792f
+#define G4D_SH2_4 0.5462742152960396f
+#define G4D_SH3_0 -0.5900435899266435f
+#define G4D_SH3_1 2.890611442640554f
+#define G4D_SH3_2 -0.4570457994644658f
+#define G4D_SH3_3 0.3731763325901154f
+#define G4D_SH3_4 -0.4570457994644658f
+#define G4D_SH3_5 1.445305721320277f
+#define G4D_SH3_6 -0.5900435899266435f
+
+// Device-resident camera, written once per forward by pack_camera_kernel and read (uniformly) by all stages.
+struct CameraDev {
+    int32_t H, W, sh_degree, grid_x;
+    int32_t grid_y, num_tiles, pad0, pad1;
+    float tanfovx, tanfovy, scale_modifier, time;
+    float focal_x, focal_y, pad2, pad3;
+    float view[16];
+    float proj[16];
+    float campos[4];
+    float bg[4];
+};
+
+#if defined(__CUDACC__)
+#define G4D_CE __host__ __device__ constexpr
+#else
+#define G4D_CE constexpr
+#endif
+// plane-pair axes of combinations(range(4), 2)   (scene/hexplane.py:79): (0,1),(0,2),(0,3),(1,2),(1,3),(2,3)
+G4D_CE int plane_axis0(int k) { return k < 3 ? 0 : (k < 5 ? 1 : 2); }
+G4D_CE int plane_axis1(int k) { return k == 0 ? 1 : (k == 1 || k == 3) ? 2 : 3; }
+
+// head output widths: pos, scales, rotations, opacity, shs
+G4D_CE int head_out(int h) { return h == 0 ? 3 : h == 1 ? 3 : h == 2 ? 4 : h == 3 ? 1 : 48; }
+// column offset of head h inside the per-Gaussian delta row (always the full 59-wide layout)
+G4D_CE int head_col(int h) { return h == 0 ? 0 : h == 1 ? 3 : h == 2 ? 6 : h == 3 ? 10 : 11; }
+constexpr int kDeltaCols = 59;
+
+}  // namespace g4d

@@ -1,0 +1,94 @@
+// g4d_internal.h -- host-side declarations shared by the translation units of libg4d.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "deform_tile.cuh"
+#include "g4d_common.cuh"
+
+namespace g4d {
+
+// per-Gaussian projected record kept by a forward (SoA; sizes in DESIGN.md §3)
+struct GeomBuffers {
+    float4* rec0;        // (px, py, conic.x, conic.y)
+    float4* rec1;        // (conic.z, opacity, r, g)
+    float2* rec2;        // (b, depth)
+    int32_t* radii;
+    uint2* rect;         // x = minx | miny<<16, y = maxx | maxy<<16   (tile units)
+    uint32_t* tiles_touched;
+    uint32_t* offsets;   // inclusive scan of tiles_touched
+    uint8_t* clamped;    // bit ch set when the forward clamped colour channel ch at 0
+};
+
+struct BinBuffers {
+    uint64_t* keys_unsorted; uint64_t* keys_sorted;
+    uint32_t* ids_unsorted; uint32_t* ids_sorted;
+    uint2* ranges;       // [tiles] (start, end)
+};
+
+struct ImageBuffers {
+    float* final_T;      // [H*W]
+    uint32_t* n_contrib; // [H*W]
+};
+
+// inputs of the rasterizer stage in device memory (post-activation), either caller tensors or the
+// tensors the fused path produced
+struct RasterInputs {
+    const float* means3D; const float* scales; const float* rotations; const float* opacities;
+    const float* shs;       // fused [N,16,3] or NULL
+    const float* sh_dc;     // used when shs == NULL: [N,1,3]
+    const float* sh_rest;   //                        [N,15,3]
+};
+
+struct FusedOutputs {   // what the fused forward saves for its backward (may be NULL in deform-only mode)
+    float* means3D; float* scales; float* rotations; float* opacities;
+    float* shs;        // deformed SH coefficients, only when the SHS head is active
+    float* rot_norm;   // |q| before F.normalize (needed by its backward)
+};
+
+// ---- launchers (defined in g4d_geom.cu / g4d_raster.cu / g4d_backward.cu) -----------------------------
+cudaError_t launch_pack_camera(const G4DCamera& cam, CameraDev* dst, cudaStream_t st);
+cudaError_t launch_pack_weights(const G4DDeformParams& p, float* w0t, float* const* w1t, cudaStream_t st);
+cudaError_t launch_collapse_time_rows(const G4DDeformParams& p, const CameraDev* cam, float time, bool use_cam_time,
+                                      float* const (*trow)[3], cudaStream_t st);
+cudaError_t launch_preprocess(const CameraDev* cam, int64_t n, const RasterInputs& in, GeomBuffers g, int32_t* out_radii,
+                              cudaStream_t st);
+// mode 0: deform only (writes the five out_* tensors); mode 1: fused deform + preprocess
+cudaError_t launch_deform(const DeformDesc& d, int mode, const CameraDev* cam, float time, bool use_cam_time, int64_t n,
+                          const float* xyz, const float* scaling, const float* rotation, const float* opacity,
+                          const float* shs, const float* sh_dc, const float* sh_rest, float* out_xyz, float* out_scaling,
+                          float* out_rotation, float* out_opacity, float* out_shs, GeomBuffers g, FusedOutputs fo,
+                          int32_t* out_radii, int sm_count, cudaStream_t st);
+
+size_t scan_temp_bytes(int64_t n);
+size_t sort_temp_bytes(int64_t r);
+cudaError_t launch_scan(const uint32_t* in, uint32_t* out, int64_t n, void* temp, size_t temp_bytes, cudaStream_t st);
+cudaError_t launch_emit_keys(const CameraDev* cam, int64_t n, GeomBuffers g, BinBuffers b, int64_t capacity, cudaStream_t st);
+cudaError_t launch_sort(BinBuffers b, int64_t r, int tile_bits, void* temp, size_t temp_bytes, cudaStream_t st);
+cudaError_t launch_tile_ranges(BinBuffers b, int64_t r, int num_tiles, cudaStream_t st);
+cudaError_t launch_blend_forward(const CameraDev* cam, int grid_x, int grid_y, GeomBuffers g, BinBuffers b, ImageBuffers im,
+                                 float* out_color, float* out_depth, cudaStream_t st);
+cudaError_t launch_blend_backward(const CameraDev* cam, int grid_x, int grid_y, GeomBuffers g, BinBuffers b, ImageBuffers im,
+                                  const float* dL_dcolor, float* g_mean2D, float* g_conic, float* g_opacity, float* g_rgb,
+                                  cudaStream_t st);
+// per-Gaussian backward; g_shs may alias separate dc/rest sinks through (g_sh_dc, g_sh_rest) when g_shs == NULL
+cudaError_t launch_preprocess_backward(const CameraDev* cam, int64_t n, const RasterInputs& in, GeomBuffers g,
+                                       const float* g_mean2D, const float* g_conic, const float* g_rgb, float* g_means3D,
+                                       float* g_means2D_out, float* g_scales, float* g_rotations, float* g_shs,
+                                       float* g_sh_dc, float* g_sh_rest, cudaStream_t st);   // fused and split SH sinks may both be given
+
+size_t deform_backward_scratch_bytes(const DeformDesc& d, int64_t n);
+// go[h] / gi[h]: gradient w.r.t. the outputs / inputs of head h's residual tensor (xyz, scaling, rotation, opacity, shs)
+cudaError_t launch_deform_backward(const DeformDesc& d, const G4DDeformParams& prm, const G4DDeformGrads& grads, float time,
+                                   int64_t n, const float* xyz, const float* const go[G4D_NUM_HEADS],
+                                   float* const gi[G4D_NUM_HEADS], float* scratch, int sm_count, cudaStream_t st);
+// coarse stage of render(): activations + projection without the deformation network
+cudaError_t launch_activate_preprocess(const CameraDev* cam, int64_t n, const float* xyz, const float* scaling,
+                                       const float* rotation, const float* opacity, const float* shs, const float* sh_dc,
+                                       const float* sh_rest, GeomBuffers g, FusedOutputs fo, int32_t* out_radii,
+                                       cudaStream_t st);
+// chain rule through exp / normalize / sigmoid (gaussian_renderer/__init__.py:97-99); in-place on the gradient buffers
+cudaError_t launch_activation_backward(int64_t n, const FusedOutputs& fo, float* g_scales, float* g_rotations,
+                                       float* g_opacities, cudaStream_t st);
+
+}  // namespace g4d

@@ -1,0 +1,268 @@
+// g4d_raster.cu -- tile binning (scan, key emission, radix sort, tile ranges) and the per-tile front-to-back
+// alpha compositing forward / back-to-front backward.   SURVEY.md Appendix A.2-A.4.
+// Reference stage replaced: the CUDA rasterizer behind /root/reference/gaussian_renderer/__init__.py:120-128.
+#include <cub/cub.cuh>
+
+#include "g4d_internal.h"
+
+namespace g4d {
+
+// ------------------------------------------------------------------------------------------------------
+size_t scan_temp_bytes(int64_t n) {
+    size_t b = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, b, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
+    return b;
+}
+size_t sort_temp_bytes(int64_t r) {
+    size_t b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)r);
+    return b;
+}
+cudaError_t launch_scan(const uint32_t* in, uint32_t* out, int64_t n, void* temp, size_t temp_bytes, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    return cub::DeviceScan::InclusiveSum(temp, temp_bytes, in, out, (int)n, st);
+}
+
+// A.2: one (tile | depth bits) key and the Gaussian index per touched tile, at consecutive slots from offsets[i-1]
+__global__ void __launch_bounds__(256) emit_keys_kernel(const CameraDev* __restrict__ cam, int64_t n, GeomBuffers g,
+                                                        BinBuffers b, int64_t capacity) {
+    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= n) return;
+    if (g.tiles_touched[gi] == 0) return;
+    int64_t off = gi == 0 ? 0 : (int64_t)g.offsets[gi - 1];
+    const uint2 rc = g.rect[gi];
+    const int minx = rc.x & 0xFFFF, miny = rc.x >> 16, maxx = rc.y & 0xFFFF, maxy = rc.y >> 16;
+    const uint32_t dbits = __float_as_uint(g.rec2[gi].y);
+    const int gx = cam->grid_x;
+    for (int y = miny; y < maxy; ++y)
+        for (int x = minx; x < maxx; ++x) {
+            if (off < capacity) {
+                b.keys_unsorted[off] = ((uint64_t)(uint32_t)(y * gx + x) << 32) | dbits;
+                b.ids_unsorted[off] = (uint32_t)gi;
+            }
+            ++off;
+        }
+}
+
+cudaError_t launch_emit_keys(const CameraDev* cam, int64_t n, GeomBuffers g, BinBuffers b, int64_t capacity, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    emit_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cam, n, g, b, capacity);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sort(BinBuffers b, int64_t r, int tile_bits, void* temp, size_t temp_bytes, cudaStream_t st) {
+    if (r == 0) return cudaSuccess;
+    return cub::DeviceRadixSort::SortPairs(temp, temp_bytes, b.keys_unsorted, b.keys_sorted, b.ids_unsorted, b.ids_sorted,
+                                           (int)r, 0, 32 + tile_bits, st);
+}
+
+__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint64_t* __restrict__ keys, int64_t r, uint2* ranges) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r) return;
+    const uint32_t t = (uint32_t)(keys[i] >> 32);
+    if (i == 0 || (uint32_t)(keys[i - 1] >> 32) != t) ranges[t].x = (uint32_t)i;
+    if (i == r - 1 || (uint32_t)(keys[i + 1] >> 32) != t) ranges[t].y = (uint32_t)(i + 1);
+}
+
+cudaError_t launch_tile_ranges(BinBuffers b, int64_t r, int num_tiles, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(b.ranges, 0, sizeof(uint2) * (size_t)num_tiles, st);
+    if (e != cudaSuccess || r == 0) return e;
+    tile_ranges_kernel<<<(unsigned)((r + 255) / 256), 256, 0, st>>>(b.keys_sorted, r, b.ranges);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// A.3 blend forward: one 16x16 CTA per tile, instances staged through shared memory in batches of 256.
+__global__ void __launch_bounds__(kTilePixels)
+blend_forward_kernel(const CameraDev* __restrict__ cam, GeomBuffers g, const uint32_t* __restrict__ ids,
+                     const uint2* __restrict__ ranges, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
+                     float* __restrict__ out_color, float* __restrict__ out_depth) {
+    __shared__ float4 s0[kTilePixels];
+    __shared__ float4 s1[kTilePixels];
+    __shared__ float2 s2[kTilePixels];
+    const int H = cam->H, W = cam->W;
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    const int lx = threadIdx.x & (kTile - 1), ly = threadIdx.x >> 4;
+    const int px = blockIdx.x * kTile + lx, py = blockIdx.y * kTile + ly;
+    const bool inside = px < W && py < H;
+    const float pxf = (float)px, pyf = (float)py;
+    const uint2 range = ranges[tile];
+    const int rounds = (int)((range.y - range.x + kTilePixels - 1) / kTilePixels);
+    int todo = (int)(range.y - range.x);
+    bool done = !inside;
+    float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
+    uint32_t contributor = 0, last_contributor = 0;
+    for (int i = 0; i < rounds; ++i, todo -= kTilePixels) {
+        if (__syncthreads_count(done) == kTilePixels) break;
+        const int progress = i * kTilePixels + threadIdx.x;
+        if (range.x + progress < range.y) {
+            const uint32_t id = ids[range.x + progress];
+            s0[threadIdx.x] = g.rec0[id];
+            s1[threadIdx.x] = g.rec1[id];
+            s2[threadIdx.x] = g.rec2[id];
+        }
+        __syncthreads();
+        const int cnt = min(kTilePixels, todo);
+        for (int j = 0; !done && j < cnt; ++j) {
+            contributor++;
+            const float4 a = s0[j];
+            const float4 b = s1[j];
+            const float dx = a.x - pxf, dy = a.y - pyf;
+            const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+            if (power > 0.f) continue;
+            const float alpha = fminf(kAlphaMax, b.y * __expf(power));
+            if (alpha < kAlphaMin) continue;
+            const float test_T = T * (1.f - alpha);
+            if (test_T < kTransmittanceStop) { done = true; continue; }
+            const float w = alpha * T;
+            const float2 c = s2[j];
+            C0 = fmaf(b.z, w, C0); C1 = fmaf(b.w, w, C1); C2 = fmaf(c.x, w, C2);
+            D = fmaf(c.y, w, D);
+            T = test_T;
+            last_contributor = contributor;
+        }
+    }
+    if (inside) {
+        const size_t pix = (size_t)py * W + px;
+        const size_t hw = (size_t)H * W;
+        final_T[pix] = T;
+        n_contrib[pix] = last_contributor;
+        out_color[pix] = fmaf(T, cam->bg[0], C0);
+        out_color[hw + pix] = fmaf(T, cam->bg[1], C1);
+        out_color[2 * hw + pix] = fmaf(T, cam->bg[2], C2);
+        out_depth[pix] = D;
+    }
+}
+
+cudaError_t launch_blend_forward(const CameraDev* cam, int grid_x, int grid_y, GeomBuffers g, BinBuffers b, ImageBuffers im,
+                                 float* out_color, float* out_depth, cudaStream_t st) {
+    if (grid_x * grid_y == 0) return cudaSuccess;
+    blend_forward_kernel<<<dim3(grid_x, grid_y), kTilePixels, 0, st>>>(cam, g, b.ids_sorted, b.ranges, im.final_T,
+                                                                       im.n_contrib, out_color, out_depth);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// A.4 blend backward: same tiling, instances traversed back to front.  Per instance the 9 partial gradients
+// of a warp's 32 pixels are reduced with shuffles (only when some lane contributes) and lane 0 issues the
+// atomics, so global RED traffic is <= 8 x 9 per (tile, instance) instead of 256 x 9.
+G4D_D float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(kTilePixels)
+blend_backward_kernel(const CameraDev* __restrict__ cam, GeomBuffers g, const uint32_t* __restrict__ ids,
+                      const uint2* __restrict__ ranges, const float* __restrict__ final_T,
+                      const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dcolor,
+                      float* __restrict__ g_mean2D, float* __restrict__ g_conic, float* __restrict__ g_opacity,
+                      float* __restrict__ g_rgb) {
+    __shared__ float4 s0[kTilePixels];
+    __shared__ float4 s1[kTilePixels];
+    __shared__ float s2[kTilePixels];
+    __shared__ uint32_t sid[kTilePixels];
+    const int H = cam->H, W = cam->W;
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    const int lx = threadIdx.x & (kTile - 1), ly = threadIdx.x >> 4;
+    const int px = blockIdx.x * kTile + lx, py = blockIdx.y * kTile + ly;
+    const bool inside = px < W && py < H;
+    const float pxf = (float)px, pyf = (float)py;
+    const uint2 range = ranges[tile];
+    const int total = (int)(range.y - range.x);
+    const int rounds = (total + kTilePixels - 1) / kTilePixels;
+    const size_t pix = (size_t)py * W + px, hw = (size_t)H * W;
+    const float Tfin = inside ? final_T[pix] : 0.f;
+    float T = Tfin;
+    const int last = inside ? (int)n_contrib[pix] : 0;
+    float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
+    if (inside) { dp0 = dL_dcolor[pix]; dp1 = dL_dcolor[hw + pix]; dp2 = dL_dcolor[2 * hw + pix]; }
+    const float bgdot = cam->bg[0] * dp0 + cam->bg[1] * dp1 + cam->bg[2] * dp2;
+    const float ddx = 0.5f * (float)W, ddy = 0.5f * (float)H;
+    float ac0 = 0.f, ac1 = 0.f, ac2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
+    // block-wide maximum of n_contrib: entries beyond it contribute to no pixel of the tile
+    const int max_last = __reduce_max_sync(0xffffffffu, last);
+    __shared__ int s_max[kTilePixels / 32];
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = max_last;
+    __syncthreads();
+    int tile_last = 0;
+#pragma unroll
+    for (int w = 0; w < kTilePixels / 32; ++w) tile_last = max(tile_last, s_max[w]);
+    const int lane = threadIdx.x & 31;
+
+    for (int i = 0; i < rounds; ++i) {
+        // batch i covers list positions [total - (i+1)*256, total - i*256) traversed from the back
+        const int hi = total - i * kTilePixels;           // exclusive upper position of this batch
+        if (hi - kTilePixels >= tile_last) continue;      // whole batch behind every pixel's last contributor
+        __syncthreads();
+        const int pos = hi - 1 - (int)threadIdx.x;         // thread t stages list position hi-1-t
+        if (pos >= 0) {
+            const uint32_t id = ids[range.x + pos];
+            sid[threadIdx.x] = id;
+            s0[threadIdx.x] = g.rec0[id];
+            s1[threadIdx.x] = g.rec1[id];
+            s2[threadIdx.x] = g.rec2[id].x;
+        }
+        __syncthreads();
+        const int cnt = min(kTilePixels, hi);
+        for (int j = 0; j < cnt; ++j) {
+            const int lpos = hi - 1 - j;                  // position in the tile list (0-based)
+            if (lpos >= tile_last) continue;              // uniform across the block
+            bool valid = inside && lpos < last;
+            const float4 a = s0[j];
+            const float4 b = s1[j];
+            const float dx = a.x - pxf, dy = a.y - pyf;
+            const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+            const float G = __expf(power);
+            const float alpha = fminf(kAlphaMax, b.y * G);
+            valid = valid && power <= 0.f && alpha >= kAlphaMin;
+            if (!__any_sync(0xffffffffu, valid)) continue;
+            float v_mx = 0.f, v_my = 0.f, v_cx = 0.f, v_cy = 0.f, v_cz = 0.f, v_op = 0.f, v_r = 0.f, v_g = 0.f, v_b = 0.f;
+            if (valid) {
+                T = T / (1.f - alpha);
+                const float w = alpha * T;
+                const float c0 = b.z, c1 = b.w, c2 = s2[j];
+                ac0 = last_alpha * lc0 + (1.f - last_alpha) * ac0; lc0 = c0;
+                ac1 = last_alpha * lc1 + (1.f - last_alpha) * ac1; lc1 = c1;
+                ac2 = last_alpha * lc2 + (1.f - last_alpha) * ac2; lc2 = c2;
+                float dL_dalpha = (c0 - ac0) * dp0 + (c1 - ac1) * dp1 + (c2 - ac2) * dp2;
+                v_r = w * dp0; v_g = w * dp1; v_b = w * dp2;
+                dL_dalpha *= T;
+                last_alpha = alpha;
+                dL_dalpha += (-Tfin / (1.f - alpha)) * bgdot;
+                const float dL_dG = b.y * dL_dalpha;
+                const float gdx = G * dx, gdy = G * dy;
+                v_mx = dL_dG * (-gdx * a.z - gdy * a.w) * ddx;
+                v_my = dL_dG * (-gdy * b.x - gdx * a.w) * ddy;
+                v_cx = -0.5f * gdx * dx * dL_dG;
+                v_cy = -gdx * dy * dL_dG;
+                v_cz = -0.5f * gdy * dy * dL_dG;
+                v_op = G * dL_dalpha;
+            }
+            v_mx = warp_sum(v_mx); v_my = warp_sum(v_my);
+            v_cx = warp_sum(v_cx); v_cy = warp_sum(v_cy); v_cz = warp_sum(v_cz);
+            v_op = warp_sum(v_op);
+            v_r = warp_sum(v_r); v_g = warp_sum(v_g); v_b = warp_sum(v_b);
+            if (lane == 0) {
+                const uint32_t id = sid[j];
+                atomicAdd(g_mean2D + 2 * id, v_mx); atomicAdd(g_mean2D + 2 * id + 1, v_my);
+                atomicAdd(g_conic + 3 * id, v_cx); atomicAdd(g_conic + 3 * id + 1, v_cy); atomicAdd(g_conic + 3 * id + 2, v_cz);
+                atomicAdd(g_opacity + id, v_op);
+                atomicAdd(g_rgb + 3 * id, v_r); atomicAdd(g_rgb + 3 * id + 1, v_g); atomicAdd(g_rgb + 3 * id + 2, v_b);
+            }
+        }
+    }
+}
+
+cudaError_t launch_blend_backward(const CameraDev* cam, int grid_x, int grid_y, GeomBuffers g, BinBuffers b, ImageBuffers im,
+                                  const float* dL_dcolor, float* g_mean2D, float* g_conic, float* g_opacity, float* g_rgb,
+                                  cudaStream_t st) {
+    if (grid_x * grid_y == 0) return cudaSuccess;
+    blend_backward_kernel<<<dim3(grid_x, grid_y), kTilePixels, 0, st>>>(cam, g, b.ids_sorted, b.ranges, im.final_T,
+                                                                        im.n_contrib, dL_dcolor, g_mean2D, g_conic,
+                                                                        g_opacity, g_rgb);
+    return cudaGetLastError();
+}
+
+}  // namespace g4d

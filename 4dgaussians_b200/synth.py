@@ -118,3 +118,68 @@ WORKLOADS = {
     "C3": dict(n=300_000, width=1352, height=1014, net="dynerf", radius=2.2, focal=729.0, scale_mean=0.01, bg=(0, 0, 0)),
     "C4": dict(n=2_000_000, width=1920, height=1080, net="dynerf", radius=2.2, focal=1200.0, scale_mean=0.01, bg=(0, 0, 0)),
 }
+
+
+class SyntheticGaussianModel:
+    """Duck-types the GaussianModel attributes that render() reads (scene/gaussian_model.py:46-131):
+    ``get_xyz, _scaling, _rotation, _opacity, _features_dc, _features_rest, get_features, active_sh_degree,
+    max_sh_degree, _deformation, _deformation_table`` + the three activations."""
+
+    def __init__(self, scene: Dict[str, torch.Tensor], deformation, device="cuda", sh_degree: int = 3, requires_grad=False):
+        mk = lambda t: torch.nn.Parameter(t.to(device).contiguous(), requires_grad=requires_grad)
+        self._xyz = mk(scene["xyz"])
+        self._scaling = mk(scene["scaling"])
+        self._rotation = mk(scene["rotation"])
+        self._opacity = mk(scene["opacity"])
+        self._features_dc = mk(scene["features_dc"])
+        self._features_rest = mk(scene["features_rest"])
+        self._deformation = deformation
+        self._deformation_table = torch.ones(self._xyz.shape[0], dtype=torch.bool, device=device)
+        self.active_sh_degree = sh_degree
+        self.max_sh_degree = 3
+        self.scaling_activation = torch.exp
+        self.opacity_activation = torch.sigmoid
+        self.rotation_activation = torch.nn.functional.normalize
+
+    @property
+    def get_xyz(self):
+        return self._xyz
+
+    @property
+    def get_features(self):
+        return torch.cat((self._features_dc, self._features_rest), dim=1)
+
+    def gaussian_parameters(self):
+        return [self._xyz, self._scaling, self._rotation, self._opacity, self._features_dc, self._features_rest]
+
+
+def hidden_args(net: str):
+    """ModelHiddenParams (arguments/__init__.py:74-107) for the named reference config."""
+    from argparse import Namespace
+    cfgs = {
+        "dnerf": dict(channels=32, resolution=[64, 64, 64, 75], multires=[1, 2], net_width=64, no_do=True, no_dshs=True),
+        "hypernerf": dict(channels=16, resolution=[64, 64, 64, 100], multires=[1, 2, 4], net_width=128, no_do=True, no_dshs=True),
+        "dynerf": dict(channels=16, resolution=[64, 64, 64, 150], multires=[1, 2], net_width=128, no_do=False, no_dshs=False),
+        # small shapes for fast tests (same code paths as dnerf / dynerf)
+        "small64": dict(channels=16, resolution=[12, 10, 9, 7], multires=[1, 2], net_width=64, no_do=True, no_dshs=True),
+        "small128": dict(channels=16, resolution=[9, 12, 10, 8], multires=[1, 2], net_width=128, no_do=False, no_dshs=False),
+    }
+    c = cfgs[net]
+    return Namespace(net_width=c["net_width"], timebase_pe=4, defor_depth=1, posebase_pe=10, scale_rotation_pe=2, opacity_pe=2,
+                     timenet_width=64, timenet_output=32, bounds=1.6, grid_pe=0,
+                     kplanes_config={"grid_dimensions": 2, "input_coordinate_dim": 4, "output_coordinate_dim": c["channels"],
+                                     "resolution": list(c["resolution"])},
+                     multires=list(c["multires"]), no_dx=False, no_grid=False, no_ds=False, no_dr=False, no_do=c["no_do"],
+                     no_dshs=c["no_dshs"], empty_voxel=False, static_mlp=False, apply_rotation=False)
+
+
+def perturb_deformation(module, seed: int = 0):
+    """Synthetic 'trained' weights (SURVEY §8d): time planes 1 + N(0, 0.05) so that the deformation is not constant;
+    everything else keeps the reference initialisation."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for lvl in module.deformation_net.grid.grids:
+            for k, p in enumerate(lvl):
+                if k in (2, 4, 5):
+                    p.add_((torch.randn(p.shape, generator=g) * 0.05).to(p.device))
+    return module

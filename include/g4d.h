@@ -1,0 +1,192 @@
+/*
+ * g4d -- C-ABI of the B200-native fused deform + rasterize render path for 4D Gaussian Splatting.
+ *
+ * Plain C, plain pointers and sizes, no torch types.  Every pointer named `d_*` or documented as
+ * "device" is a CUDA device pointer on the workspace's device; everything else is host memory.
+ * All tensors are contiguous fp32 unless stated.  All entry points return 0 on success, a negative
+ * G4D_ERR_* code otherwise (g4d_last_error() gives the text); nothing here ever falls back to a CPU
+ * implementation.
+ *
+ * Reference interfaces replaced (file:line under /root/reference):
+ *   g4d_rasterize_forward / _backward
+ *       <- diff_gaussian_rasterization.GaussianRasterizer.forward / autograd backward, called at
+ *          gaussian_renderer/__init__.py:120-128 with the settings built at :38-51
+ *          (upstream: _C.rasterize_gaussians / _C.rasterize_gaussians_backward)
+ *   g4d_deform_forward / _backward
+ *       <- scene/deformation.py:185-212 deform_network.forward (HexPlane scene/hexplane.py:73-106 +
+ *          MLP scene/deformation.py:67-148) and its autograd backward
+ *   g4d_render_forward / _backward
+ *       <- gaussian_renderer/__init__.py:18-138 render(): deform (":87") + activations (":97-99") +
+ *          rasterize (":120") as ONE fused device pass, no intermediate tensors through the caller
+ *   G4DCamera
+ *       <- GaussianRasterizationSettings (gaussian_renderer/__init__.py:38-51) + viewpoint_camera.time (":52")
+ *   G4DDeformParams
+ *       <- deform_network.state_dict(); planes are channel-last views of the
+ *          [1,C,H,W] checkpoint tensors, Linear weights are torch's [out,in] row-major
+ */
+#ifndef G4D_H_
+#define G4D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G4D_ABI_VERSION 1
+#define G4D_MAX_LEVELS 4
+#define G4D_NUM_HEADS 5 /* pos, scales, rotations, opacity, shs (scene/deformation.py:61-65) */
+
+enum {
+    G4D_OK = 0,
+    G4D_ERR_CUDA = -1,      /* a CUDA runtime call or kernel failed */
+    G4D_ERR_ARG = -2,       /* invalid argument / unsupported configuration */
+    G4D_ERR_NOMEM = -3,     /* device allocation failed */
+    G4D_ERR_STATE = -4,     /* backward without a matching forward, ... */
+    G4D_ERR_OVERFLOW = -5   /* tile-instance buffer overflowed in no-sync mode; re-run with sync */
+};
+
+enum { /* bits of G4DDeformParams.head_mask: a set bit means the head is ACTIVE (not no_dx etc.) */
+    G4D_HEAD_POS = 1, G4D_HEAD_SCALES = 2, G4D_HEAD_ROT = 4, G4D_HEAD_OPACITY = 8, G4D_HEAD_SHS = 16
+};
+
+typedef struct G4DWorkspace G4DWorkspace; /* per-device scratch, packed-parameter cache */
+typedef struct G4DContext G4DContext;     /* state one forward keeps for its backward */
+
+typedef struct G4DCamera {
+    int32_t image_height, image_width;
+    int32_t sh_degree; /* active SH degree 0..3 */
+    int32_t debug;     /* !=0: synchronise + check after every stage (settings.debug) */
+    float tanfovx, tanfovy, scale_modifier;
+    float time;        /* viewpoint_camera.time; ignored by the plain rasterizer entry points */
+    float viewmatrix[16]; /* world_view_transform, row-vector convention (scene/cameras.py:59) */
+    float projmatrix[16]; /* full_proj_transform (scene/cameras.py:63) */
+    float campos[3];
+    float bg[3];
+    /* optional DEVICE sources; when non-NULL they override the host arrays above (the reference
+     * passes these four as CUDA tensors) */
+    const float *d_viewmatrix, *d_projmatrix, *d_campos, *d_bg;
+} G4DCamera;
+
+typedef struct G4DDeformParams {
+    int32_t levels;    /* len(multires) <= G4D_MAX_LEVELS */
+    int32_t channels;  /* kplanes output_coordinate_dim: multiple of 4, <= 32 */
+    int32_t net_width; /* 64, 128 or 256 */
+    int32_t head_mask; /* G4D_HEAD_* bits */
+    int32_t res[G4D_MAX_LEVELS][4]; /* per level: resolution of x, y, z, t */
+    /* device: plane k of level l, CHANNEL-LAST [H][W][C]; (H,W) = (res[c1], res[c0]) for the k-th
+     * pair (c0,c1) of combinations(range(4),2)  (scene/hexplane.py:48-70) */
+    const float *planes[G4D_MAX_LEVELS][6];
+    const float *aabb;      /* device [2][3]: row 0 = xyz_max, row 1 = xyz_min */
+    const float *w0, *b0;   /* device: feature_out.0  [Wd][F], [Wd] */
+    const float *w1[G4D_NUM_HEADS], *b1[G4D_NUM_HEADS]; /* device: <head>.1  [Wd][Wd], [Wd] */
+    const float *w2[G4D_NUM_HEADS], *b2[G4D_NUM_HEADS]; /* device: <head>.3  [k][Wd], [k]; k = 3,3,4,1,48 */
+    uint64_t version; /* caller bumps it whenever any weight changed (packed copies are cached) */
+} G4DDeformParams;
+
+/* gradient sinks mirroring G4DDeformParams (device, same layouts; ACCUMULATED into, caller zeroes) */
+typedef struct G4DDeformGrads {
+    float *planes[G4D_MAX_LEVELS][6];
+    float *w0, *b0;
+    float *w1[G4D_NUM_HEADS], *b1[G4D_NUM_HEADS];
+    float *w2[G4D_NUM_HEADS], *b2[G4D_NUM_HEADS];
+} G4DDeformGrads;
+
+/* the GaussianModel tensors render() reads (scene/gaussian_model.py:108-131), all device */
+typedef struct G4DGaussians {
+    int64_t n;
+    const float *xyz;           /* [N,3] */
+    const float *scaling;       /* [N,3] log-scale (pre-activation) */
+    const float *rotation;      /* [N,4] raw quaternion, w first */
+    const float *opacity;       /* [N,1] logit */
+    const float *features_dc;   /* [N,1,3] */
+    const float *features_rest; /* [N,15,3]; NULL => features_dc points at a fused [N,16,3] tensor */
+} G4DGaussians;
+
+typedef struct G4DGaussianGrads { /* device, OVERWRITTEN */
+    float *xyz, *scaling, *rotation, *opacity, *features_dc, *features_rest;
+    float *means2D; /* [N,3] screen-space gradient in NDC units (z = 0): viewspace_points.grad */
+} G4DGaussianGrads;
+
+typedef struct G4DStats { /* filled by g4d_context_stats (synchronises the context's stream) */
+    int64_t num_rendered; /* R = number of (Gaussian, tile) instances */
+    int64_t num_visible;  /* Gaussians with radius > 0 */
+    int64_t instance_capacity;
+    int32_t tiles_x, tiles_y;
+} G4DStats;
+
+int g4d_abi_version(void);
+const char *g4d_last_error(void);
+
+G4DWorkspace *g4d_workspace_create(int device);
+void g4d_workspace_destroy(G4DWorkspace *ws);
+G4DContext *g4d_context_create(G4DWorkspace *ws);
+void g4d_context_destroy(G4DContext *ctx);
+int g4d_context_stats(G4DContext *ctx, G4DStats *out);
+
+/* ---- deformation network (drop-in for deform_network.forward) ----------------------------------
+ * shs may be NULL when the SHS head is inactive (then out_shs is not written). Outputs are the
+ * PRE-activation tensors, same shapes as the inputs. */
+int g4d_deform_forward(G4DWorkspace *ws, const G4DDeformParams *prm, int64_t n, const float *xyz,
+                       const float *scaling, const float *rotation, const float *opacity, const float *shs,
+                       float time, float *out_xyz, float *out_scaling, float *out_rotation, float *out_opacity,
+                       float *out_shs, void *stream);
+/* g_out_* are dL/d(outputs) (NULL = zero).  g_in_* are OVERWRITTEN with dL/d(inputs) including the
+ * residual path; weight/plane gradients are ACCUMULATED into `grads`. */
+int g4d_deform_backward(G4DWorkspace *ws, const G4DDeformParams *prm, G4DDeformGrads *grads, int64_t n,
+                        const float *xyz, float time, const float *g_out_xyz, const float *g_out_scaling,
+                        const float *g_out_rotation, const float *g_out_opacity, const float *g_out_shs,
+                        float *g_in_xyz, float *g_in_scaling, float *g_in_rotation, float *g_in_opacity,
+                        float *g_in_shs, void *stream);
+
+/* ---- rasterizer (drop-in for GaussianRasterizer) ------------------------------------------------
+ * Inputs are POST-activation (scales = exp, rotations normalised, opacities = sigmoid), shs [N,16,3].
+ * out_color [3,H,W], out_depth [1,H,W], out_radii [N] int32. */
+int g4d_rasterize_forward(G4DContext *ctx, const G4DCamera *cam, int64_t n, const float *means3D,
+                          const float *shs, const float *opacities, const float *scales, const float *rotations,
+                          float *out_color, float *out_depth, int32_t *out_radii, void *stream);
+/* all g_* OVERWRITTEN: g_means3D [N,3], g_means2D [N,3], g_shs [N,16,3], g_opacities [N,1], g_scales [N,3],
+ * g_rotations [N,4] */
+int g4d_rasterize_backward(G4DContext *ctx, const G4DCamera *cam, int64_t n, const float *means3D,
+                           const float *shs, const float *opacities, const float *scales, const float *rotations,
+                           const float *dL_dcolor, float *g_means3D, float *g_means2D, float *g_shs,
+                           float *g_opacities, float *g_scales, float *g_rotations, void *stream);
+
+/* ---- fused render (drop-in for gaussian_renderer.render) ----------------------------------------
+ * prm == NULL renders the "coarse" stage (no deformation, gaussian_renderer/__init__.py:80-81). */
+int g4d_render_forward(G4DContext *ctx, const G4DCamera *cam, const G4DDeformParams *prm, const G4DGaussians *g,
+                       float *out_color, float *out_depth, int32_t *out_radii, void *stream);
+int g4d_render_backward(G4DContext *ctx, const G4DCamera *cam, const G4DDeformParams *prm, G4DDeformGrads *pgrads,
+                        const G4DGaussians *g, const float *dL_dcolor, G4DGaussianGrads *ggrads, void *stream);
+
+/* ---- options / introspection --------------------------------------------------------------------*/
+enum { G4D_OPT_SYNC_MODE = 1,  /* 1 (default): size the instance buffer exactly (one host sync per
+                                  forward, like the reference); 0: no host sync, capacity-bounded, overflow
+                                  reported by the NEXT call on the context / g4d_context_stats */
+       G4D_OPT_INSTANCE_CAPACITY = 2, /* minimum instance capacity for no-sync mode */
+       G4D_OPT_TIGHT_CULL = 3  /* 0 (default): reference tile rects; 1: drop (Gaussian,tile) pairs that
+                                  provably contribute nothing (images identical, fewer instances) */ };
+int g4d_workspace_set_option(G4DWorkspace *ws, int option, int64_t value);
+
+/* copy an internal per-forward buffer to HOST memory (tests / debugging; synchronises).
+ * Returns the number of bytes the buffer holds (>=0) or an error; copies min(bytes, held). */
+enum { G4D_BUF_DEPTH = 1,      /* float  [N]  view-space depth                    */
+       G4D_BUF_RECT = 2,       /* int32  [N,4] (min_x, min_y, max_x, max_y) tiles */
+       G4D_BUF_TILES_TOUCHED = 3, /* uint32 [N]                                   */
+       G4D_BUF_XY = 4,         /* float  [N,2] pixel centre                       */
+       G4D_BUF_CONIC_OPACITY = 5, /* float [N,4]                                  */
+       G4D_BUF_RGB = 6,        /* float  [N,3]                                    */
+       G4D_BUF_SORTED_KEYS = 7,   /* uint64 [R]                                   */
+       G4D_BUF_SORTED_IDS = 8,    /* uint32 [R]                                   */
+       G4D_BUF_RANGES = 9,     /* uint32 [tiles,2]                                */
+       G4D_BUF_FINAL_T = 10,   /* float  [H,W]                                    */
+       G4D_BUF_N_CONTRIB = 11, /* uint32 [H,W]                                    */
+       G4D_BUF_CLAMPED = 12,   /* uint8  [N,3]                                    */
+       G4D_BUF_DEFORMED = 13   /* float  [N,11] (xyz, scale, rot, opacity) post-activation, fused path */ };
+int64_t g4d_context_read(G4DContext *ctx, int which, void *host_dst, int64_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G4D_H_ */

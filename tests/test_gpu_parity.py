@@ -1,0 +1,337 @@
+"""GPU parity tests: the CUDA path (through the C-ABI / drop-in modules) against the CPU oracle.
+
+Tolerances (north_star): fp32 image L_inf <= 1e-4; index data (depth bits, radii, tile rects, sort keys, sorted
+ids, tile ranges) BIT-EXACT given identical post-deformation inputs; gradients relative 2e-3 of the tensor's max
+(fp32 atomics in arbitrary order vs the oracle's fp64 accumulation).
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import deform_ref as dr
+from oracle import raster_ref as rr
+from util_scene import (OracleRaster, cam_tuple, g4d, make_module, oracle_params_from_module, oracle_render, raster_inputs,
+                        rel_err, synth)
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+IMG_TOL = 1e-4
+GRAD_TOL = 2e-3
+
+
+def _settings(cam, bg, sh_degree=3, scale_modifier=1.0, debug=False, dev="cuda"):
+    return g4d.GaussianRasterizationSettings(
+        image_height=cam.image_height, image_width=cam.image_width, tanfovx=math.tan(cam.FoVx * 0.5),
+        tanfovy=math.tan(cam.FoVy * 0.5), bg=torch.tensor(bg, dtype=torch.float32, device=dev), scale_modifier=scale_modifier,
+        viewmatrix=cam.world_view_transform.to(dev), projmatrix=cam.full_proj_transform.to(dev), sh_degree=sh_degree,
+        campos=cam.camera_center.to(dev), prefiltered=False, debug=debug)
+
+
+def _raster_case(n, seed, wh, theta, radius, deg, bg, scale_mean, modifier=1.0):
+    cam = synth.make_camera(theta, wh[0], wh[1], radius=radius)
+    ins64 = raster_inputs(n, seed, scale_mean=scale_mean)
+    ins = [t.float() for t in ins64]
+    rc, _ = cam_tuple(cam, bg, sh_degree=deg, scale_modifier=modifier)
+    return cam, ins, rc
+
+
+RASTER_CASES = [
+    dict(n=10_000, seed=0, wh=(400, 400), theta=15.0, radius=4.0, deg=3, bg=(1.0, 1.0, 1.0), scale_mean=0.02),   # BASELINE C0
+    dict(n=3_000, seed=1, wh=(203, 117), theta=-80.0, radius=1.6, deg=2, bg=(0.0, 0.0, 0.0), scale_mean=0.05),    # ragged, near plane
+    dict(n=777, seed=2, wh=(64, 48), theta=120.0, radius=3.0, deg=0, bg=(0.3, 0.6, 0.9), scale_mean=0.3),         # heavy overlap
+    dict(n=1, seed=3, wh=(32, 32), theta=0.0, radius=4.0, deg=1, bg=(0.5, 0.5, 0.5), scale_mean=0.1),
+]
+
+
+@pytest.mark.parametrize("ci", range(len(RASTER_CASES)))
+def test_rasterizer_forward_indices_bit_exact_and_image(ci):
+    c = RASTER_CASES[ci]
+    cam, ins, rc = _raster_case(**c)
+    m3, sc, ro, op, sh = [t.cuda() for t in ins]
+    rast = g4d.GaussianRasterizer(_settings(cam, c["bg"], c["deg"]))
+    from importlib import import_module
+    rz = import_module("4dgaussians_b200.rasterizer")
+    m2 = torch.zeros_like(m3, requires_grad=True)
+    m3r = m3.clone().requires_grad_(True)
+    color, radii, depth = rast(means3D=m3r, means2D=m2, shs=sh, colors_precomp=None, opacities=op, scales=sc, rotations=ro,
+                               cov3D_precomp=None)
+    ctx = color.grad_fn.lease.ctx
+    ref = rr.rasterize_forward(rc, *[t.numpy() for t in (ins[0], ins[1], ins[2], ins[3], ins[4])])
+    pr, bn = ref["proj"], ref["bin"]
+    # --- bit-exact index data
+    assert np.array_equal(radii.cpu().numpy(), ref["radii"])
+    for name, want in (("depth", pr.depth), ("rect", pr.rect), ("tiles_touched", pr.tiles_touched), ("xy", pr.xy),
+                       ("conic_opacity", pr.conic_op), ("rgb", pr.rgb), ("clamped", pr.clamped)):
+        got = ctx.read(name)
+        assert got.shape == want.shape, name
+        assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), name
+    st = ctx.stats()
+    assert st.num_rendered == bn.R and st.num_visible == int((ref["radii"] > 0).sum())
+    assert np.array_equal(ctx.read("sorted_keys"), bn.keys)
+    assert np.array_equal(ctx.read("sorted_ids"), bn.ids)
+    assert np.array_equal(ctx.read("ranges"), bn.ranges)
+    # --- images within the fp32 tolerance
+    assert color.shape == (3, cam.image_height, cam.image_width) and depth.shape == (1, cam.image_height, cam.image_width)
+    assert np.abs(color.detach().cpu().numpy() - ref["color"]).max() <= IMG_TOL
+    assert np.abs(depth.cpu().numpy() - ref["depth"]).max() <= 4 * IMG_TOL
+    assert (ctx.read("n_contrib").reshape(cam.image_height, -1) != ref["n_contrib"]).mean() < 0.005
+
+
+@pytest.mark.parametrize("ci", range(len(RASTER_CASES)))
+def test_rasterizer_backward(ci):
+    c = RASTER_CASES[ci]
+    cam, ins, rc = _raster_case(**c)
+    dev_ins = [t.cuda().requires_grad_(True) for t in ins]
+    m3, sc, ro, op, sh = dev_ins
+    m2 = torch.zeros_like(m3, requires_grad=True)
+    rast = g4d.GaussianRasterizer(_settings(cam, c["bg"], c["deg"]))
+    color, radii, depth = rast(means3D=m3, means2D=m2, shs=sh, colors_precomp=None, opacities=op, scales=sc, rotations=ro,
+                               cov3D_precomp=None)
+    g = torch.Generator().manual_seed(ci)
+    dL = torch.randn(color.shape, generator=g)
+    color.backward(dL.cuda())
+    ref = rr.rasterize_forward(rc, *[t.numpy() for t in ins])
+    want = rr.rasterize_backward(rc, *[t.numpy() for t in ins], ref, dL.numpy())
+    for t, nm in ((m3, "means3D"), (m2, "means2D"), (sh, "shs"), (op, "opacities"), (sc, "scales"), (ro, "rots")):
+        assert t.grad is not None, nm
+        e = rel_err(t.grad.cpu().numpy().reshape(want[nm].shape), want[nm])
+        assert e <= GRAD_TOL, (nm, e)
+
+
+def test_rasterizer_edge_cases():
+    cam = synth.make_camera(0.0, 40, 24)
+    rast = g4d.GaussianRasterizer(_settings(cam, (0.3, 0.3, 0.3)))
+    z = lambda *s: torch.zeros(*s, device="cuda")
+    color, radii, depth = rast(means3D=z(0, 3), means2D=z(0, 3), shs=z(0, 16, 3), colors_precomp=None, opacities=z(0, 1),
+                               scales=z(0, 3), rotations=z(0, 4), cov3D_precomp=None)
+    assert torch.allclose(color, torch.full_like(color, 0.3)) and radii.numel() == 0 and float(depth.abs().max()) == 0.0
+    with pytest.raises(Exception):
+        rast(means3D=z(1, 3), means2D=z(1, 3), shs=None, colors_precomp=None, opacities=z(1, 1), scales=z(1, 3),
+             rotations=z(1, 4), cov3D_precomp=None)
+    with pytest.raises(Exception):
+        rast(means3D=z(1, 3), means2D=z(1, 3), shs=z(1, 16, 3), colors_precomp=None, opacities=z(1, 1), scales=None,
+             rotations=None, cov3D_precomp=None)
+    # all Gaussians culled (behind the camera)
+    cc = cam.camera_center
+    behind = (cc + cc / cc.norm()).reshape(1, 3).cuda()
+    color, radii, depth = rast(means3D=behind, means2D=z(1, 3), shs=z(1, 16, 3), colors_precomp=None,
+                               opacities=torch.full((1, 1), 0.9, device="cuda"), scales=torch.full((1, 3), 0.1, device="cuda"),
+                               rotations=torch.tensor([[1.0, 0, 0, 0]], device="cuda"), cov3D_precomp=None)
+    assert int(radii[0]) == 0 and torch.allclose(color, torch.full_like(color, 0.3))
+    # CPU tensors must be refused loudly (no CPU fallback)
+    with pytest.raises(RuntimeError):
+        rast(means3D=torch.zeros(1, 3), means2D=torch.zeros(1, 3), shs=torch.zeros(1, 16, 3), colors_precomp=None,
+             opacities=torch.zeros(1, 1), scales=torch.ones(1, 3), rotations=torch.ones(1, 4), cov3D_precomp=None)
+
+
+# --------------------------------------------------------------------------------------------------- deformation
+def _deform_inputs(n, seed, dev="cuda"):
+    from oracle.make_golden_deform import synth_inputs
+    (xyz, sc, rot, op, shs), probes = synth_inputs(n, seed)
+    return [t.to(dev) for t in (xyz, sc, rot, op, shs)], probes
+
+
+@pytest.mark.parametrize("net,n", [("small64", 1000), ("small128", 517), ("dnerf", 4099), ("hypernerf", 2050), ("dynerf", 3001)])
+@pytest.mark.parametrize("t", [0.0, 0.37, 1.0])
+def test_deform_forward_vs_oracle(net, n, t):
+    mod = make_module(net, seed=3)
+    cfg, prm = oracle_params_from_module(mod)
+    ins, _ = _deform_inputs(n, 5)
+    with torch.no_grad():
+        outs = mod(*ins, torch.tensor(t).repeat(n, 1).cuda())
+        want = dr.deform_forward(cfg, prm, *[x.cpu() for x in ins], t)
+    for o, w, nm in zip(outs, want, ("pts", "scales", "rot", "opacity", "shs")):
+        assert o.shape == w.shape, nm
+        assert float((o.cpu() - w).abs().max()) <= 2e-5, (nm, float((o.cpu() - w).abs().max()))
+    a = mod.args
+    assert (outs[3] is ins[3]) == bool(a.no_do) and (outs[4] is ins[4]) == bool(a.no_dshs)
+
+
+@pytest.mark.parametrize("name", ["dnerf", "hypernerf", "dynerf"])
+def test_deform_forward_vs_reference_golden(name):
+    """Golden vectors produced by the REFERENCE's own scene.deformation.deform_network (tests/golden/deform_*.npz)."""
+    from oracle.make_golden_deform import synth_inputs
+    z = np.load(os.path.join(GOLD, f"deform_{name}.npz"))
+    cfg = dr.CONFIGS[name]
+    aabb = torch.tensor([[1.31, 1.27, 1.3], [-1.29, -1.3, -1.22]])
+    prm = dr.random_params(cfg, seed=int(z["seed"]), aabb=aabb)
+    mod = g4d.deform_network(synth.hidden_args(name))
+    sd = mod.state_dict()
+    sd.update(dr.params_to_state_dict(prm))
+    mod.load_state_dict(sd)
+    mod = mod.cuda()
+    (xyz, sc, rot, op, shs), _ = synth_inputs(int(z["n"]), int(z["seed"]))
+    for ti, t in enumerate(z["times"]):
+        with torch.no_grad():
+            outs = mod(xyz.cuda(), sc.cuda(), rot.cuda(), op.cuda(), shs.cuda(), torch.tensor(float(t)).repeat(xyz.shape[0], 1).cuda())
+        for nm, o in zip(("pts", "scales", "rot", "opacity", "shs"), outs):
+            assert float((o.cpu() - torch.from_numpy(z[f"t{ti}_{nm}"])).abs().max()) <= 3e-5, (name, nm)
+
+
+@pytest.mark.parametrize("net,n", [("small64", 700), ("small128", 517), ("dynerf", 1500), ("dnerf", 1300)])
+def test_deform_backward_vs_oracle(net, n):
+    t = 0.61
+    mod = make_module(net, seed=4)
+    cfg, prm = oracle_params_from_module(mod)
+    ins, probes = _deform_inputs(n, 6)
+    dev_in = [x.clone().requires_grad_(True) for x in ins]
+    outs = mod(*dev_in, torch.tensor(t).repeat(n, 1).cuda())
+    loss = sum((o * p.cuda()).sum() for o, p in zip(outs, probes))
+    loss.backward()
+    cpu_in = [x.cpu().clone().requires_grad_(True) for x in ins]
+    w = dr.deform_forward(cfg, prm, *cpu_in, t)
+    sum((o * p).sum() for o, p in zip(w, probes)).backward()
+    for a, b, nm in zip(dev_in, cpu_in, ("xyz", "scales", "rot", "opacity", "shs")):
+        e = rel_err(a.grad.cpu().numpy(), b.grad.numpy())
+        assert e <= GRAD_TOL, (nm, e)
+    osd = dr.params_to_state_dict(prm)
+    for k, p in mod.named_parameters():
+        if k not in osd or not p.requires_grad:
+            continue
+        ref_g = osd[k].grad
+        if ref_g is None:      # inactive head: no gradient on either side
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        e = rel_err(p.grad.cpu().numpy(), ref_g.numpy())
+        assert e <= GRAD_TOL, (k, e)
+
+
+# --------------------------------------------------------------------------------------------------- fused render()
+class _Pipe:
+    convert_SHs_python = False
+    compute_cov3D_python = False
+    debug = False
+
+
+FUSED_CASES = [dict(net="small64", n=900, wh=(96, 64), theta=20.0, radius=4.0, t=0.3, deg=3, bg=(1.0, 1.0, 1.0), scale=0.08),
+               dict(net="small128", n=1100, wh=(80, 112), theta=-50.0, radius=2.0, t=0.8, deg=2, bg=(0.0, 0.0, 0.0), scale=0.05),
+               dict(net="dynerf", n=2500, wh=(203, 152), theta=100.0, radius=2.2, t=0.5, deg=3, bg=(0.0, 0.0, 0.0), scale=0.04)]
+
+
+def _fused_setup(c, stage="fine", grad=True):
+    scene = synth.make_scene(c["n"], seed=11, scale_mean=c["scale"])
+    mod = make_module(c["net"], seed=2, aabb=scene["aabb"])
+    pc = synth.SyntheticGaussianModel(scene, mod, sh_degree=c["deg"], requires_grad=grad)
+    cam = synth.make_camera(c["theta"], c["wh"][0], c["wh"][1], radius=c["radius"], time=c["t"])
+    return scene, mod, pc, cam
+
+
+@pytest.mark.parametrize("ci", range(len(FUSED_CASES)))
+@pytest.mark.parametrize("stage", ["fine", "coarse"])
+def test_fused_render_forward(ci, stage):
+    c = FUSED_CASES[ci]
+    scene, mod, pc, cam = _fused_setup(c, grad=False)
+    bg = torch.tensor(c["bg"], device="cuda")
+    with torch.no_grad():
+        out = g4d.render(cam, pc, _Pipe(), bg, stage=stage)
+    cfg, prm = oracle_params_from_module(mod)
+    with torch.no_grad():
+        color, depth, radii, rc, deformed = oracle_render(cfg, prm, scene, cam, c["t"], c["bg"], sh_degree=c["deg"], stage=stage)
+    assert set(out.keys()) == {"render", "viewspace_points", "visibility_filter", "radii", "depth"}
+    # radii / visibility may differ only where the fused MLP's fp32 rounding moves a Gaussian across a ceil()/cull
+    # boundary (SURVEY §7 "bit-exact ... given identical post-deformation inputs")
+    mism = (out["radii"].cpu().numpy() != radii.numpy()).mean()
+    assert mism <= (0.0 if stage == "coarse" else 2e-3), mism
+    assert float((out["render"].cpu() - color).abs().max()) <= (IMG_TOL if stage == "coarse" else 5 * IMG_TOL)
+    assert float((out["depth"].cpu() - depth).abs().max()) <= 2e-3
+    assert torch.equal(out["visibility_filter"], out["radii"] > 0)
+
+
+@pytest.mark.parametrize("ci", range(len(FUSED_CASES)))
+@pytest.mark.parametrize("stage", ["fine", "coarse"])
+def test_fused_render_backward(ci, stage):
+    c = FUSED_CASES[ci]
+    scene, mod, pc, cam = _fused_setup(c, grad=True)
+    bg = torch.tensor(c["bg"], device="cuda")
+    out = g4d.render(cam, pc, _Pipe(), bg, stage=stage)
+    g = torch.Generator().manual_seed(ci)
+    dL = torch.randn(out["render"].shape, generator=g)
+    (out["render"] * dL.cuda()).sum().backward()
+    cfg, prm = oracle_params_from_module(mod)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in scene.items() if k != "aabb"}
+    color, depth, radii, rc, _ = oracle_render(cfg, prm, leaves, cam, c["t"], c["bg"], sh_degree=c["deg"], stage=stage)
+    (color * dL).sum().backward()
+    pairs = (("xyz", pc._xyz), ("scaling", pc._scaling), ("rotation", pc._rotation), ("opacity", pc._opacity),
+             ("features_dc", pc._features_dc), ("features_rest", pc._features_rest))
+    for nm, p in pairs:
+        e = rel_err(p.grad.cpu().numpy(), leaves[nm].grad.numpy())
+        assert e <= 3 * GRAD_TOL, (nm, e)
+    e = rel_err(out["viewspace_points"].grad.cpu().numpy(), OracleRaster.last_means2D_grad)
+    assert e <= 3 * GRAD_TOL, ("viewspace_points", e)
+    if stage == "fine":
+        osd = dr.params_to_state_dict(prm)
+        for k, p in mod.named_parameters():
+            if k in osd and p.requires_grad and osd[k].grad is not None:
+                e = rel_err(p.grad.cpu().numpy(), osd[k].grad.numpy())
+                assert e <= 3 * GRAD_TOL, (k, e)
+    else:
+        assert all(p.grad is None for p in mod.parameters())
+
+
+def test_render_matches_unfused_dropin_composition():
+    """render() fused == reference-style composition through the drop-in modules (deform_network -> activations ->
+    GaussianRasterizer), both on the GPU."""
+    c = FUSED_CASES[2]
+    scene, mod, pc, cam = _fused_setup(c, grad=False)
+    bg = torch.tensor(c["bg"], device="cuda")
+    with torch.no_grad():
+        fused = g4d.render(cam, pc, _Pipe(), bg, stage="fine")
+        n = c["n"]
+        m3, sc, rot, op, sh = mod(pc.get_xyz, pc._scaling, pc._rotation, pc._opacity, pc.get_features,
+                                  torch.tensor(c["t"]).repeat(n, 1).cuda())
+        rast = g4d.GaussianRasterizer(_settings(cam, c["bg"], c["deg"]))
+        img, radii, depth = rast(means3D=m3, means2D=torch.zeros_like(m3), shs=sh, colors_precomp=None,
+                                 opacities=torch.sigmoid(op), scales=torch.exp(sc), rotations=torch.nn.functional.normalize(rot),
+                                 cov3D_precomp=None)
+    assert float((fused["render"] - img).abs().max()) <= IMG_TOL
+    assert (fused["radii"] != radii).float().mean() <= 1e-3
+
+
+# --------------------------------------------------------------------------------------------------- full-size properties
+def test_full_size_properties_C3():
+    """BASELINE.json config 3 sizes (300k Gaussians, 1352x1014): size-independent properties."""
+    w = synth.WORKLOADS["C3"]
+    scene = synth.make_scene(w["n"], seed=0, scale_mean=w["scale_mean"])
+    mod = make_module(w["net"], seed=0, aabb=scene["aabb"])
+    pc = synth.SyntheticGaussianModel(scene, mod, sh_degree=3)
+    cam = synth.make_camera(30.0, w["width"], w["height"], radius=w["radius"], focal=w["focal"], time=0.4)
+    with torch.no_grad():
+        a = g4d.render(cam, pc, _Pipe(), torch.tensor([0.0, 0.0, 0.0], device="cuda"))
+        b = g4d.render(cam, pc, _Pipe(), torch.tensor([0.25, 0.5, 1.0], device="cuda"))
+        a2 = g4d.render(cam, pc, _Pipe(), torch.tensor([0.0, 0.0, 0.0], device="cuda"))
+    assert torch.equal(a["render"], a2["render"]) and torch.equal(a["radii"], a2["radii"])      # forward is deterministic
+    # background linearity: img(bg) - img(0) = final_T * bg
+    T0 = (b["render"][0] - a["render"][0]) / 0.25
+    for ch, v in ((1, 0.5), (2, 1.0)):
+        assert float(((b["render"][ch] - a["render"][ch]) / v - T0).abs().max()) <= 1e-5
+    assert float(T0.min()) >= -1e-6 and float(T0.max()) <= 1.0 + 1e-6
+    assert bool(torch.isfinite(a["render"]).all()) and bool(torch.isfinite(a["depth"]).all())
+    assert int((a["radii"] > 0).sum()) > 1000
+
+
+def test_full_size_binning_properties():
+    n, wh = 300_000, (1352, 1014)
+    cam = synth.make_camera(-40.0, wh[0], wh[1], radius=2.2, focal=729.0)
+    ins = [t.float().cuda() for t in raster_inputs(n, 1, scale_mean=0.01)]
+    rast = g4d.GaussianRasterizer(_settings(cam, (0, 0, 0)))
+    m3 = ins[0].clone().requires_grad_(True)
+    color, radii, depth = rast(means3D=m3, means2D=torch.zeros_like(m3), shs=ins[4], colors_precomp=None, opacities=ins[3],
+                               scales=ins[1], rotations=ins[2], cov3D_precomp=None)
+    ctx = color.grad_fn.lease.ctx
+    keys, ids, ranges = ctx.read("sorted_keys"), ctx.read("sorted_ids"), ctx.read("ranges")
+    tt, dep, rect = ctx.read("tiles_touched"), ctx.read("depth"), ctx.read("rect")
+    R = ctx.stats().num_rendered
+    assert R == int(tt.astype(np.int64).sum()) == keys.shape[0]
+    assert np.all(np.diff(keys.astype(np.uint64).view(np.int64)) >= 0)                 # sorted (keys < 2^63)
+    assert np.array_equal((keys & np.uint64(0xFFFFFFFF)).astype(np.uint32), dep[ids].view(np.uint32))
+    same = np.diff(keys.view(np.int64)) == 0
+    assert np.all(np.diff(ids.astype(np.int64))[same] > 0)                              # stable: ties by index
+    tile = (keys >> np.uint64(32)).astype(np.int64)
+    lens = (ranges[:, 1].astype(np.int64) - ranges[:, 0].astype(np.int64))
+    assert lens.sum() == R and np.array_equal(np.bincount(tile, minlength=ranges.shape[0]), lens)
+    area = (rect[:, 2] - rect[:, 0]).astype(np.int64) * (rect[:, 3] - rect[:, 1]).astype(np.int64)
+    assert np.array_equal(area, tt.astype(np.int64))
+    assert np.array_equal(radii.cpu().numpy() > 0, tt > 0)

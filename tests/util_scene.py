@@ -29,3 +29,75 @@ def cam_tuple(camera, bg, sh_degree=3, scale_modifier=1.0):
     # use the fp32-rounded tangents in the dense path too
     cd["tanfovx"] = float(np.float32(cd["tanfovx"])); cd["tanfovy"] = float(np.float32(cd["tanfovy"]))
     return rc, cd
+
+
+# ---------------------------------------------------------------------------------------------------
+# helpers for the GPU parity tests: oracle-side composition of the whole render() path
+# ---------------------------------------------------------------------------------------------------
+import importlib
+
+g4d = importlib.import_module("4dgaussians_b200")
+
+
+class OracleRaster(torch.autograd.Function):
+    """CPU autograd wrapper around the C rasterizer oracle (forward + hand-derived backward)."""
+
+    @staticmethod
+    def forward(ctx, means3D, shs, opac, scales, rots, rc):
+        from oracle import raster_ref as rr
+        arrs = [t.detach().numpy().astype(np.float32) for t in (means3D, scales, rots, opac, shs)]
+        f = rr.rasterize_forward(rc, *arrs)
+        ctx.rc, ctx.f, ctx.arrs = rc, f, arrs
+        return torch.from_numpy(f["color"].copy()), torch.from_numpy(f["depth"].copy()), torch.from_numpy(f["radii"].copy())
+
+    @staticmethod
+    def backward(ctx, g_color, _gd, _gr):
+        from oracle import raster_ref as rr
+        g = rr.rasterize_backward(ctx.rc, *ctx.arrs, ctx.f, g_color.numpy().astype(np.float32))
+        ctx.means2D_grad = g["means2D"]
+        OracleRaster.last_means2D_grad = g["means2D"]
+        return (torch.from_numpy(g["means3D"]), torch.from_numpy(g["shs"]), torch.from_numpy(g["opacities"]),
+                torch.from_numpy(g["scales"]), torch.from_numpy(g["rots"]), None)
+
+
+def oracle_params_from_module(module):
+    """DeformConfig + DeformParams (CPU fp32 leaves with requires_grad) mirroring a g4d deform_network."""
+    from oracle import deform_ref as dr
+    a = module.args
+    kc = a.kplanes_config
+    cfg = dr.DeformConfig(channels=kc["output_coordinate_dim"], resolution=tuple(kc["resolution"]), multires=tuple(a.multires),
+                          net_width=a.net_width, no_dx=a.no_dx, no_ds=a.no_ds, no_dr=a.no_dr, no_do=a.no_do, no_dshs=a.no_dshs)
+    sd = {k: v.detach().cpu().contiguous().clone() for k, v in module.state_dict().items()}
+    prm = dr.params_from_state_dict(sd, cfg.levels)
+    for t in prm.leaves():
+        t.requires_grad_(True)
+    return cfg, prm
+
+
+def oracle_render(cfg, prm, scene_cpu, camera, t, bg, sh_degree=3, stage="fine", scale_modifier=1.0):
+    """Reference composition (gaussian_renderer/__init__.py:80-128) on the oracle: deform -> activations -> rasterize.
+    scene_cpu: dict of CPU tensors (leaves may require grad).  Returns (color, depth, radii, rc)."""
+    from oracle import deform_ref as dr
+    shs = torch.cat([scene_cpu["features_dc"], scene_cpu["features_rest"]], dim=1)
+    if stage == "fine":
+        pts, sc, rot, op, sh = dr.deform_forward(cfg, prm, scene_cpu["xyz"], scene_cpu["scaling"], scene_cpu["rotation"],
+                                                 scene_cpu["opacity"], shs, float(t))
+    else:
+        pts, sc, rot, op, sh = scene_cpu["xyz"], scene_cpu["scaling"], scene_cpu["rotation"], scene_cpu["opacity"], shs
+    s, r, o = dr.activate(sc, rot, op)
+    rc, _ = cam_tuple(camera, bg, sh_degree=sh_degree, scale_modifier=scale_modifier)
+    color, depth, radii = OracleRaster.apply(pts, sh, o, s, r, rc)
+    return color, depth, radii, rc, (pts, s, r, o, sh)
+
+
+def make_module(net: str, seed: int = 0, device="cuda", aabb=None):
+    m = g4d.deform_network(synth.hidden_args(net))
+    synth.perturb_deformation(m, seed)
+    if aabb is not None:
+        m.deformation_net.set_aabb(aabb[0].tolist(), aabb[1].tolist())
+    return m.to(device)
+
+
+def rel_err(got, ref, floor=1e-3):
+    got = np.asarray(got, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
+    return float(np.abs(got - ref).max() / max(floor, np.abs(ref).max()))
