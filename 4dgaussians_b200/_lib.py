@@ -18,7 +18,8 @@ MAX_LEVELS = 4
 NUM_HEADS = 5
 HEAD_POS, HEAD_SCALES, HEAD_ROT, HEAD_OPACITY, HEAD_SHS = 1, 2, 4, 8, 16
 
-OPT_SYNC_MODE, OPT_INSTANCE_CAPACITY, OPT_TIGHT_CULL = 1, 2, 3
+OPT_SYNC_MODE, OPT_INSTANCE_CAPACITY, OPT_TIGHT_CULL, OPT_STAGE_TIMING = 1, 2, 3, 4
+STAGES = ("prep", "geom", "scan", "emit", "sort", "ranges", "blend", "blend_bwd", "geom_bwd", "deform_bwd")
 
 BUF = dict(depth=1, rect=2, tiles_touched=3, xy=4, conic_opacity=5, rgb=6, sorted_keys=7, sorted_ids=8, ranges=9,
            final_T=10, n_contrib=11, clamped=12, deformed=13)
@@ -28,6 +29,7 @@ ABI_SYMBOLS = [
     "g4d_abi_version", "g4d_last_error", "g4d_workspace_create", "g4d_workspace_destroy", "g4d_context_create",
     "g4d_context_destroy", "g4d_context_stats", "g4d_deform_forward", "g4d_deform_backward", "g4d_rasterize_forward",
     "g4d_rasterize_backward", "g4d_render_forward", "g4d_render_backward", "g4d_workspace_set_option", "g4d_context_read",
+    "g4d_context_stage_times",
 ]
 
 fp = C.c_void_p   # device pointers travel as integers
@@ -100,6 +102,7 @@ def load():
         lib.g4d_workspace_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int64]
         lib.g4d_context_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
         lib.g4d_context_read.restype = C.c_int64
+        lib.g4d_context_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
         lib.g4d_deform_forward.argtypes = [C.c_void_p, C.POINTER(DeformParams), C.c_int64] + [fp] * 5 + [C.c_float] + \
             [fp] * 5 + [C.c_void_p]
         lib.g4d_deform_backward.argtypes = [C.c_void_p, C.POINTER(DeformParams), C.POINTER(DeformGrads), C.c_int64, fp,
@@ -167,6 +170,13 @@ class Context:
         s = Stats()
         check(load().g4d_context_stats(self.handle, C.byref(s)), "g4d_context_stats")
         return s
+
+    def stage_times(self) -> Dict[str, float]:
+        arr = (C.c_float * len(STAGES))()
+        rc = load().g4d_context_stage_times(self.handle, arr, len(STAGES))
+        if rc < 0:
+            check(rc, "g4d_context_stage_times")
+        return {k: float(arr[i]) for i, k in enumerate(STAGES)}
 
     def read(self, name: str):
         """Copy an internal buffer to a numpy array (tests / debugging)."""

@@ -55,6 +55,7 @@ struct G4DWorkspace {
     int sync_mode = 1;
     int64_t min_capacity = 0;
     int tight_cull = 0;
+    int stage_timing = 0;
     // packed (transposed) MLP weights, refreshed when G4DDeformParams.version changes
     uint64_t packed_version = ~0ull;
     const void* packed_key = nullptr;
@@ -79,11 +80,33 @@ struct G4DContext {
     ImageBuffers im{};
     FusedOutputs fo{};
     float* trow_ptr[G4D_MAX_LEVELS][3] = {};
+    cudaEvent_t ev[2 * G4D_STAGE_COUNT] = {};
+    bool ev_used[G4D_STAGE_COUNT] = {};
+    bool ev_created = false;
 };
 
 namespace {
 
 size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+// RAII bracket of one stage with CUDA events on the launching stream (only when G4D_OPT_STAGE_TIMING is on)
+struct StageTimer {
+    G4DContext* c; int stage; cudaStream_t st; bool on;
+    StageTimer(G4DContext* c_, int stage_, cudaStream_t st_) : c(c_), stage(stage_), st(st_), on(c_->ws->stage_timing != 0) {
+        if (!on) return;
+        if (!c->ev_created) {
+            for (int i = 0; i < 2 * G4D_STAGE_COUNT; ++i) cudaEventCreate(&c->ev[i]);
+            c->ev_created = true;
+        }
+        cudaEventRecord(c->ev[2 * stage], st);
+    }
+    ~StageTimer() {
+        if (!on) return;
+        cudaEventRecord(c->ev[2 * stage + 1], st);
+        c->ev_used[stage] = true;
+    }
+};
+void reset_stage_flags(G4DContext* c, int first, int last) { for (int i = first; i <= last; ++i) c->ev_used[i] = false; }
 
 int ensure_geom(G4DContext* c, int64_t n) {
     const size_t N = (size_t)(n > 0 ? n : 1);
@@ -220,7 +243,10 @@ int bin_and_blend(G4DContext* c, const G4DCamera* cam, int64_t n, float* out_col
     if (n > 0) {
         const size_t tb = scan_temp_bytes(n);
         G4D_CUDA(ws->temp.ensure(tb));
-        G4D_CUDA(launch_scan(c->g.tiles_touched, c->g.offsets, n, ws->temp.p, tb, st));
+        {
+            StageTimer tm(c, G4D_STAGE_SCAN, st);
+            G4D_CUDA(launch_scan(c->g.tiles_touched, c->g.offsets, n, ws->temp.p, tb, st));
+        }
         G4D_CUDA(cudaMemcpyAsync(ws->h_pinned, c->g.offsets + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         G4D_CUDA(cudaStreamSynchronize(st));   // the one host sync of the path (as in the reference, A.2)
         R = (int64_t)ws->h_pinned[0];
@@ -232,14 +258,24 @@ int bin_and_blend(G4DContext* c, const G4DCamera* cam, int64_t n, float* out_col
     int tile_bits = 0;
     while ((1 << tile_bits) < num_tiles) ++tile_bits;
     if (R > 0) {
-        G4D_CUDA(launch_emit_keys(dcam, n, c->g, c->b, c->capacity, st));
+        {
+            StageTimer tm(c, G4D_STAGE_EMIT, st);
+            G4D_CUDA(launch_emit_keys(dcam, n, c->g, c->b, c->capacity, st));
+        }
         const size_t sb = sort_temp_bytes(R);
         G4D_CUDA(ws->temp.ensure(sb));
+        StageTimer tm(c, G4D_STAGE_SORT, st);
         G4D_CUDA(launch_sort(c->b, R, tile_bits, ws->temp.p, sb, st));
     }
-    G4D_CUDA(launch_tile_ranges(c->b, R, num_tiles, st));
+    {
+        StageTimer tm(c, G4D_STAGE_RANGES, st);
+        G4D_CUDA(launch_tile_ranges(c->b, R, num_tiles, st));
+    }
     if ((rc = debug_sync(cam, st, "binning")) != G4D_OK) return rc;
-    G4D_CUDA(launch_blend_forward(dcam, c->grid_x, c->grid_y, c->g, c->b, c->im, out_color, out_depth, st));
+    {
+        StageTimer tm(c, G4D_STAGE_BLEND, st);
+        G4D_CUDA(launch_blend_forward(dcam, c->grid_x, c->grid_y, c->g, c->b, c->im, out_color, out_depth, st));
+    }
     if ((rc = debug_sync(cam, st, "blend_forward")) != G4D_OK) return rc;
     c->n = n;
     c->has_forward = true;
@@ -259,10 +295,15 @@ int raster_backward_stages(G4DContext* c, const G4DCamera* cam, int64_t n, const
     if (n == 0) return G4D_OK;
     G4D_CUDA(cudaMemsetAsync(g_mean2D, 0, N * 8 * 4, st));
     G4D_CUDA(cudaMemsetAsync(g_opacities, 0, N * 4, st));
-    G4D_CUDA(launch_blend_backward(dcam, c->grid_x, c->grid_y, c->g, c->b, c->im, dL_dcolor, g_mean2D, g_conic, g_opacities,
-                                   g_rgb, st));
+    reset_stage_flags(c, G4D_STAGE_BLEND_BWD, G4D_STAGE_DEFORM_BWD);
+    {
+        StageTimer tm(c, G4D_STAGE_BLEND_BWD, st);
+        G4D_CUDA(launch_blend_backward(dcam, c->grid_x, c->grid_y, c->g, c->b, c->im, dL_dcolor, g_mean2D, g_conic, g_opacities,
+                                       g_rgb, st));
+    }
     int rc;
     if ((rc = debug_sync(cam, st, "blend_backward")) != G4D_OK) return rc;
+    StageTimer tm(c, G4D_STAGE_GEOM_BWD, st);
     G4D_CUDA(launch_preprocess_backward(dcam, n, in, c->g, g_mean2D, g_conic, g_rgb, g_means3D, g_means2D, g_scales,
                                         g_rotations, g_shs, g_sh_dc, g_sh_rest, st));
     return debug_sync(cam, st, "preprocess_backward");
@@ -311,6 +352,7 @@ G4DContext* g4d_context_create(G4DWorkspace* ws) {
 void g4d_context_destroy(G4DContext* c) {
     if (!c) return;
     cudaSetDevice(c->ws->device);
+    if (c->ev_created) for (int i = 0; i < 2 * G4D_STAGE_COUNT; ++i) cudaEventDestroy(c->ev[i]);
     c->cam.release(); c->geom.release(); c->bin.release(); c->img.release(); c->fused.release(); c->gscratch.release(); c->gdeform.release();
     c->trow.release();
     delete c;
@@ -322,8 +364,23 @@ int g4d_workspace_set_option(G4DWorkspace* ws, int option, int64_t value) {
         case G4D_OPT_SYNC_MODE: ws->sync_mode = value ? 1 : 0; return G4D_OK;
         case G4D_OPT_INSTANCE_CAPACITY: ws->min_capacity = value; return G4D_OK;
         case G4D_OPT_TIGHT_CULL: ws->tight_cull = value ? 1 : 0; return G4D_OK;
+        case G4D_OPT_STAGE_TIMING: ws->stage_timing = value ? 1 : 0; return G4D_OK;
         default: return fail(G4D_ERR_ARG, "unknown option");
     }
+}
+
+int g4d_context_stage_times(G4DContext* c, float* out_ms, int capacity) {
+    if (!c || !out_ms || capacity < G4D_STAGE_COUNT) return fail(G4D_ERR_ARG, "need room for G4D_STAGE_COUNT floats");
+    cudaSetDevice(c->ws->device);
+    G4D_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < G4D_STAGE_COUNT; ++i) {
+        out_ms[i] = 0.f;
+        if (c->ev_created && c->ev_used[i]) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, c->ev[2 * i], c->ev[2 * i + 1]) == cudaSuccess) out_ms[i] = ms;
+        }
+    }
+    return G4D_STAGE_COUNT;
 }
 
 int g4d_context_stats(G4DContext* c, G4DStats* out) {
@@ -379,9 +436,16 @@ int g4d_rasterize_forward(G4DContext* c, const G4DCamera* cam, int64_t n, const 
     c->has_forward = false; c->is_fused = false; c->deformed = false;
     if ((rc = ensure_geom(c, n)) != G4D_OK) return rc;
     if ((rc = ensure_image(c, cam->image_height, cam->image_width)) != G4D_OK) return rc;
-    G4D_CUDA(launch_pack_camera(*cam, c->cam.as<CameraDev>(), st));
+    reset_stage_flags(c, 0, G4D_STAGE_COUNT - 1);
+    {
+        StageTimer tm(c, G4D_STAGE_PREP, st);
+        G4D_CUDA(launch_pack_camera(*cam, c->cam.as<CameraDev>(), st));
+    }
     RasterInputs in{means3D, scales, rotations, opacities, shs, nullptr, nullptr};
-    G4D_CUDA(launch_preprocess(c->cam.as<CameraDev>(), n, in, c->g, out_radii, st));
+    {
+        StageTimer tm(c, G4D_STAGE_GEOM, st);
+        G4D_CUDA(launch_preprocess(c->cam.as<CameraDev>(), n, in, c->g, out_radii, st));
+    }
     return bin_and_blend(c, cam, n, out_color, out_depth, st);
 }
 
@@ -518,13 +582,21 @@ int g4d_render_forward(G4DContext* c, const G4DCamera* cam, const G4DDeformParam
     if ((rc = ensure_image(c, cam->image_height, cam->image_width)) != G4D_OK) return rc;
     if ((rc = ensure_fused(c, n, with_sh)) != G4D_OK) return rc;
     CameraDev* dcam = c->cam.as<CameraDev>();
-    G4D_CUDA(launch_pack_camera(*cam, dcam, st));
+    reset_stage_flags(c, 0, G4D_STAGE_COUNT - 1);
     const float* shs = g->features_rest ? nullptr : g->features_dc;
     const float* dc = g->features_rest ? g->features_dc : nullptr;
+    {
+        StageTimer tm(c, G4D_STAGE_PREP, st);
+        G4D_CUDA(launch_pack_camera(*cam, dcam, st));
+        if (prm) {
+            if ((rc = refresh_packed(ws, prm, st)) != G4D_OK) return rc;
+            if ((rc = setup_trow(c->trow, c->trow_ptr, prm)) != G4D_OK) return rc;
+            G4D_CUDA(launch_collapse_time_rows(*prm, dcam, cam->time, false, c->trow_ptr, st));
+        }
+    }
+    StageTimer* geom_tm = new StageTimer(c, G4D_STAGE_GEOM, st);
+    struct Del { StageTimer*& p; ~Del() { delete p; p = nullptr; } } del{geom_tm};
     if (prm) {
-        if ((rc = refresh_packed(ws, prm, st)) != G4D_OK) return rc;
-        if ((rc = setup_trow(c->trow, c->trow_ptr, prm)) != G4D_OK) return rc;
-        G4D_CUDA(launch_collapse_time_rows(*prm, dcam, cam->time, false, c->trow_ptr, st));
         const DeformDesc d = make_desc(ws, prm, c->trow_ptr);
         G4D_CUDA(launch_deform(d, 1, dcam, cam->time, false, n, g->xyz, g->scaling, g->rotation, g->opacity, shs, dc,
                                g->features_rest, nullptr, nullptr, nullptr, nullptr, nullptr, c->g, c->fo, out_radii,
@@ -533,6 +605,7 @@ int g4d_render_forward(G4DContext* c, const G4DCamera* cam, const G4DDeformParam
         G4D_CUDA(launch_activate_preprocess(dcam, n, g->xyz, g->scaling, g->rotation, g->opacity, shs, dc, g->features_rest,
                                             c->g, c->fo, out_radii, st));
     }
+    delete geom_tm; geom_tm = nullptr;
     if ((rc = debug_sync(cam, st, "deform+preprocess")) != G4D_OK) return rc;
     rc = bin_and_blend(c, cam, n, out_color, out_depth, st);
     if (rc != G4D_OK) return rc;
@@ -594,7 +667,10 @@ int g4d_render_backward(G4DContext* c, const G4DCamera* cam, const G4DDeformPara
     G4D_CUDA(ws->scratch.ensure(deform_backward_scratch_bytes(d, n)));
     const float* go[G4D_NUM_HEADS] = {gd_xyz, gd_sc, gd_rot, gd_op, gd_sh};
     float* gi[G4D_NUM_HEADS] = {gg->xyz, gg->scaling, gg->rotation, gg->opacity, nullptr};
-    G4D_CUDA(launch_deform_backward(d, *prm, *pgrads, cam->time, n, g->xyz, go, gi, ws->scratch.as<float>(), ws->sm_count, st));
+    {
+        StageTimer tm(c, G4D_STAGE_DEFORM_BWD, st);
+        G4D_CUDA(launch_deform_backward(d, *prm, *pgrads, cam->time, n, g->xyz, go, gi, ws->scratch.as<float>(), ws->sm_count, st));
+    }
     return debug_sync(cam, st, "deform_backward");
 }
 

@@ -26,6 +26,8 @@ import torch.nn.init as init
 
 from . import _lib
 
+_VERSION_COUNTER = itertools.count(1)   # process-global: a fresh module can never reuse a (version, pointer) pair
+
 _HEADS = ("pos_deform", "scales_deform", "rotations_deform", "opacity_deform", "shs_deform")
 _HEAD_OUT = (3, 3, 4, 1, 48)
 
@@ -181,7 +183,7 @@ class deform_network(nn.Module):
         sig = tuple((p.data_ptr(), p._version) for p in self.flat_parameters())
         if sig != self._version_seen:
             self._version_seen = sig
-            self._param_version += 1
+            self._param_version = next(_VERSION_COUNTER)
         return self._param_version
 
     def c_params(self, keep: list) -> _lib.DeformParams:

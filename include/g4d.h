@@ -165,8 +165,10 @@ enum { G4D_OPT_SYNC_MODE = 1,  /* 1 (default): size the instance buffer exactly 
                                   forward, like the reference); 0: no host sync, capacity-bounded, overflow
                                   reported by the NEXT call on the context / g4d_context_stats */
        G4D_OPT_INSTANCE_CAPACITY = 2, /* minimum instance capacity for no-sync mode */
-       G4D_OPT_TIGHT_CULL = 3  /* 0 (default): reference tile rects; 1: drop (Gaussian,tile) pairs that
-                                  provably contribute nothing (images identical, fewer instances) */ };
+       G4D_OPT_TIGHT_CULL = 3, /* 0 (default): reference tile rects; 1: drop (Gaussian,tile) pairs that
+                                  provably contribute nothing (images identical, fewer instances) */
+       G4D_OPT_STAGE_TIMING = 4 /* 1: bracket every stage with CUDA events on the launching stream
+                                   (bench.py's live per-kernel durations); 0 (default): off */ };
 int g4d_workspace_set_option(G4DWorkspace *ws, int option, int64_t value);
 
 /* copy an internal per-forward buffer to HOST memory (tests / debugging; synchronises).
@@ -185,6 +187,17 @@ enum { G4D_BUF_DEPTH = 1,      /* float  [N]  view-space depth                  
        G4D_BUF_CLAMPED = 12,   /* uint8  [N,3]                                    */
        G4D_BUF_DEFORMED = 13   /* float  [N,11] (xyz, scale, rot, opacity) post-activation, fused path */ };
 int64_t g4d_context_read(G4DContext *ctx, int which, void *host_dst, int64_t bytes);
+
+/* per-stage device time (ms) of the LAST forward / backward on this context, measured with CUDA events on the
+ * launching stream (needs G4D_OPT_STAGE_TIMING = 1; synchronises).  out_ms[G4D_STAGE_COUNT]; stages that did
+ * not run hold 0.  Returns G4D_STAGE_COUNT or an error. */
+enum { G4D_STAGE_PREP = 0,        /* camera pack, weight pack, time-row collapse            */
+       G4D_STAGE_GEOM = 1,        /* deform+activate+project (fused) or preprocess           */
+       G4D_STAGE_SCAN = 2, G4D_STAGE_EMIT = 3, G4D_STAGE_SORT = 4, G4D_STAGE_RANGES = 5,
+       G4D_STAGE_BLEND = 6,
+       G4D_STAGE_BLEND_BWD = 7, G4D_STAGE_GEOM_BWD = 8, G4D_STAGE_DEFORM_BWD = 9,
+       G4D_STAGE_COUNT = 10 };
+int g4d_context_stage_times(G4DContext *ctx, float *out_ms, int capacity);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,68 @@
+"""world_size-2 gloo test of the data-parallel host logic (FlatGradBucket, view sharding, stats reduction)."""
+import importlib
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+dp = importlib.import_module("4dgaussians_b200.dp")
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    plane = torch.nn.Parameter(torch.rand(1, 4, 5, 3).contiguous(memory_format=torch.channels_last))
+    w = torch.nn.Parameter(torch.rand(6, 4))
+    xyz = torch.nn.Parameter(torch.rand(7, 3))
+    bucket = dp.FlatGradBucket([xyz, plane, w])
+    assert plane.grad.shape == plane.shape and plane.grad.stride() == plane.stride()
+    views = dp.shard_views(6, rank, world)
+    bucket.zero_()
+    for v in views:      # "loss" of view v: (v+1) * sum of every parameter, mean over the global batch
+        loss = (v + 1) * (xyz.sum() + 2 * plane.sum() + 3 * w.sum()) / len(views)
+        loss.backward()
+    flat_ptr = bucket.flat.data_ptr()
+    bucket.allreduce_mean(dist, world)
+    assert bucket.flat.data_ptr() == flat_ptr and xyz.grad.data_ptr() == flat_ptr     # grads are still views of the bucket
+    gn = torch.full((7, 1), float(rank + 1)); den = torch.full((7, 1), 1.0); rad = torch.arange(7, dtype=torch.float32) * (rank + 1)
+    dp.allreduce_densification_stats(dist, world, gn, den, rad)
+    q.put((rank, views, xyz.grad.clone(), plane.grad.clone(), w.grad.clone(), gn.clone(), den.clone(), rad.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_flat_bucket_allreduce_two_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=90) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(30)
+        assert p.exitcode == 0
+    (r0, v0, gx0, gp0, gw0, gn0, den0, rad0), (r1, v1, gx1, gp1, gw1, gn1, den1, rad1) = res
+    assert v0 == [0, 2, 4] and v1 == [1, 3, 5]
+    # mean over the 6 views of (v+1) = 3.5
+    assert torch.allclose(gx0, torch.full((7, 3), 3.5)) and torch.equal(gx0, gx1)
+    assert torch.allclose(gp0, torch.full((1, 4, 5, 3), 7.0)) and torch.allclose(gw1, torch.full((6, 4), 10.5))
+    assert torch.allclose(gn0, torch.full((7, 1), 3.0)) and torch.allclose(den1, torch.full((7, 1), 2.0))
+    assert torch.equal(rad0, torch.arange(7, dtype=torch.float32) * 2) and torch.equal(rad0, rad1)
+
+
+def test_single_rank_is_identity():
+    p = torch.nn.Parameter(torch.ones(3, 2))
+    b = dp.FlatGradBucket([p])
+    (p * 2).sum().backward()
+    b.allreduce_mean(None, 1)
+    assert torch.equal(p.grad, torch.full((3, 2), 2.0)) and dp.shard_views(5, 0, 1) == [0, 1, 2, 3, 4]

@@ -1,0 +1,60 @@
+"""Tiny driver for ncu: a few fused fwd(+bwd) steps of a BASELINE workload through the public render() API.
+    ncu ... python tools/profile_step.py --workload C3 --iters 2 --backward 1
+Never a bench number (it runs under a profiler)."""
+import argparse
+import importlib
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+class Pipe:
+    convert_SHs_python = False
+    compute_cov3D_python = False
+    debug = False
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="C3")
+    ap.add_argument("--iters", type=int, default=2)
+    ap.add_argument("--backward", type=int, default=1)
+    ap.add_argument("--stage-times", type=int, default=0)
+    a = ap.parse_args()
+    g4d = importlib.import_module("4dgaussians_b200")
+    synth = importlib.import_module("4dgaussians_b200.synth")
+    w = synth.WORKLOADS[a.workload]
+    scene = synth.make_scene(w["n"], seed=0, scale_mean=w["scale_mean"])
+    mod = g4d.deform_network(synth.hidden_args(w["net"]))
+    synth.perturb_deformation(mod, 0)
+    mod.deformation_net.set_aabb(scene["aabb"][0].tolist(), scene["aabb"][1].tolist())
+    mod = mod.cuda()
+    pc = synth.SyntheticGaussianModel(scene, mod, sh_degree=3, requires_grad=bool(a.backward))
+    cams = synth.orbit_cameras(8, w["width"], w["height"], radius=w["radius"], focal=w["focal"], timestamps=300)
+    bg = torch.tensor(w["bg"], dtype=torch.float32, device="cuda")
+    target = torch.rand(3, w["height"], w["width"], device="cuda")
+    ws = g4d._lib.Workspace.get(0)
+    if a.stage_times:
+        ws.set_option(g4d._lib.OPT_STAGE_TIMING, 1)
+    for i in range(a.iters):
+        cam = cams[i % len(cams)]
+        if a.backward:
+            out = g4d.render(cam, pc, Pipe, bg)
+            (out["render"] - target).abs().mean().backward()
+        else:
+            with torch.no_grad():
+                out = g4d.render(cam, pc, Pipe, bg)
+        torch.cuda.synchronize()
+        if a.stage_times and ws._free_contexts:
+            c = ws._free_contexts[-1]
+            s = c.stats()
+            print("iter", i, "R=%d visible=%d" % (s.num_rendered, s.num_visible),
+                  {k: round(v, 4) for k, v in c.stage_times().items()}, flush=True)
+
+
+if __name__ == "__main__":
+    main()
