@@ -244,7 +244,7 @@ def run_ours(args):
             "stage_ms": stages, "train_step": train, "wall_s_timed_region": t_wall,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference_arm(steps=1, warmup=0, quiet=True)["cpu_baseline"]
+            line["cpu_baseline"] = cpu_reference_arm(steps=1, warmup=1, quiet=True)["cpu_baseline"]
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -305,7 +305,8 @@ def cpu_reference_arm(steps: int, warmup: int, quiet: bool = False):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from util_scene import cam_tuple, oracle_params_from_module
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    torch.set_num_threads(min(cores, 32))     # the element-wise CPU kernels stop scaling (and start thrashing) beyond that
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     cfg, prm = oracle_params_from_module(mod)
     for t_ in prm.leaves():
         t_.requires_grad_(False)
@@ -318,7 +319,7 @@ def cpu_reference_arm(steps: int, warmup: int, quiet: bool = False):
     cams = synth.orbit_cameras(max(8, steps + warmup), w["width"], w["height"], radius=w["radius"], focal=w["focal"], timestamps=300)
     shs = torch.cat([scene["features_dc"], scene["features_rest"]], dim=1)
     n = w["n"]
-    times = []
+    times, t_def, t_ras = [], [], []
     rr.lib()
     for i in range(steps + warmup):
         cam = cams[i % len(cams)]
@@ -331,15 +332,17 @@ def cpu_reference_arm(steps: int, warmup: int, quiet: bool = False):
                 pts, sc, rot, op, sh = dr.deform_forward(cfg, prm, scene["xyz"], scene["scaling"], scene["rotation"],
                                                          scene["opacity"], shs, cam.time)
             s, r, o = dr.activate(sc, rot, op)
+        t1 = time.perf_counter()
         rc, _ = cam_tuple(cam, w["bg"], sh_degree=3)
         rr.rasterize_forward(rc, pts.numpy(), s.numpy(), r.numpy(), o.numpy(), sh.numpy())
         dt = time.perf_counter() - t0
         if i >= warmup:
-            times.append(dt)
+            times.append(dt); t_def.append(t1 - t0); t_ras.append(dt - (t1 - t0))
     ms = 1e3 * float(np.mean(times))
     fps = 1e3 / ms
     cb = {"value": fps, "unit": UNIT, "cores": cores, "kind": kind,
-          "sample": "%d full C3 view(s) (300k Gaussians, 1352x1014): PyTorch-CPU deformation + OpenMP C rasterizer oracle, forward" % len(times)}
+          "sample": "%d full C3 view(s) (300k Gaussians, 1352x1014): PyTorch-CPU deformation (%.2f s/view) + OpenMP C rasterizer "
+                    "oracle (%.2f s/view), forward" % (len(times), float(np.mean(t_def)), float(np.mean(t_ras)))}
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": "C3: 300k Gaussians, 1352x1014, dynerf net, host CPU, %d threads" % cores},
