@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "g4d_abi_version", "g4d_last_error", "g4d_workspace_create", "g4d_workspace_destroy", "g4d_context_create",
     "g4d_context_destroy", "g4d_context_stats", "g4d_deform_forward", "g4d_deform_backward", "g4d_rasterize_forward",
     "g4d_rasterize_backward", "g4d_render_forward", "g4d_render_backward", "g4d_workspace_set_option", "g4d_context_read",
-    "g4d_context_stage_times",
+    "g4d_context_stage_times", "g4d_debug_umma",
 ]
 
 fp = C.c_void_p   # device pointers travel as integers
@@ -103,6 +103,7 @@ def load():
         lib.g4d_context_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
         lib.g4d_context_read.restype = C.c_int64
         lib.g4d_context_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
+        lib.g4d_debug_umma.argtypes = [C.c_void_p, C.POINTER(C.c_int), fp, fp, fp, C.c_void_p]
         lib.g4d_deform_forward.argtypes = [C.c_void_p, C.POINTER(DeformParams), C.c_int64] + [fp] * 5 + [C.c_float] + \
             [fp] * 5 + [C.c_void_p]
         lib.g4d_deform_backward.argtypes = [C.c_void_p, C.POINTER(DeformParams), C.POINTER(DeformGrads), C.c_int64, fp,

@@ -25,6 +25,7 @@ UNITS = {
     "g4d_raster.cu": [],
     "g4d_backward.cu": [],
     "g4d_api.cu": [],
+    "g4d_tc_selftest.cu": [],
 }
 
 

@@ -674,4 +674,13 @@ int g4d_render_backward(G4DContext* c, const G4DCamera* cam, const G4DDeformPara
     return debug_sync(cam, st, "deform_backward");
 }
 
+int g4d_debug_umma(G4DWorkspace* ws, const int* cfg, const float* A, const float* B, float* D, void* stream) {
+    if (!ws || !cfg || !A || !B || !D) return fail(G4D_ERR_ARG, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    G4D_CUDA(cudaSetDevice(ws->device));
+    G4D_CUDA(ws->scratch.ensure((size_t)2 * 128 * 128 * 4 + 256));
+    G4D_CUDA(launch_umma_selftest(cfg, A, B, ws->scratch.as<float>(), D, st));
+    return G4D_OK;
+}
+
 }  // extern "C"

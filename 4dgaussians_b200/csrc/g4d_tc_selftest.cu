@@ -1,0 +1,137 @@
+// g4d_tc_selftest.cu -- single-CTA self test of the tcgen05 building blocks in tc_umma.cuh:
+//   D[128 x N] = A[128 x K] * B[N x K]^T   with 3xTF32, A through TMEM, B through shared memory.
+// The layout / descriptor hypotheses are runtime parameters so that one GPU session can tell which encoding the
+// hardware accepts (there is no GPU in the build container).  Debug entry point g4d_debug_umma (include/g4d.h).
+#include "g4d_internal.h"
+#include "tc_umma.cuh"
+
+namespace g4d {
+
+struct UmmaTestCfg {
+    int N, K;
+    int layout_mode;   // 0: K cores contiguous (LBO=128, SBO=(K/4)*128); 1: 8-row groups contiguous (SBO=128, LBO=(N/8)*128)
+    int swap_desc;     // 1: put LBO in the SBO field and vice versa
+    int a_cols_per_k;  // TMEM columns the A operand advances per element of K (1 for 32-bit types)
+    int use_tma;       // 1: B arrives pre-packed (hi | lo) in global memory and is staged with cp.async.bulk
+    int single_pass;   // 1: plain TF32 (hi*hi only)
+    int version_bit;   // descriptor version field (1 on sm_100)
+};
+
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(UmmaTestCfg c, const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ Bpacked,
+                     float* __restrict__ D) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(8) uint64_t bar_mma, bar_tma;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t N = c.N, K = c.K;
+    uint8_t* b_hi = smem_raw;
+    uint8_t* b_lo = smem_raw + N * K * 4;
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, tc::kTmemCols);
+    if (tid == 0) { mbar_init(&bar_mma, 1); mbar_init(&bar_tma, 1); fence_barrier_init(); }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = tmem_base_s;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t lbo = c.layout_mode == 0 ? 128u : (N >> 3) * 128u;
+    const uint32_t sbo = c.layout_mode == 0 ? (K >> 2) * 128u : 128u;
+    // ---- B -> shared memory (canonical layout), hi and lo parts
+    if (c.use_tma) {
+        if (tid == 0) {
+            mbar_expect_tx(&bar_tma, 2 * N * K * 4);
+            tma_bulk_g2s(b_hi, Bpacked, N * K * 4, &bar_tma);
+            tma_bulk_g2s(b_lo, Bpacked + N * K, N * K * 4, &bar_tma);
+        }
+        mbar_wait(&bar_tma, 0);
+    } else {
+        for (uint32_t i = tid; i < N * K; i += blockDim.x) {
+            const uint32_t n = i / K, k = i % K;
+            uint32_t hi, lo;
+            tc::tf32_split(B[i], hi, lo);
+            const uint32_t off = (n >> 3) * sbo + (k >> 2) * lbo + (n & 7) * 16 + (k & 3) * 4;
+            *reinterpret_cast<uint32_t*>(b_hi + off) = hi;
+            *reinterpret_cast<uint32_t*>(b_lo + off) = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
+    }
+    // ---- A -> TMEM: thread r owns lane r; hi at columns [0, K*cpk), lo right after
+    {
+        const int r = tid;
+        const uint32_t cpk = c.a_cols_per_k;
+        for (uint32_t k0 = 0; k0 < K; k0 += 8) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tc::tf32_split(A[r * K + k0 + j], hi[j], lo[j]);
+            tc::tmem_st8(tbase + lane_base + k0 * cpk, hi);
+            tc::tmem_st8(tbase + lane_base + K * cpk + k0 * cpk, lo);
+        }
+        tc::wait_st();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t d_col = 256;
+    if (tid == 0) {
+        const uint32_t idesc = tc::make_idesc_tf32(128, N);
+        bool acc = false;
+        const int passes = c.single_pass ? 1 : 3;
+        for (int p = 0; p < passes; ++p) {
+            const uint32_t a = tbase + ((c.single_pass || p != 0) ? 0u : K * c.a_cols_per_k);
+            const uint8_t* b = (!c.single_pass && p == 1) ? b_lo : b_hi;
+            for (uint32_t ks = 0; ks < K; ks += 8) {
+                const uint32_t saddr = tc::smem_addr(b) + (ks >> 2) * lbo;
+                uint64_t bd = c.swap_desc ? tc::make_smem_desc(saddr, sbo, lbo) : tc::make_smem_desc(saddr, lbo, sbo);
+                if (!c.version_bit) bd &= ~(1ull << 46);
+                tc::umma_tf32_ts(tbase + d_col, a + ks * c.a_cols_per_k, bd, idesc, acc);
+                acc = true;
+            }
+        }
+        tc::umma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, 0);
+    tc::fence_after_sync();
+    {
+        const int r = tid;
+        for (uint32_t n0 = 0; n0 < N; n0 += 8) {
+            uint32_t v[8];
+            tc::tmem_ld8(tbase + lane_base + d_col + n0, v);
+            tc::wait_ld();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) D[r * N + n0 + j] = __uint_as_float(v[j]);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, tc::kTmemCols);
+}
+
+// pack an [N][K] fp32 matrix into (hi | lo) canonical tf32 images (layout_mode 0)
+__global__ void pack_canonical_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int K) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * K) return;
+    const uint32_t n = i / K, k = i % K;
+    uint32_t hi, lo;
+    tc::tf32_split(src[i], hi, lo);
+    const uint32_t off = tc::canon_off(n, k, K) >> 2;
+    reinterpret_cast<uint32_t*>(dst)[off] = hi;
+    reinterpret_cast<uint32_t*>(dst)[N * K + off] = lo;
+}
+
+cudaError_t launch_umma_selftest(const int cfg[8], const float* A, const float* B, float* scratch_packed, float* D, cudaStream_t st) {
+    UmmaTestCfg c{cfg[0], cfg[1], cfg[2], cfg[3], cfg[4], cfg[5], cfg[6], cfg[7]};
+    if (c.N < 16 || c.N > 128 || (c.N % 16) || c.K < 8 || c.K > 128 || (c.K % 8) || c.a_cols_per_k < 1 || c.a_cols_per_k > 2)
+        return cudaErrorInvalidValue;
+    if (c.use_tma) {
+        pack_canonical_kernel<<<(c.N * c.K + 255) / 256, 256, 0, st>>>(B, scratch_packed, c.N, c.K);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    const size_t smem = (size_t)2 * c.N * c.K * 4 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    umma_selftest_kernel<<<1, 128, smem, st>>>(c, A, B, scratch_packed, D);
+    return cudaGetLastError();
+}
+
+}  // namespace g4d

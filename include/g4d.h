@@ -199,6 +199,11 @@ enum { G4D_STAGE_PREP = 0,        /* camera pack, weight pack, time-row collapse
        G4D_STAGE_COUNT = 10 };
 int g4d_context_stage_times(G4DContext *ctx, float *out_ms, int capacity);
 
+/* DEBUG: single-CTA self test of the tcgen05 building blocks: D[128,N] = A[128,K] * B[N,K]^T (3xTF32, A through TMEM,
+ * B through shared memory).  cfg = {N, K, layout_mode, swap_desc, a_cols_per_k, use_tma, single_pass, version_bit}.
+ * A, B, D are device fp32; not on any product path. */
+int g4d_debug_umma(G4DWorkspace *ws, const int *cfg, const float *A, const float *B, float *D, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
