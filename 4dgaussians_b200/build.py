@@ -26,6 +26,7 @@ UNITS = {
     "g4d_backward.cu": [],
     "g4d_api.cu": [],
     "g4d_tc_selftest.cu": [],
+    "g4d_deform_tc.cu": ["-fmad=false"],
 }
 
 

@@ -56,6 +56,11 @@ struct G4DWorkspace {
     int64_t min_capacity = 0;
     int tight_cull = 0;
     int stage_timing = 0;
+    int tensor_cores = 1;
+    DevBuf tc_packed;
+    TcWeights tcw{};
+    uint64_t tc_version = ~0ull;
+    const void* tc_key = nullptr;
     // packed (transposed) MLP weights, refreshed when G4DDeformParams.version changes
     uint64_t packed_version = ~0ull;
     const void* packed_key = nullptr;
@@ -189,6 +194,16 @@ int refresh_packed(G4DWorkspace* ws, const G4DDeformParams* p, cudaStream_t st) 
     G4D_CUDA(launch_pack_weights(*p, ws->w0t, ws->w1t, st));
     ws->packed_version = p->version;
     ws->packed_key = (const void*)p->w0;
+    return G4D_OK;
+}
+
+// tensor-core weight images, same caching rule as refresh_packed
+int refresh_tc(G4DWorkspace* ws, const G4DDeformParams* p, cudaStream_t st) {
+    if (ws->tc_version == p->version && ws->tc_key == (const void*)p->w0 && ws->tc_packed.p) return G4D_OK;
+    G4D_CUDA(ws->tc_packed.ensure(tc_packed_floats(*p) * 4));
+    G4D_CUDA(launch_tc_pack_weights(*p, ws->tc_packed.as<float>(), &ws->tcw, st));
+    ws->tc_version = p->version;
+    ws->tc_key = (const void*)p->w0;
     return G4D_OK;
 }
 
@@ -335,7 +350,7 @@ G4DWorkspace* g4d_workspace_create(int device) {
 void g4d_workspace_destroy(G4DWorkspace* ws) {
     if (!ws) return;
     cudaSetDevice(ws->device);
-    ws->packed.release(); ws->trow.release(); ws->temp.release(); ws->scratch.release();
+    ws->packed.release(); ws->tc_packed.release(); ws->trow.release(); ws->temp.release(); ws->scratch.release();
     if (ws->h_pinned) cudaFreeHost(ws->h_pinned);
     delete ws;
 }
@@ -365,6 +380,7 @@ int g4d_workspace_set_option(G4DWorkspace* ws, int option, int64_t value) {
         case G4D_OPT_INSTANCE_CAPACITY: ws->min_capacity = value; return G4D_OK;
         case G4D_OPT_TIGHT_CULL: ws->tight_cull = value ? 1 : 0; return G4D_OK;
         case G4D_OPT_STAGE_TIMING: ws->stage_timing = value ? 1 : 0; return G4D_OK;
+        case G4D_OPT_TENSOR_CORES: ws->tensor_cores = value ? 1 : 0; return G4D_OK;
         default: return fail(G4D_ERR_ARG, "unknown option");
     }
 }
@@ -415,8 +431,11 @@ int g4d_deform_forward(G4DWorkspace* ws, const G4DDeformParams* prm, int64_t n, 
     const DeformDesc d = make_desc(ws, prm, trow);
     GeomBuffers g{};
     FusedOutputs fo{};
+    const bool use_tc = ws->tensor_cores && tc_deform_supported(d);
+    if (use_tc && (rc = refresh_tc(ws, prm, st)) != G4D_OK) return rc;
     G4D_CUDA(launch_deform(d, 0, nullptr, time, false, n, xyz, scaling, rotation, opacity, shs, nullptr, nullptr, out_xyz,
-                           out_scaling, out_rotation, out_opacity, out_shs, g, fo, nullptr, ws->sm_count, st));
+                           out_scaling, out_rotation, out_opacity, out_shs, g, fo, nullptr, ws->sm_count, st,
+                           use_tc ? &ws->tcw : nullptr));
     return G4D_OK;
 }
 
@@ -598,9 +617,11 @@ int g4d_render_forward(G4DContext* c, const G4DCamera* cam, const G4DDeformParam
     struct Del { StageTimer*& p; ~Del() { delete p; p = nullptr; } } del{geom_tm};
     if (prm) {
         const DeformDesc d = make_desc(ws, prm, c->trow_ptr);
+        const bool use_tc = ws->tensor_cores && tc_deform_supported(d);
+        if (use_tc && (rc = refresh_tc(ws, prm, st)) != G4D_OK) return rc;
         G4D_CUDA(launch_deform(d, 1, dcam, cam->time, false, n, g->xyz, g->scaling, g->rotation, g->opacity, shs, dc,
                                g->features_rest, nullptr, nullptr, nullptr, nullptr, nullptr, c->g, c->fo, out_radii,
-                               ws->sm_count, st));
+                               ws->sm_count, st, use_tc ? &ws->tcw : nullptr));
     } else {
         G4D_CUDA(launch_activate_preprocess(dcam, n, g->xyz, g->scaling, g->rotation, g->opacity, shs, dc, g->features_rest,
                                             c->g, c->fo, out_radii, st));

@@ -7,8 +7,7 @@
 //
 // Reference path replaced: /root/reference/gaussian_renderer/__init__.py:52 (time tensor), :87-89 (deform),
 // :97-99 (activations) and the preprocess stage inside the rasterizer called at :120.
-#include "g4d_internal.h"
-#include "g4d_math.cuh"
+#include "geom_finish.cuh"
 
 namespace g4d {
 
@@ -120,18 +119,6 @@ cudaError_t launch_collapse_time_rows(const G4DDeformParams& p, const CameraDev*
 }
 
 // ------------------------------------------------------------------------------------------------------
-G4D_D void store_projected(const GeomBuffers& g, int64_t gi, bool ok, const Projected& pr, float opacity, const float rgb[3],
-                           uint32_t bits, int32_t* out_radii) {
-    g.rec0[gi] = make_float4(pr.px, pr.py, pr.conx, pr.cony);
-    g.rec1[gi] = make_float4(pr.conz, ok ? opacity : 0.f, rgb[0], rgb[1]);
-    g.rec2[gi] = make_float2(rgb[2], pr.depth);
-    g.radii[gi] = pr.radius;
-    if (out_radii) out_radii[gi] = pr.radius;
-    g.rect[gi] = make_uint2((uint32_t)pr.rminx | ((uint32_t)pr.rminy << 16), (uint32_t)pr.rmaxx | ((uint32_t)pr.rmaxy << 16));
-    g.tiles_touched[gi] = pr.tiles;
-    g.clamped[gi] = (uint8_t)bits;
-}
-
 // Standalone preprocess: one thread per Gaussian, inputs are post-activation (A.1).
 __global__ void __launch_bounds__(256) preprocess_kernel(const CameraDev* __restrict__ camp, int64_t n, RasterInputs in,
                                                          GeomBuffers g, int32_t* out_radii) {
@@ -169,14 +156,6 @@ cudaError_t launch_preprocess(const CameraDev* cam, int64_t n, const RasterInput
 }
 
 // ------------------------------------------------------------------------------------------------------
-struct DeformIO {
-    const float *xyz, *scaling, *rotation, *opacity, *shs, *sh_dc, *sh_rest;
-    float *out_xyz, *out_scaling, *out_rotation, *out_opacity, *out_shs;
-    GeomBuffers g;
-    FusedOutputs fo;
-    int32_t* out_radii;
-};
-
 // Persistent kernel: one CTA per SM, each looping over tiles of TG Gaussians.
 //   MODE 0: deformation network only (drop-in for deform_network.forward; outputs pre-activation tensors)
 //   MODE 1: fused deformation + activations + projection (the render() hot path)
@@ -286,41 +265,16 @@ deform_kernel(DeformDesc d, DeformSmem L, const CameraDev* __restrict__ camp, fl
                 if (hs) { sl[0] += o[3]; sl[1] += o[4]; sl[2] += o[5]; }
                 if (hr) { q[0] += o[6]; q[1] += o[7]; q[2] += o[8]; q[3] += o[9]; }
                 if (ho) ol += o[10];
-                // activations (gaussian_renderer/__init__.py:97-99): exp, F.normalize(eps=1e-12), sigmoid
-                const Vec3 sc{expf(sl[0]), expf(sl[1]), expf(sl[2])};
-                const float qn = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
-                const Quat rq{q[0] / qn, q[1] / qn, q[2] / qn, q[3] / qn};
-                const float op = 1.f / (1.f + expf(-ol));
-                Projected pr;
-                const bool ok = project_gaussian(cam, p, sc, rq, pr);
-                float rgb[3] = {0.f, 0.f, 0.f};
-                uint32_t bits = 0;
-                if (ok) {
-                    const float* dsh = o + 11;
-                    if (io.shs) {
-                        const float* sh = io.shs + gi * 48;
-                        sh_to_rgb(cam, p, [&](int k, int ch) { return __ldg(sh + 3 * k + ch) + (hsh ? dsh[3 * k + ch] : 0.f); }, rgb, bits);
-                    } else {
-                        const float* dc = io.sh_dc + gi * 3;
-                        const float* rest = io.sh_rest + gi * 45;
-                        sh_to_rgb(cam, p, [&](int k, int ch) {
-                            return (k == 0 ? __ldg(dc + ch) : __ldg(rest + 3 * (k - 1) + ch)) + (hsh ? dsh[3 * k + ch] : 0.f);
-                        }, rgb, bits);
-                    }
-                }
-                store_projected(io.g, gi, ok, pr, op, rgb, bits, io.out_radii);
-                if (io.fo.means3D) {
-                    io.fo.means3D[3 * gi] = p.x; io.fo.means3D[3 * gi + 1] = p.y; io.fo.means3D[3 * gi + 2] = p.z;
-                    io.fo.scales[3 * gi] = sc.x; io.fo.scales[3 * gi + 1] = sc.y; io.fo.scales[3 * gi + 2] = sc.z;
-                    *reinterpret_cast<float4*>(io.fo.rotations + 4 * gi) = make_float4(rq.r, rq.x, rq.y, rq.z);
-                    io.fo.opacities[gi] = op;
-                    if (io.fo.rot_norm) io.fo.rot_norm[gi] = qn;
-                }
+                const float* dsh = o + 11;
+                fused_finish(cam, io, gi, p, sl, q, ol, [&](int i) { return hsh ? dsh[i] : 0.f; });
             }
         }
         __syncthreads();
     }
 }
+
+cudaError_t launch_deform_tc(const DeformDesc& d, const TcWeights& tw, int mode, const CameraDev* cam, float time,
+                             bool use_cam_time, int64_t n, const DeformIO& io, int sm_count, cudaStream_t st);
 
 template <int TG, int WD, int MODE>
 static cudaError_t launch_deform_t(const DeformDesc& d, const CameraDev* cam, float time, bool use_cam_time, int64_t n,
@@ -340,10 +294,11 @@ cudaError_t launch_deform(const DeformDesc& d, int mode, const CameraDev* cam, f
                           const float* xyz, const float* scaling, const float* rotation, const float* opacity,
                           const float* shs, const float* sh_dc, const float* sh_rest, float* out_xyz, float* out_scaling,
                           float* out_rotation, float* out_opacity, float* out_shs, GeomBuffers g, FusedOutputs fo,
-                          int32_t* out_radii, int sm_count, cudaStream_t st) {
+                          int32_t* out_radii, int sm_count, cudaStream_t st, const TcWeights* tw) {
     if (n == 0) return cudaSuccess;
     DeformIO io{xyz, scaling, rotation, opacity, shs, sh_dc, sh_rest, out_xyz, out_scaling, out_rotation, out_opacity,
                 out_shs, g, fo, out_radii};
+    if (tw) return launch_deform_tc(d, *tw, mode, cam, time, use_cam_time, n, io, sm_count, st);
     if (d.WD == 128) {
         return mode == 0 ? launch_deform_t<64, 128, 0>(d, cam, time, use_cam_time, n, io, sm_count, st)
                          : launch_deform_t<64, 128, 1>(d, cam, time, use_cam_time, n, io, sm_count, st);

@@ -46,6 +46,18 @@ struct FusedOutputs {   // what the fused forward saves for its backward (may be
     float* rot_norm;   // |q| before F.normalize (needed by its backward)
 };
 
+// tensor-core weight images (g4d_deform_tc.cu): (hi | lo) TF32 parts in the canonical K-major smem layout
+struct TcWeights {
+    const float* w0;                   // packed (hi | lo), [128][F] canonical
+    const float* w1[G4D_NUM_HEADS];    // packed (hi | lo), [128][128]
+    const float* w2[G4D_NUM_HEADS];    // packed (hi | lo), [kp16][128]
+    int kp16[G4D_NUM_HEADS];
+};
+
+size_t tc_packed_floats(const G4DDeformParams& prm);
+cudaError_t launch_tc_pack_weights(const G4DDeformParams& prm, float* blob, TcWeights* out, cudaStream_t st);
+bool tc_deform_supported(const DeformDesc& d);
+
 // ---- launchers (defined in g4d_geom.cu / g4d_raster.cu / g4d_backward.cu) -----------------------------
 cudaError_t launch_pack_camera(const G4DCamera& cam, CameraDev* dst, cudaStream_t st);
 cudaError_t launch_pack_weights(const G4DDeformParams& p, float* w0t, float* const* w1t, cudaStream_t st);
@@ -58,7 +70,7 @@ cudaError_t launch_deform(const DeformDesc& d, int mode, const CameraDev* cam, f
                           const float* xyz, const float* scaling, const float* rotation, const float* opacity,
                           const float* shs, const float* sh_dc, const float* sh_rest, float* out_xyz, float* out_scaling,
                           float* out_rotation, float* out_opacity, float* out_shs, GeomBuffers g, FusedOutputs fo,
-                          int32_t* out_radii, int sm_count, cudaStream_t st);
+                          int32_t* out_radii, int sm_count, cudaStream_t st, const TcWeights* tw = nullptr);
 
 size_t scan_temp_bytes(int64_t n);
 size_t sort_temp_bytes(int64_t r);

@@ -1,0 +1,65 @@
+// geom_finish.cuh -- the per-Gaussian tail of the fused forward, shared by the SIMT and the tensor-core kernels:
+// activations (gaussian_renderer/__init__.py:97-99) -> projection (A.1) -> SH colour -> record + saved tensors.
+// Included only by translation units compiled with -fmad=false (see g4d_math.cuh).
+#pragma once
+#include "g4d_internal.h"
+#include "g4d_math.cuh"
+
+namespace g4d {
+
+struct DeformIO {
+    const float *xyz, *scaling, *rotation, *opacity, *shs, *sh_dc, *sh_rest;
+    float *out_xyz, *out_scaling, *out_rotation, *out_opacity, *out_shs;
+    GeomBuffers g;
+    FusedOutputs fo;
+    int32_t* out_radii;
+};
+
+G4D_D void store_projected(const GeomBuffers& g, int64_t gi, bool ok, const Projected& pr, float opacity, const float rgb[3],
+                           uint32_t bits, int32_t* out_radii) {
+    g.rec0[gi] = make_float4(pr.px, pr.py, pr.conx, pr.cony);
+    g.rec1[gi] = make_float4(pr.conz, ok ? opacity : 0.f, rgb[0], rgb[1]);
+    g.rec2[gi] = make_float2(rgb[2], pr.depth);
+    g.radii[gi] = pr.radius;
+    if (out_radii) out_radii[gi] = pr.radius;
+    g.rect[gi] = make_uint2((uint32_t)pr.rminx | ((uint32_t)pr.rminy << 16), (uint32_t)pr.rmaxx | ((uint32_t)pr.rmaxy << 16));
+    g.tiles_touched[gi] = pr.tiles;
+    g.clamped[gi] = (uint8_t)bits;
+}
+
+// p, sl (log-scale), q (raw quaternion), ol (opacity logit) already include the network's deltas.
+// ShDelta: float operator()(int flat_index in [0,48)) -> delta of SH coefficient (0 when the SHS head is inactive).
+template <class ShDelta>
+G4D_D void fused_finish(const CameraDev& cam, const DeformIO& io, int64_t gi, Vec3 p, const float sl[3], const float q[4], float ol,
+                        ShDelta dsh) {
+    const Vec3 sc{expf(sl[0]), expf(sl[1]), expf(sl[2])};
+    const float qn = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-12f);
+    const Quat rq{q[0] / qn, q[1] / qn, q[2] / qn, q[3] / qn};
+    const float op = 1.f / (1.f + expf(-ol));
+    Projected pr;
+    const bool ok = project_gaussian(cam, p, sc, rq, pr);
+    float rgb[3] = {0.f, 0.f, 0.f};
+    uint32_t bits = 0;
+    if (ok) {
+        if (io.shs) {
+            const float* sh = io.shs + gi * 48;
+            sh_to_rgb(cam, p, [&](int k, int ch) { return __ldg(sh + 3 * k + ch) + dsh(3 * k + ch); }, rgb, bits);
+        } else {
+            const float* dc = io.sh_dc + gi * 3;
+            const float* rest = io.sh_rest + gi * 45;
+            sh_to_rgb(cam, p, [&](int k, int ch) {
+                return (k == 0 ? __ldg(dc + ch) : __ldg(rest + 3 * (k - 1) + ch)) + dsh(3 * k + ch);
+            }, rgb, bits);
+        }
+    }
+    store_projected(io.g, gi, ok, pr, op, rgb, bits, io.out_radii);
+    if (io.fo.means3D) {
+        io.fo.means3D[3 * gi] = p.x; io.fo.means3D[3 * gi + 1] = p.y; io.fo.means3D[3 * gi + 2] = p.z;
+        io.fo.scales[3 * gi] = sc.x; io.fo.scales[3 * gi + 1] = sc.y; io.fo.scales[3 * gi + 2] = sc.z;
+        *reinterpret_cast<float4*>(io.fo.rotations + 4 * gi) = make_float4(rq.r, rq.x, rq.y, rq.z);
+        io.fo.opacities[gi] = op;
+        if (io.fo.rot_norm) io.fo.rot_norm[gi] = qn;
+    }
+}
+
+}  // namespace g4d

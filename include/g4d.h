@@ -167,8 +167,10 @@ enum { G4D_OPT_SYNC_MODE = 1,  /* 1 (default): size the instance buffer exactly 
        G4D_OPT_INSTANCE_CAPACITY = 2, /* minimum instance capacity for no-sync mode */
        G4D_OPT_TIGHT_CULL = 3, /* 0 (default): reference tile rects; 1: drop (Gaussian,tile) pairs that
                                   provably contribute nothing (images identical, fewer instances) */
-       G4D_OPT_STAGE_TIMING = 4 /* 1: bracket every stage with CUDA events on the launching stream
-                                   (bench.py's live per-kernel durations); 0 (default): off */ };
+       G4D_OPT_STAGE_TIMING = 4, /* 1: bracket every stage with CUDA events on the launching stream
+                                   (bench.py's live per-kernel durations); 0 (default): off */
+       G4D_OPT_TENSOR_CORES = 5  /* 1 (default): run the deformation MLP on tcgen05 tensor cores (3xTF32) when the
+                                   configuration allows (net_width 128, C in {16,32}, F <= 64); 0: FP32 FFMA kernels */ };
 int g4d_workspace_set_option(G4DWorkspace *ws, int option, int64_t value);
 
 /* copy an internal per-forward buffer to HOST memory (tests / debugging; synchronises).

@@ -343,3 +343,38 @@ def test_full_size_binning_properties():
     area = (rect[:, 2] - rect[:, 0]).astype(np.int64) * (rect[:, 3] - rect[:, 1]).astype(np.int64)
     assert np.array_equal(area, tt.astype(np.int64))
     assert np.array_equal(radii.cpu().numpy() > 0, tt > 0)
+
+
+# --------------------------------------------------------------------------------------------------- tensor cores
+def test_tcgen05_building_blocks_selftest():
+    """D[128,N] = A[128,K] B[N,K]^T through TMEM / tcgen05.mma kind::tf32 with 3xTF32: fp32-level accuracy."""
+    import ctypes as C
+    lib = g4d._lib.load()
+    ws = g4d._lib.Workspace.get(0)
+    for (N, K, tma) in ((128, 128, 1), (128, 32, 1), (48, 64, 0), (16, 64, 1)):
+        gen = torch.Generator().manual_seed(N + K)
+        A = torch.randn(128, K, generator=gen).cuda(); B = torch.randn(N, K, generator=gen).cuda()
+        D = torch.zeros(128, N, device="cuda")
+        cfg = (C.c_int * 8)(N, K, 0, 0, 1, tma, 0, 1)
+        g4d._lib.check(lib.g4d_debug_umma(ws.handle, cfg, A.data_ptr(), B.data_ptr(), D.data_ptr(), 0), "g4d_debug_umma")
+        ref = A.double() @ B.double().t()
+        assert float((D.double() - ref).abs().max() / ref.abs().max()) <= 2e-6, (N, K)
+
+
+@pytest.mark.parametrize("net,n", [("small128", 1000), ("dynerf", 5000), ("hypernerf", 3000)])
+def test_tensor_core_mlp_matches_ffma_path(net, n):
+    """The tcgen05 (3xTF32) MLP and the FP32 FFMA MLP are two implementations of the same function."""
+    mod = make_module(net, seed=7)
+    ins, _ = _deform_inputs(n, 9)
+    ws = g4d._lib.Workspace.get(0)
+    t = torch.tensor(0.42).repeat(n, 1).cuda()
+    try:
+        with torch.no_grad():
+            ws.set_option(g4d._lib.OPT_TENSOR_CORES, 1)
+            a = [o.clone() for o in mod(*ins, t)]
+            ws.set_option(g4d._lib.OPT_TENSOR_CORES, 0)
+            b = [o.clone() for o in mod(*ins, t)]
+    finally:
+        ws.set_option(g4d._lib.OPT_TENSOR_CORES, 1)
+    for x, y, nm in zip(a, b, ("pts", "scales", "rot", "opacity", "shs")):
+        assert float((x - y).abs().max()) <= 5e-6, (nm, float((x - y).abs().max()))
