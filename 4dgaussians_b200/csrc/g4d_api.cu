@@ -260,6 +260,7 @@ int bin_and_blend(G4DContext* c, const G4DCamera* cam, int64_t n, float* out_col
         G4D_CUDA(ws->temp.ensure(tb));
         {
             StageTimer tm(c, G4D_STAGE_SCAN, st);
+            if (ws->tight_cull) G4D_CUDA(launch_cull_count(n, c->g, st));
             G4D_CUDA(launch_scan(c->g.tiles_touched, c->g.offsets, n, ws->temp.p, tb, st));
         }
         G4D_CUDA(cudaMemcpyAsync(ws->h_pinned, c->g.offsets + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -275,7 +276,7 @@ int bin_and_blend(G4DContext* c, const G4DCamera* cam, int64_t n, float* out_col
     if (R > 0) {
         {
             StageTimer tm(c, G4D_STAGE_EMIT, st);
-            G4D_CUDA(launch_emit_keys(dcam, n, c->g, c->b, c->capacity, st));
+            G4D_CUDA(launch_emit_keys(dcam, n, c->g, c->b, c->capacity, ws->tight_cull, st));
         }
         const size_t sb = sort_temp_bytes(R);
         G4D_CUDA(ws->temp.ensure(sb));

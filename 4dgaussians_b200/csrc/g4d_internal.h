@@ -75,7 +75,9 @@ cudaError_t launch_deform(const DeformDesc& d, int mode, const CameraDev* cam, f
 size_t scan_temp_bytes(int64_t n);
 size_t sort_temp_bytes(int64_t r);
 cudaError_t launch_scan(const uint32_t* in, uint32_t* out, int64_t n, void* temp, size_t temp_bytes, cudaStream_t st);
-cudaError_t launch_emit_keys(const CameraDev* cam, int64_t n, GeomBuffers g, BinBuffers b, int64_t capacity, cudaStream_t st);
+cudaError_t launch_cull_count(int64_t n, GeomBuffers g, cudaStream_t st);
+cudaError_t launch_emit_keys(const CameraDev* cam, int64_t n, GeomBuffers g, BinBuffers b, int64_t capacity, int tight,
+                             cudaStream_t st);
 cudaError_t launch_sort(BinBuffers b, int64_t r, int tile_bits, void* temp, size_t temp_bytes, cudaStream_t st);
 cudaError_t launch_tile_ranges(BinBuffers b, int64_t r, int num_tiles, cudaStream_t st);
 cudaError_t launch_blend_forward(const CameraDev* cam, int grid_x, int grid_y, GeomBuffers g, BinBuffers b, ImageBuffers im,

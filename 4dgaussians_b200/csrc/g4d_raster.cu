@@ -24,9 +24,55 @@ cudaError_t launch_scan(const uint32_t* in, uint32_t* out, int64_t n, void* temp
     return cub::DeviceScan::InclusiveSum(temp, temp_bytes, in, out, (int)n, st);
 }
 
+// ---- exact-image tile culling (G4D_OPT_TIGHT_CULL) -------------------------------------------------------------
+// A (Gaussian, tile) pair can be dropped without changing a single pixel when even the best-placed point of the
+// tile's pixel rectangle has alpha = opacity * exp(-q/2) < 1/255 (the blend stage skips such contributions, A.3).
+// q is a convex quadratic, so its minimum over the rectangle is 0 (centre inside) or lies on one of the 4 edges.
+// The 1e-4 margin covers the different rounding of the per-pixel evaluation in the blend kernel.
+G4D_D float edge_min(float a, float b, float c, float fixed, float lo, float hi) {
+    // min over t in [lo,hi] of a*fixed^2 + 2*b*fixed*t + c*t^2
+    float t = -b * fixed / c;
+    t = fminf(fmaxf(t, lo), hi);
+    return a * fixed * fixed + 2.f * b * fixed * t + c * t * t;
+}
+G4D_D bool tile_contributes(float4 r0, float4 r1, int tx, int ty) {
+    const float A = r0.z, B = r0.w, C = r1.x, op = r1.y;
+    const float dx0 = r0.x - (float)(tx * kTile + kTile - 1), dx1 = r0.x - (float)(tx * kTile);
+    const float dy0 = r0.y - (float)(ty * kTile + kTile - 1), dy1 = r0.y - (float)(ty * kTile);
+    float qmin;
+    if (dx0 <= 0.f && dx1 >= 0.f && dy0 <= 0.f && dy1 >= 0.f) qmin = 0.f;
+    else {
+        qmin = fminf(fminf(edge_min(A, B, C, dx0, dy0, dy1), edge_min(A, B, C, dx1, dy0, dy1)),
+                     fminf(edge_min(C, B, A, dy0, dx0, dx1), edge_min(C, B, A, dy1, dx0, dx1)));
+        qmin = fmaxf(qmin, 0.f);
+    }
+    return op * __expf(-0.5f * qmin) * 1.0001f >= kAlphaMin;
+}
+
+// tight mode: tiles_touched := number of tiles of the rect that can contribute (same predicate as emit_keys_kernel,
+// same translation unit, hence bit-identical decisions)
+__global__ void __launch_bounds__(256) cull_count_kernel(int64_t n, GeomBuffers g) {
+    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= n) return;
+    if (g.tiles_touched[gi] == 0) return;
+    const uint2 rc = g.rect[gi];
+    const int minx = rc.x & 0xFFFF, miny = rc.x >> 16, maxx = rc.y & 0xFFFF, maxy = rc.y >> 16;
+    const float4 r0 = g.rec0[gi], r1 = g.rec1[gi];
+    uint32_t cnt = 0;
+    for (int y = miny; y < maxy; ++y)
+        for (int x = minx; x < maxx; ++x) cnt += tile_contributes(r0, r1, x, y) ? 1u : 0u;
+    g.tiles_touched[gi] = cnt;
+}
+
+cudaError_t launch_cull_count(int64_t n, GeomBuffers g, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    cull_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, g);
+    return cudaGetLastError();
+}
+
 // A.2: one (tile | depth bits) key and the Gaussian index per touched tile, at consecutive slots from offsets[i-1]
 __global__ void __launch_bounds__(256) emit_keys_kernel(const CameraDev* __restrict__ cam, int64_t n, GeomBuffers g,
-                                                        BinBuffers b, int64_t capacity) {
+                                                        BinBuffers b, int64_t capacity, int tight) {
     const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gi >= n) return;
     if (g.tiles_touched[gi] == 0) return;
@@ -35,8 +81,11 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(const CameraDev* __restr
     const int minx = rc.x & 0xFFFF, miny = rc.x >> 16, maxx = rc.y & 0xFFFF, maxy = rc.y >> 16;
     const uint32_t dbits = __float_as_uint(g.rec2[gi].y);
     const int gx = cam->grid_x;
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+    if (tight) { r0 = g.rec0[gi]; r1 = g.rec1[gi]; }
     for (int y = miny; y < maxy; ++y)
         for (int x = minx; x < maxx; ++x) {
+            if (tight && !tile_contributes(r0, r1, x, y)) continue;
             if (off < capacity) {
                 b.keys_unsorted[off] = ((uint64_t)(uint32_t)(y * gx + x) << 32) | dbits;
                 b.ids_unsorted[off] = (uint32_t)gi;
@@ -45,9 +94,10 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(const CameraDev* __restr
         }
 }
 
-cudaError_t launch_emit_keys(const CameraDev* cam, int64_t n, GeomBuffers g, BinBuffers b, int64_t capacity, cudaStream_t st) {
+cudaError_t launch_emit_keys(const CameraDev* cam, int64_t n, GeomBuffers g, BinBuffers b, int64_t capacity, int tight,
+                             cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    emit_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cam, n, g, b, capacity);
+    emit_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cam, n, g, b, capacity, tight);
     return cudaGetLastError();
 }
 

@@ -378,3 +378,31 @@ def test_tensor_core_mlp_matches_ffma_path(net, n):
         ws.set_option(g4d._lib.OPT_TENSOR_CORES, 1)
     for x, y, nm in zip(a, b, ("pts", "scales", "rot", "opacity", "shs")):
         assert float((x - y).abs().max()) <= 5e-6, (nm, float((x - y).abs().max()))
+
+
+def test_tight_cull_gives_bit_identical_images_with_fewer_instances():
+    """G4D_OPT_TIGHT_CULL drops (Gaussian, tile) pairs whose best alpha over the tile is < 1/255: same pixels, smaller R."""
+    cam = synth.make_camera(35.0, 640, 480, radius=2.2, focal=400.0)
+    ins = [t.float().cuda() for t in raster_inputs(40_000, 5, scale_mean=0.02)]
+    rast = g4d.GaussianRasterizer(_settings(cam, (0.1, 0.2, 0.3)))
+    ws = g4d._lib.Workspace.get(0)
+
+    def run():
+        m3 = ins[0].clone().requires_grad_(True)
+        sc = ins[1].clone().requires_grad_(True)
+        color, radii, depth = rast(means3D=m3, means2D=torch.zeros_like(m3), shs=ins[4], colors_precomp=None, opacities=ins[3],
+                                   scales=sc, rotations=ins[2], cov3D_precomp=None)
+        R = color.grad_fn.lease.ctx.stats().num_rendered
+        color.backward(torch.ones_like(color))
+        return color.detach().clone(), radii.clone(), depth.clone(), R, m3.grad.clone(), sc.grad.clone()
+    try:
+        ws.set_option(g4d._lib.OPT_TIGHT_CULL, 0)
+        a = run()
+        ws.set_option(g4d._lib.OPT_TIGHT_CULL, 1)
+        b = run()
+    finally:
+        ws.set_option(g4d._lib.OPT_TIGHT_CULL, 0)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    assert b[3] < 0.9 * a[3], (a[3], b[3])
+    for x, y in ((a[4], b[4]), (a[5], b[5])):
+        assert float((x - y).abs().max()) <= 1e-4 * max(1e-3, float(x.abs().max()))
