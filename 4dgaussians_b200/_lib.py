@@ -18,7 +18,7 @@ MAX_LEVELS = 4
 NUM_HEADS = 5
 HEAD_POS, HEAD_SCALES, HEAD_ROT, HEAD_OPACITY, HEAD_SHS = 1, 2, 4, 8, 16
 
-OPT_SYNC_MODE, OPT_INSTANCE_CAPACITY, OPT_TIGHT_CULL, OPT_STAGE_TIMING, OPT_TENSOR_CORES = 1, 2, 3, 4, 5
+OPT_SYNC_MODE, OPT_INSTANCE_CAPACITY, OPT_TIGHT_CULL, OPT_STAGE_TIMING, OPT_TENSOR_CORES, OPT_TC_DEBUG = 1, 2, 3, 4, 5, 6
 STAGES = ("prep", "geom", "scan", "emit", "sort", "ranges", "blend", "blend_bwd", "geom_bwd", "deform_bwd")
 
 BUF = dict(depth=1, rect=2, tiles_touched=3, xy=4, conic_opacity=5, rgb=6, sorted_keys=7, sorted_ids=8, ranges=9,
@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "g4d_abi_version", "g4d_last_error", "g4d_workspace_create", "g4d_workspace_destroy", "g4d_context_create",
     "g4d_context_destroy", "g4d_context_stats", "g4d_deform_forward", "g4d_deform_backward", "g4d_rasterize_forward",
     "g4d_rasterize_backward", "g4d_render_forward", "g4d_render_backward", "g4d_workspace_set_option", "g4d_context_read",
-    "g4d_context_stage_times", "g4d_debug_umma",
+    "g4d_context_stage_times", "g4d_debug_umma", "g4d_debug_tc_cycles",
 ]
 
 fp = C.c_void_p   # device pointers travel as integers
@@ -104,6 +104,7 @@ def load():
         lib.g4d_context_read.restype = C.c_int64
         lib.g4d_context_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
         lib.g4d_debug_umma.argtypes = [C.c_void_p, C.POINTER(C.c_int), fp, fp, fp, C.c_void_p]
+        lib.g4d_debug_tc_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         lib.g4d_deform_forward.argtypes = [C.c_void_p, C.POINTER(DeformParams), C.c_int64] + [fp] * 5 + [C.c_float] + \
             [fp] * 5 + [C.c_void_p]
         lib.g4d_deform_backward.argtypes = [C.c_void_p, C.POINTER(DeformParams), C.POINTER(DeformGrads), C.c_int64, fp,

@@ -61,6 +61,8 @@ struct G4DWorkspace {
     TcWeights tcw{};
     uint64_t tc_version = ~0ull;
     const void* tc_key = nullptr;
+    DevBuf tc_dbg;
+    int tc_debug = 0;
     // packed (transposed) MLP weights, refreshed when G4DDeformParams.version changes
     uint64_t packed_version = ~0ull;
     const void* packed_key = nullptr;
@@ -204,6 +206,15 @@ int refresh_tc(G4DWorkspace* ws, const G4DDeformParams* p, cudaStream_t st) {
     G4D_CUDA(launch_tc_pack_weights(*p, ws->tc_packed.as<float>(), &ws->tcw, st));
     ws->tc_version = p->version;
     ws->tc_key = (const void*)p->w0;
+    return G4D_OK;
+}
+
+int attach_tc_debug(G4DWorkspace* ws, cudaStream_t st) {
+    ws->tcw.dbg = nullptr;
+    if (!ws->tc_debug) return G4D_OK;
+    G4D_CUDA(ws->tc_dbg.ensure((size_t)ws->sm_count * 12 * 8));
+    G4D_CUDA(cudaMemsetAsync(ws->tc_dbg.p, 0, (size_t)ws->sm_count * 12 * 8, st));
+    ws->tcw.dbg = ws->tc_dbg.as<long long>();
     return G4D_OK;
 }
 
@@ -382,6 +393,7 @@ int g4d_workspace_set_option(G4DWorkspace* ws, int option, int64_t value) {
         case G4D_OPT_TIGHT_CULL: ws->tight_cull = value ? 1 : 0; return G4D_OK;
         case G4D_OPT_STAGE_TIMING: ws->stage_timing = value ? 1 : 0; return G4D_OK;
         case G4D_OPT_TENSOR_CORES: ws->tensor_cores = value ? 1 : 0; return G4D_OK;
+        case G4D_OPT_TC_DEBUG: ws->tc_debug = value ? 1 : 0; return G4D_OK;
         default: return fail(G4D_ERR_ARG, "unknown option");
     }
 }
@@ -434,6 +446,7 @@ int g4d_deform_forward(G4DWorkspace* ws, const G4DDeformParams* prm, int64_t n, 
     FusedOutputs fo{};
     const bool use_tc = ws->tensor_cores && tc_deform_supported(d);
     if (use_tc && (rc = refresh_tc(ws, prm, st)) != G4D_OK) return rc;
+    if (use_tc && (rc = attach_tc_debug(ws, st)) != G4D_OK) return rc;
     G4D_CUDA(launch_deform(d, 0, nullptr, time, false, n, xyz, scaling, rotation, opacity, shs, nullptr, nullptr, out_xyz,
                            out_scaling, out_rotation, out_opacity, out_shs, g, fo, nullptr, ws->sm_count, st,
                            use_tc ? &ws->tcw : nullptr));
@@ -620,6 +633,7 @@ int g4d_render_forward(G4DContext* c, const G4DCamera* cam, const G4DDeformParam
         const DeformDesc d = make_desc(ws, prm, c->trow_ptr);
         const bool use_tc = ws->tensor_cores && tc_deform_supported(d);
         if (use_tc && (rc = refresh_tc(ws, prm, st)) != G4D_OK) return rc;
+        if (use_tc && (rc = attach_tc_debug(ws, st)) != G4D_OK) return rc;
         G4D_CUDA(launch_deform(d, 1, dcam, cam->time, false, n, g->xyz, g->scaling, g->rotation, g->opacity, shs, dc,
                                g->features_rest, nullptr, nullptr, nullptr, nullptr, nullptr, c->g, c->fo, out_radii,
                                ws->sm_count, st, use_tc ? &ws->tcw : nullptr));
@@ -702,6 +716,19 @@ int g4d_debug_umma(G4DWorkspace* ws, const int* cfg, const float* A, const float
     G4D_CUDA(cudaSetDevice(ws->device));
     G4D_CUDA(ws->scratch.ensure((size_t)2 * 128 * 128 * 4 + 256));
     G4D_CUDA(launch_umma_selftest(cfg, A, B, ws->scratch.as<float>(), D, st));
+    return G4D_OK;
+}
+
+int g4d_debug_tc_cycles(G4DWorkspace* ws, double* out12) {
+    if (!ws || !out12) return fail(G4D_ERR_ARG, "NULL argument");
+    G4D_CUDA(cudaSetDevice(ws->device));
+    G4D_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < 12; ++i) out12[i] = 0.0;
+    if (!ws->tc_dbg.p) return G4D_OK;
+    std::vector<long long> h((size_t)ws->sm_count * 12);
+    G4D_CUDA(cudaMemcpy(h.data(), ws->tc_dbg.p, h.size() * 8, cudaMemcpyDeviceToHost));
+    for (int c = 0; c < ws->sm_count; ++c)
+        for (int i = 0; i < 12; ++i) out12[i] += (double)h[(size_t)c * 12 + i] / ws->sm_count;
     return G4D_OK;
 }
 

@@ -23,16 +23,17 @@ namespace g4d {
 
 constexpr uint32_t kColA1Hi = 0, kColA1Lo = 128, kColD = 256, kColX = 384, kColXLo = 448;
 
-struct TcSmem { uint32_t w1, w2, w0, bias, bars, total; };
+struct TcSmem { uint32_t w1, w2, w0, bias, w2s, bars, total; };
 
 inline TcSmem tc_smem_layout(int F, int max_kp16) {
     TcSmem s{};
     uint32_t off = 0;
     auto take = [&](uint32_t bytes) { uint32_t o = off; off += (bytes + 127u) & ~127u; return o; };
     s.w1 = take(2u * 128 * 128 * 4);
-    s.w2 = take(2u * max_kp16 * 128 * 4);
+    s.w2 = take(max_kp16 == 48 ? 2u * 48 * 128 * 4 : 128u);
     s.w0 = take(2u * 128 * F * 4);
     s.bias = take((128 + G4D_NUM_HEADS * 128 + 64) * 4);
+    s.w2s = take(4 * 128 * 16);
     s.bars = take(64);
     s.total = off;
     return s;
@@ -102,44 +103,59 @@ cudaError_t launch_tc_pack_weights(const G4DDeformParams& prm, float* blob, TcWe
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
+__device__ __forceinline__ int b2off_of(int mask, int h) {
+    int o = 0;
+    for (int i = 0; i < h; ++i)
+        if (mask & (1 << i)) o += head_out(i);
+    return o;
+}
+
 constexpr int kBarFeat = 1, kBarXFree = 2, kBarScratch = 3, kBarScratchFree = 4, kBarM = 5;
 constexpr uint32_t kColScratch = kColA1Hi;   // p(3) + dsh(48) handed from M to G after the last head (A1 is dead then)
 
+// One channel vector (4 channels) of one level: product over the 6 planes of the bilinear samples.
+__device__ __forceinline__ float4 sample_vector(const DeformDesc* __restrict__ dp, int l, int v, int C4, float px, float py, float pz) {
+    const DeformDesc& d = *dp;   // lives in shared memory (a by-reference kernel parameter would be spilled to the stack)
+    const float pcs[3] = {px, py, pz};
+    Tap1D tx[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) tx[a] = make_tap(pcs[a], d.res[l][a]);
+    float4 prod = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const int c0 = plane_axis0(k), c1 = plane_axis1(k);
+        float4 s;
+        if (c1 == 3) {
+            const float4* rowp = reinterpret_cast<const float4*>(d.trow[l][c0]);
+            const float4 r0 = __ldg(rowp + tx[c0].i0 * C4 + v), r1 = __ldg(rowp + tx[c0].i1 * C4 + v);
+            const float w0 = tx[c0].w0, w1 = tx[c0].w1;
+            s.x = fmaf(r1.x, w1, r0.x * w0); s.y = fmaf(r1.y, w1, r0.y * w0);
+            s.z = fmaf(r1.z, w1, r0.z * w0); s.w = fmaf(r1.w, w1, r0.w * w0);
+        } else {
+            const int W = d.res[l][c0];
+            const float4* pl = reinterpret_cast<const float4*>(d.planes[l][k]);
+            const Tap1D &X = tx[c0], &Y = tx[c1];
+            const float4 nw = __ldg(pl + (Y.i0 * W + X.i0) * C4 + v), ne = __ldg(pl + (Y.i0 * W + X.i1) * C4 + v);
+            const float4 sw = __ldg(pl + (Y.i1 * W + X.i0) * C4 + v), se = __ldg(pl + (Y.i1 * W + X.i1) * C4 + v);
+            const float wnw = X.w0 * Y.w0, wne = X.w1 * Y.w0, wsw = X.w0 * Y.w1, wse = X.w1 * Y.w1;
+            s.x = fmaf(se.x, wse, fmaf(sw.x, wsw, fmaf(ne.x, wne, nw.x * wnw)));
+            s.y = fmaf(se.y, wse, fmaf(sw.y, wsw, fmaf(ne.y, wne, nw.y * wnw)));
+            s.z = fmaf(se.z, wse, fmaf(sw.z, wsw, fmaf(ne.z, wne, nw.z * wnw)));
+            s.w = fmaf(se.w, wse, fmaf(sw.w, wsw, fmaf(ne.w, wne, nw.w * wnw)));
+        }
+        prod.x *= s.x; prod.y *= s.y; prod.z *= s.z; prod.w *= s.w;
+    }
+    return prod;
+}
+
 template <int C, int L>
-__device__ __forceinline__ void sample_features_regs(const DeformDesc& d, const float pcs[3], float (&feat)[C * L]) {
+__device__ __forceinline__ void sample_features_regs(const DeformDesc* d, const float pcs[3], float (&feat)[C * L]) {
     constexpr int C4 = C / 4;
 #pragma unroll
     for (int l = 0; l < L; ++l) {
-        Tap1D tx[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) tx[a] = make_tap(pcs[a], d.res[l][a]);
 #pragma unroll
         for (int v = 0; v < C4; ++v) {
-            float4 prod = make_float4(1.f, 1.f, 1.f, 1.f);
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const int c0 = plane_axis0(k), c1 = plane_axis1(k);
-                float4 s;
-                if (c1 == 3) {
-                    const float4* rowp = reinterpret_cast<const float4*>(d.trow[l][c0]);
-                    const float4 r0 = __ldg(rowp + tx[c0].i0 * C4 + v), r1 = __ldg(rowp + tx[c0].i1 * C4 + v);
-                    const float w0 = tx[c0].w0, w1 = tx[c0].w1;
-                    s.x = fmaf(r1.x, w1, r0.x * w0); s.y = fmaf(r1.y, w1, r0.y * w0);
-                    s.z = fmaf(r1.z, w1, r0.z * w0); s.w = fmaf(r1.w, w1, r0.w * w0);
-                } else {
-                    const int W = d.res[l][c0];
-                    const float4* pl = reinterpret_cast<const float4*>(d.planes[l][k]);
-                    const Tap1D &X = tx[c0], &Y = tx[c1];
-                    const float4 nw = __ldg(pl + (Y.i0 * W + X.i0) * C4 + v), ne = __ldg(pl + (Y.i0 * W + X.i1) * C4 + v);
-                    const float4 sw = __ldg(pl + (Y.i1 * W + X.i0) * C4 + v), se = __ldg(pl + (Y.i1 * W + X.i1) * C4 + v);
-                    const float wnw = X.w0 * Y.w0, wne = X.w1 * Y.w0, wsw = X.w0 * Y.w1, wse = X.w1 * Y.w1;
-                    s.x = fmaf(se.x, wse, fmaf(sw.x, wsw, fmaf(ne.x, wne, nw.x * wnw)));
-                    s.y = fmaf(se.y, wse, fmaf(sw.y, wsw, fmaf(ne.y, wne, nw.y * wnw)));
-                    s.z = fmaf(se.z, wse, fmaf(sw.z, wsw, fmaf(ne.z, wne, nw.z * wnw)));
-                    s.w = fmaf(se.w, wse, fmaf(sw.w, wsw, fmaf(ne.w, wne, nw.w * wnw)));
-                }
-                prod.x *= s.x; prod.y *= s.y; prod.z *= s.z; prod.w *= s.w;
-            }
+            const float4 prod = sample_vector(d, l, v, C4, pcs[0], pcs[1], pcs[2]);
             feat[l * C + 4 * v + 0] = prod.x; feat[l * C + 4 * v + 1] = prod.y;
             feat[l * C + 4 * v + 2] = prod.z; feat[l * C + 4 * v + 3] = prod.w;
         }
@@ -153,18 +169,24 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
     constexpr int F = C * L;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ CameraDev cam;
+    __shared__ DeformDesc sd;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int row = tid & 127;
-    const bool is_m = tid < 128;
+    for (int i = tid; i < (int)(sizeof(DeformDesc) / 4); i += 256)
+        reinterpret_cast<uint32_t*>(&sd)[i] = reinterpret_cast<const uint32_t*>(&d)[i];
+    // the hardware scheduler favours the higher warp ids of an SM sub-partition: the latency-critical M group takes them
+    const bool is_m = tid >= 128;
+    const bool issuer = tid == 128;
     const int64_t ntiles = (n + 127) / 128;
     if (MODE == 1 || use_cam_time) {
         for (int i = tid; i < (int)(sizeof(CameraDev) / 4); i += 256)
             reinterpret_cast<uint32_t*>(&cam)[i] = reinterpret_cast<const uint32_t*>(camp)[i];
     }
     float* sBias = reinterpret_cast<float*>(smem + Ls.bias);     // b0[128] | b1[5][128] | b2[64]
+    float4* sW2s = reinterpret_cast<float4*>(smem + Ls.w2s);     // [4 small heads][128 hidden]: (W2[0][j], W2[1][j], W2[2][j], W2[3][j])
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Ls.bars);
-    uint64_t *bar_w0 = bars, *bar_w1 = bars + 1, *bar_w2 = bars + 2, *bar_mma = bars + 3;
+    uint64_t *bar_w0 = bars, *bar_w1 = bars + 1, *bar_mma = bars + 3;
     int b2off[G4D_NUM_HEADS];
     {
         int o = 0;
@@ -176,10 +198,16 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
         if (!(d.head_mask & (1 << h))) continue;
         for (int i = tid; i < 128; i += 256) sBias[128 + h * 128 + i] = __ldg(d.b1[h] + i);
         for (int i = tid; i < head_out(h); i += 256) sBias[128 + G4D_NUM_HEADS * 128 + b2off[h] + i] = __ldg(d.b2[h] + i);
+        if (h < 4) {
+            const int ko = head_out(h);
+            for (int j = tid; j < 128; j += 256)
+                sW2s[h * 128 + j] = make_float4(__ldg(d.w2[h] + j), ko > 1 ? __ldg(d.w2[h] + 128 + j) : 0.f,
+                                               ko > 2 ? __ldg(d.w2[h] + 256 + j) : 0.f, ko > 3 ? __ldg(d.w2[h] + 384 + j) : 0.f);
+        }
     }
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, tc::kTmemCols);
     if (tid == 0) {
-        mbar_init(bar_w0, 1); mbar_init(bar_w1, 1); mbar_init(bar_w2, 1); mbar_init(bar_mma, 1);
+        mbar_init(bar_w0, 1); mbar_init(bar_w1, 1); mbar_init(bar_mma, 1);
         fence_barrier_init();
     }
     tc::fence_before_sync();
@@ -196,23 +224,26 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
 
     if (is_m) {
         // =========================================== M group ===========================================
-        if (tid == 0) {
-            mbar_expect_tx(bar_w0, 2u * 128 * F * 4);
+        if (issuer) {
+            // resident operands: W0 and (when active) the SH head's W2 image
+            const uint32_t w2b = hsh ? 2u * 48 * 128 * 4 : 0u;
+            mbar_expect_tx(bar_w0, 2u * 128 * F * 4 + w2b);
             tma_bulk_g2s(smem + Ls.w0, tw.w0, 2u * 128 * F * 4, bar_w0);
+            if (hsh) tma_bulk_g2s(smem + Ls.w2, tw.w2[4], w2b, bar_w0);
             if (d.head_mask) {
                 const int h0 = __ffs(d.head_mask) - 1;
                 mbar_expect_tx(bar_w1, 2u * 65536);
                 tma_bulk_g2s(smem + Ls.w1, tw.w1[h0], 65536, bar_w1);
                 tma_bulk_g2s(smem + Ls.w1 + 65536, tw.w1[h0] + 16384, 65536, bar_w1);
-                const uint32_t w2b = (uint32_t)tw.kp16[h0] * 128 * 4;
-                mbar_expect_tx(bar_w2, 2u * w2b);
-                tma_bulk_g2s(smem + Ls.w2, tw.w2[h0], w2b, bar_w2);
-                tma_bulk_g2s(smem + Ls.w2 + w2b, tw.w2[h0] + tw.kp16[h0] * 128, w2b, bar_w2);
             }
         }
         mbar_wait(bar_w0, 0);
-        uint32_t ph_w1 = 0, ph_w2 = 0, ph_mma = 0;
+        uint32_t ph_w1 = 0, ph_mma = 0;
         bool first = true;
+        // optional per-phase cycle accounting (issuer thread; G4D debug only)
+        long long cyc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        long long tprev = clock64();
+#define G4D_CYC(i) do { if (tw.dbg && issuer) { const long long tn_ = clock64(); cyc[i] += tn_ - tprev; tprev = tn_; } } while (0)
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
             const int64_t gi = tile * 128 + row;
             const bool valid = gi < n;
@@ -224,16 +255,20 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                 if (io.rotation) { const float4 r4 = *reinterpret_cast<const float4*>(io.rotation + 4 * gi); q[0] = r4.x; q[1] = r4.y; q[2] = r4.z; q[3] = r4.w; }
                 if (io.opacity) ol = io.opacity[gi];
             }
+            G4D_CYC(0);   // input loads
             // ---- layer 0: D = feat * W0^T   (features were put into X by the G group)
             bar_sync(kBarFeat, 256);
-            if (tid == 0) {
+            G4D_CYC(1);   // wait for the features
+            if (issuer) {
                 tc::fence_after_sync();
-                tc::gemm_3xtf32(tbase + kColD, tbase + kColX, tbase + kColXLo, sW0, sW0 + 128u * F * 4, 128, F, F, 0, false);
+                tc::gemm_3xtf32<F>(tbase + kColD, tbase + kColX, tbase + kColXLo, sW0, sW0 + 128u * F * 4, 128, F, 0, false);
                 tc::umma_commit(bar_mma);
             }
             mbar_wait(bar_mma, ph_mma); ph_mma ^= 1u;
             tc::fence_after_sync();
+            G4D_CYC(2);   // layer-0 MMA
             if (!first) { bar_sync(kBarScratchFree, 256); tc::fence_after_sync(); }   // G has read the previous tile's scratch (A1 region)
+            G4D_CYC(3);   // wait scratch free
             // ---- epilogue 0: a1 = relu(D + b0) -> A1 (hi | lo)
 #pragma unroll 1
             for (int ch = 0; ch < 8; ++ch) {
@@ -241,14 +276,21 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                 uint32_t v[16], hi[16], lo[16];
                 tc::tmem_ld16(lane_base + kColD + c0, v);
                 tc::wait_ld();
+                float bb[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) tc::tf32_split(fmaxf(__uint_as_float(v[j]) + sBias[c0 + j], 0.f), hi[j], lo[j]);
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(sBias + c0 + j);
+                    bb[j] = b4.x; bb[j + 1] = b4.y; bb[j + 2] = b4.z; bb[j + 3] = b4.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) tc::tf32_split(fmaxf(__uint_as_float(v[j]) + bb[j], 0.f), hi[j], lo[j]);
                 tc::tmem_st16(lane_base + kColA1Hi + c0, hi);
                 tc::tmem_st16(lane_base + kColA1Lo + c0, lo);
             }
             tc::wait_st();
             tc::fence_before_sync();
             bar_sync(kBarM, 128);
+            G4D_CYC(4);   // epilogue 0
 
             float dl[11];
 #pragma unroll
@@ -257,12 +299,12 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
 #pragma unroll
             for (int j = 0; j < 48; ++j) dsh[j] = 0.f;
 
-#pragma unroll
+#pragma unroll 1
             for (int h = 0; h < G4D_NUM_HEADS; ++h) {
                 if (!(d.head_mask & (1 << h))) continue;
-                const int kp16 = (h == 4) ? 48 : 16;
                 const float* b1 = sBias + 128 + h * 128;
-                int nh = -1;   // next head whose weights go into the buffers once this head has released them
+                const float* b2 = sBias + 128 + G4D_NUM_HEADS * 128 + b2off_of(d.head_mask, h);
+                int nh = -1;   // next head whose W1 goes into the buffer once this head has released it
                 {
                     const int later = d.head_mask >> (h + 1);
                     if (later) nh = h + 1 + (__ffs(later) - 1);
@@ -270,76 +312,98 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                 }
                 // ---- layer 1: D = a1 * W1^T
                 mbar_wait(bar_w1, ph_w1); ph_w1 ^= 1u;
-                if (tid == 0) {
+                G4D_CYC(5);   // wait W1
+                if (issuer) {
                     tc::fence_after_sync();
-                    tc::gemm_3xtf32(tbase + kColD, tbase + kColA1Hi, tbase + kColA1Lo, sW1, sW1 + 65536u, 128, 128, 128, 0, false);
+                    tc::gemm_3xtf32<128>(tbase + kColD, tbase + kColA1Hi, tbase + kColA1Lo, sW1, sW1 + 65536u, 128, 128, 0, false);
                     tc::umma_commit(bar_mma);
                 }
                 mbar_wait(bar_mma, ph_mma); ph_mma ^= 1u;
                 tc::fence_after_sync();
-                if (tid == 0 && nh >= 0) {   // W1 buffer is free: stream the next W1
+                G4D_CYC(6);   // layer-1 MMA
+                if (issuer && nh >= 0) {   // W1 buffer is free: stream the next W1
                     mbar_expect_tx(bar_w1, 2u * 65536);
                     tma_bulk_g2s(smem + Ls.w1, tw.w1[nh], 65536, bar_w1);
                     tma_bulk_g2s(smem + Ls.w1 + 65536, tw.w1[nh] + 16384, 65536, bar_w1);
                 }
-                mbar_wait(bar_w2, ph_w2); ph_w2 ^= 1u;
+                if (h < 4) {
+                    // ---- small head: layer 2 (k <= 4 outputs) fused into the epilogue in exact fp32 -- cheaper than two
+                    //      tensor-core round trips for a 128 x 4 x 128 GEMM
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4* w2 = sW2s + h * 128;
 #pragma unroll 1
-                for (int hh = 0; hh < 2; ++hh) {
-                    // hidden half hh: a2 = relu(D[:, 64hh : 64hh+64] + b1) -> X (hi | lo)
-#pragma unroll 1
-                    for (int ch = 0; ch < 4; ++ch) {
-                        const uint32_t cl = (uint32_t)(ch * 16);
-                        const uint32_t cg = (uint32_t)(hh * 64) + cl;
-                        uint32_t v[16], hi[16], lo[16];
-                        tc::tmem_ld16(lane_base + kColD + cg, v);
-                        tc::wait_ld();
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) tc::tf32_split(fmaxf(__uint_as_float(v[j]) + b1[cg + j], 0.f), hi[j], lo[j]);
-                        tc::tmem_st16(lane_base + kColX + cl, hi);
-                        tc::tmem_st16(lane_base + kColXLo + cl, lo);
-                    }
-                    tc::wait_st();
-                    tc::fence_before_sync();
-                    bar_sync(kBarM, 128);
-                    // ---- layer 2 partial: D2 (+)= a2_half * W2[:, 64hh : 64hh+64]^T   (D2 = D columns [0, kp16))
-                    if (tid == 0) {
-                        tc::fence_after_sync();
-                        tc::gemm_3xtf32(tbase + kColD, tbase + kColX, tbase + kColXLo, sW2, sW2 + (uint32_t)kp16 * 128 * 4, (uint32_t)kp16,
-                                        64, 128, (uint32_t)(hh * 16), hh == 1);
-                        tc::umma_commit(bar_mma);
-                    }
-                    mbar_wait(bar_mma, ph_mma); ph_mma ^= 1u;
-                    tc::fence_after_sync();
-                }
-                if (tid == 0 && nh >= 0) {   // W2 buffer is free
-                    const uint32_t w2b = (uint32_t)tw.kp16[nh] * 128 * 4;
-                    mbar_expect_tx(bar_w2, 2u * w2b);
-                    tma_bulk_g2s(smem + Ls.w2, tw.w2[nh], w2b, bar_w2);
-                    tma_bulk_g2s(smem + Ls.w2 + w2b, tw.w2[nh] + tw.kp16[nh] * 128, w2b, bar_w2);
-                }
-                // ---- the head's output row
-                {
-                    const float* b2 = sBias + 128 + G4D_NUM_HEADS * 128 + b2off[h];
-                    if (h < 4) {
+                    for (int ch = 0; ch < 8; ++ch) {
                         uint32_t v[16];
-                        tc::tmem_ld16(lane_base + kColD, v);
+                        tc::tmem_ld16(lane_base + kColD + ch * 16, v);
+                        tc::wait_ld();
+                        float bb[16];
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(b1 + ch * 16 + j);
+                            bb[j] = b4.x; bb[j + 1] = b4.y; bb[j + 2] = b4.z; bb[j + 3] = b4.w;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float a2 = fmaxf(__uint_as_float(v[j]) + bb[j], 0.f);
+                            const float4 w = w2[ch * 16 + j];
+                            acc.x = fmaf(a2, w.x, acc.x); acc.y = fmaf(a2, w.y, acc.y);
+                            acc.z = fmaf(a2, w.z, acc.z); acc.w = fmaf(a2, w.w, acc.w);
+                        }
+                    }
+                    if (h == 0) { dl[0] = acc.x + b2[0]; dl[1] = acc.y + b2[1]; dl[2] = acc.z + b2[2]; }
+                    else if (h == 1) { dl[3] = acc.x + b2[0]; dl[4] = acc.y + b2[1]; dl[5] = acc.z + b2[2]; }
+                    else if (h == 2) { dl[6] = acc.x + b2[0]; dl[7] = acc.y + b2[1]; dl[8] = acc.z + b2[2]; dl[9] = acc.w + b2[3]; }
+                    else { dl[10] = acc.x + b2[0]; }
+                    G4D_CYC(8);   // small-head epilogue + fp32 layer 2
+                } else {
+#pragma unroll 1
+                    for (int hh = 0; hh < 2; ++hh) {
+                        // hidden half hh: a2 = relu(D[:, 64hh : 64hh+64] + b1) -> X (hi | lo)
+#pragma unroll 1
+                        for (int ch = 0; ch < 4; ++ch) {
+                            const uint32_t cl = (uint32_t)(ch * 16);
+                            const uint32_t cg = (uint32_t)(hh * 64) + cl;
+                            uint32_t v[16], hi[16], lo[16];
+                            tc::tmem_ld16(lane_base + kColD + cg, v);
+                            tc::wait_ld();
+                            float bb[16];
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(b1 + cg + j);
+                                bb[j] = b4.x; bb[j + 1] = b4.y; bb[j + 2] = b4.z; bb[j + 3] = b4.w;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) tc::tf32_split(fmaxf(__uint_as_float(v[j]) + bb[j], 0.f), hi[j], lo[j]);
+                            tc::tmem_st16(lane_base + kColX + cl, hi);
+                            tc::tmem_st16(lane_base + kColXLo + cl, lo);
+                        }
+                        tc::wait_st();
+                        tc::fence_before_sync();
+                        bar_sync(kBarM, 128);
+                        G4D_CYC(8);   // hidden-half epilogue
+                        // ---- layer 2 partial: D2 (+)= a2_half * W2[:, 64hh : 64hh+64]^T   (D2 = D columns [0, 48))
+                        if (issuer) {
+                            tc::fence_after_sync();
+                            tc::gemm_3xtf32<64>(tbase + kColD, tbase + kColX, tbase + kColXLo, sW2, sW2 + 48u * 128 * 4, 48, 128,
+                                                (uint32_t)(hh * 16), hh == 1);
+                            tc::umma_commit(bar_mma);
+                        }
+                        mbar_wait(bar_mma, ph_mma); ph_mma ^= 1u;
+                        tc::fence_after_sync();
+                        G4D_CYC(9);   // layer-2 partial MMA
+                    }
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        uint32_t v[16];
+                        tc::tmem_ld16(lane_base + kColD + ch * 16, v);
                         tc::wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (j < head_out(h)) dl[head_col(h) + j] = __uint_as_float(v[j]) + b2[j];
-                    } else {
-#pragma unroll
-                        for (int ch = 0; ch < 3; ++ch) {
-                            uint32_t v[16];
-                            tc::tmem_ld16(lane_base + kColD + ch * 16, v);
-                            tc::wait_ld();
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) dsh[ch * 16 + j] = __uint_as_float(v[j]) + b2[ch * 16 + j];
-                        }
+                        for (int j = 0; j < 16; ++j) dsh[ch * 16 + j] = __uint_as_float(v[j]) + b2[ch * 16 + j];
                     }
                 }
                 tc::fence_before_sync();
-                bar_sync(kBarM, 128);   // D (incl. D2) may be overwritten by the next layer-1 GEMM
+                bar_sync(kBarM, 128);   // D may be overwritten by the next layer-1 GEMM
+                G4D_CYC(10);  // head output / hand-over
             }
             bar_arrive(kBarXFree, 256);   // every MMA reading X has completed: G may store the next tile's features
             p.x += dl[0]; p.y += dl[1]; p.z += dl[2];
@@ -374,8 +438,13 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                     fused_finish_geometry(cam, io, gi, p, sl, q, ol);
                 }
             }
+            G4D_CYC(11);  // scratch hand-off + geometry tail
         }
         if (!first) { bar_sync(kBarScratchFree, 256); }   // pair the G group's last arrive
+        if (tw.dbg && issuer) {
+            for (int i = 0; i < 12; ++i) tw.dbg[blockIdx.x * 12 + i] = cyc[i];
+        }
+#undef G4D_CYC
     } else {
         // =========================================== G group ===========================================
         float feat[F];
@@ -388,7 +457,7 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                 pcs[1] = (io.xyz[3 * gi + 1] - amax[1]) * ascale[1] - 1.0f;
                 pcs[2] = (io.xyz[3 * gi + 2] - amax[2]) * ascale[2] - 1.0f;
             }
-            sample_features_regs<C, L>(d, pcs, feat);
+            sample_features_regs<C, L>(&sd, pcs, feat);
         };
         if (tile < ntiles) sample_tile(tile);
         bool first = true;

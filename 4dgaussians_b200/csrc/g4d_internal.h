@@ -52,6 +52,7 @@ struct TcWeights {
     const float* w1[G4D_NUM_HEADS];    // packed (hi | lo), [128][128]
     const float* w2[G4D_NUM_HEADS];    // packed (hi | lo), [kp16][128]
     int kp16[G4D_NUM_HEADS];
+    long long* dbg;                    // optional [grid][12] per-phase cycle counters (debug)
 };
 
 size_t tc_packed_floats(const G4DDeformParams& prm);

@@ -103,21 +103,23 @@ __host__ __device__ constexpr uint32_t canon_off(uint32_t n, uint32_t k, uint32_
 
 // One GEMM  D[128 x N] (+)= A[128 x K] * B[N x K]^T  as 3 TF32 products (lo*hi, hi*lo, hi*hi), A hi/lo in TMEM at
 // a_hi / a_lo (K columns each), B hi/lo in shared memory (canonical layout, kcore0 = first 16-byte K core to use,
-// Kfull = K extent the layout was packed with).  Issued by ONE thread.
+// Kfull = K extent the layout was packed with).  Issued by ONE thread; fully unrolled so that the descriptor
+// arithmetic is a chain of constant adds and the UTCHMMA issue rate is not limited by address computation.
+template <int K>
 __device__ __forceinline__ void gemm_3xtf32(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi_saddr, uint32_t b_lo_saddr,
-                                            uint32_t N, uint32_t K, uint32_t Kfull, uint32_t kcore0, bool accumulate) {
+                                            uint32_t N, uint32_t Kfull, uint32_t kcore0, bool accumulate) {
     const uint32_t idesc = make_idesc_tf32(128, N);
     const uint32_t sbo = (Kfull >> 2) * 128u;
-    bool acc = accumulate;
-#pragma unroll 1
+    const uint64_t bd_hi = make_smem_desc(b_hi_saddr + kcore0 * 128u, 128u, sbo);
+    const uint64_t bd_lo = make_smem_desc(b_lo_saddr + kcore0 * 128u, 128u, sbo);
+#pragma unroll
     for (int p = 0; p < 3; ++p) {
         const uint32_t a = (p == 0) ? a_lo : a_hi;
-        const uint32_t b = (p == 1) ? b_lo_saddr : b_hi_saddr;
-#pragma unroll 1
-        for (uint32_t ks = 0; ks < K; ks += 8) {
-            const uint64_t bd = make_smem_desc(b + (kcore0 + (ks >> 2)) * 128u, 128u, sbo);
-            umma_tf32_ts(d_tmem, a + ks, bd, idesc, acc);
-            acc = true;
+        const uint64_t bd = (p == 1) ? bd_lo : bd_hi;
+#pragma unroll
+        for (int ks = 0; ks < K; ks += 8) {
+            // one k-step = two 128-byte K cores = +16 in the descriptor's 16-byte address field
+            umma_tf32_ts(d_tmem, a + ks, bd + (uint64_t)((ks >> 2) * 8), idesc, accumulate || p > 0 || ks > 0);
         }
     }
 }

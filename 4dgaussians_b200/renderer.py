@@ -77,7 +77,7 @@ class _FusedRender(torch.autograd.Function):
         prm = module.c_params(keep) if module is not None else None
         pgrads, cg = [], None
         if module is not None:
-            pgrads = [torch.zeros_like(p) for p in module.flat_parameters()]
+            pgrads = module.alloc_grads()
             cg = module.c_grads(pgrads)
         g = _lib.Gaussians(n, x.data_ptr(), s.data_ptr(), r.data_ptr(), o.data_ptr(), dc.data_ptr(), rest.data_ptr())
         gx = torch.empty(n, 3, device=dev); gs = torch.empty(n, 3, device=dev); gr = torch.empty(n, 4, device=dev)

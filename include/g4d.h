@@ -169,8 +169,9 @@ enum { G4D_OPT_SYNC_MODE = 1,  /* 1 (default): size the instance buffer exactly 
                                   provably contribute nothing (images identical, fewer instances) */
        G4D_OPT_STAGE_TIMING = 4, /* 1: bracket every stage with CUDA events on the launching stream
                                    (bench.py's live per-kernel durations); 0 (default): off */
-       G4D_OPT_TENSOR_CORES = 5  /* 1 (default): run the deformation MLP on tcgen05 tensor cores (3xTF32) when the
-                                   configuration allows (net_width 128, C in {16,32}, F <= 64); 0: FP32 FFMA kernels */ };
+       G4D_OPT_TENSOR_CORES = 5, /* 1 (default): run the deformation MLP on tcgen05 tensor cores (3xTF32) when the
+                                   configuration allows (net_width 128, C in {16,32}, F <= 64); 0: FP32 FFMA kernels */
+       G4D_OPT_TC_DEBUG = 6      /* 1: the tensor-core kernel records per-phase cycle counters (g4d_debug_tc_cycles) */ };
 int g4d_workspace_set_option(G4DWorkspace *ws, int option, int64_t value);
 
 /* copy an internal per-forward buffer to HOST memory (tests / debugging; synchronises).
@@ -205,6 +206,8 @@ int g4d_context_stage_times(G4DContext *ctx, float *out_ms, int capacity);
  * B through shared memory).  cfg = {N, K, layout_mode, swap_desc, a_cols_per_k, use_tma, single_pass, version_bit}.
  * A, B, D are device fp32; not on any product path. */
 int g4d_debug_umma(G4DWorkspace *ws, const int *cfg, const float *A, const float *B, float *D, void *stream);
+/* DEBUG: mean per-CTA cycles the last tensor-core deform launch spent in each of its 12 phases (G4D_OPT_TC_DEBUG). */
+int g4d_debug_tc_cycles(G4DWorkspace *ws, double *out12);
 
 #ifdef __cplusplus
 }

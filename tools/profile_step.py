@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--iters", type=int, default=2)
     ap.add_argument("--backward", type=int, default=1)
     ap.add_argument("--stage-times", type=int, default=0)
+    ap.add_argument("--tc-debug", type=int, default=0)
     a = ap.parse_args()
     g4d = importlib.import_module("4dgaussians_b200")
     synth = importlib.import_module("4dgaussians_b200.synth")
@@ -40,6 +41,8 @@ def main():
     ws = g4d._lib.Workspace.get(0)
     if a.stage_times:
         ws.set_option(g4d._lib.OPT_STAGE_TIMING, 1)
+    if a.tc_debug:
+        ws.set_option(g4d._lib.OPT_TC_DEBUG, 1)
     for i in range(a.iters):
         cam = cams[i % len(cams)]
         if a.backward:
@@ -49,6 +52,13 @@ def main():
             with torch.no_grad():
                 out = g4d.render(cam, pc, Pipe, bg)
         torch.cuda.synchronize()
+        if a.tc_debug:
+            import ctypes as C
+            arr = (C.c_double * 12)()
+            g4d._lib.load().g4d_debug_tc_cycles(ws.handle, arr)
+            names = ["inputs", "wait_feat", "L0_mma", "wait_scratch_free", "epi0", "wait_W1", "L1_mma", "wait_W2", "epi_half",
+                     "L2_mma", "head_out", "tail"]
+            print("tc cycles/CTA:", {k: int(arr[i]) for i, k in enumerate(names)}, "total", int(sum(arr)), flush=True)
         if a.stage_times and ws._free_contexts:
             c = ws._free_contexts[-1]
             s = c.stats()
