@@ -87,6 +87,10 @@ struct G4DContext {
     ImageBuffers im{};
     FusedOutputs fo{};
     float* trow_ptr[G4D_MAX_LEVELS][3] = {};
+    uint32_t* h_r = nullptr;          // pinned: instance count of the last forward (no-sync mode)
+    cudaEvent_t ev_r = nullptr;
+    bool pending = false;             // an asynchronous R read-back has not been checked yet
+    int64_t used_capacity = 0;        // capacity the pending forward ran with
     cudaEvent_t ev[2 * G4D_STAGE_COUNT] = {};
     bool ev_used[G4D_STAGE_COUNT] = {};
     bool ev_created = false;
@@ -260,12 +264,35 @@ int debug_sync(const G4DCamera* cam, cudaStream_t st, const char* stage) {
     return G4D_OK;
 }
 
+// no-sync mode: the previous forward's instance count arrives asynchronously; look at it before reusing the context
+int check_pending(G4DContext* c) {
+    if (!c->pending) return G4D_OK;
+    G4D_CUDA(cudaEventSynchronize(c->ev_r));
+    c->pending = false;
+    c->R = (int64_t)c->h_r[0];
+    if (c->R > c->used_capacity) {
+        const int64_t need = c->R + c->R / 2;
+        if (need > c->ws->min_capacity) c->ws->min_capacity = need;
+        c->has_forward = false;
+        char msg[160];
+        snprintf(msg, sizeof(msg), "%lld tile instances did not fit the capacity of %lld used by the previous no-sync forward; its image is incomplete",
+                 (long long)c->R, (long long)c->used_capacity);
+        return fail(G4D_ERR_OVERFLOW, "instance buffer overflow", msg);
+    }
+    return G4D_OK;
+}
+
 // stages after the per-Gaussian projection: scan -> R -> emit -> sort -> ranges -> blend
 int bin_and_blend(G4DContext* c, const G4DCamera* cam, int64_t n, float* out_color, float* out_depth, cudaStream_t st) {
     G4DWorkspace* ws = c->ws;
     const CameraDev* dcam = c->cam.as<CameraDev>();
     int rc;
     int64_t R = 0;
+    const int num_tiles = c->grid_x * c->grid_y;
+    int tile_bits = 0;
+    while ((1 << tile_bits) < num_tiles) ++tile_bits;
+    // no-sync needs a capacity learnt from an earlier (synchronous) forward on this context
+    const bool nosync = !ws->sync_mode && !cam->debug && c->capacity > 0 && c->R > 0 && n > 0;
     if (n > 0) {
         const size_t tb = scan_temp_bytes(n);
         G4D_CUDA(ws->temp.ensure(tb));
@@ -274,29 +301,54 @@ int bin_and_blend(G4DContext* c, const G4DCamera* cam, int64_t n, float* out_col
             if (ws->tight_cull) G4D_CUDA(launch_cull_count(n, c->g, st));
             G4D_CUDA(launch_scan(c->g.tiles_touched, c->g.offsets, n, ws->temp.p, tb, st));
         }
-        G4D_CUDA(cudaMemcpyAsync(ws->h_pinned, c->g.offsets + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        G4D_CUDA(cudaStreamSynchronize(st));   // the one host sync of the path (as in the reference, A.2)
-        R = (int64_t)ws->h_pinned[0];
+        if (!nosync) {
+            G4D_CUDA(cudaMemcpyAsync(ws->h_pinned, c->g.offsets + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            G4D_CUDA(cudaStreamSynchronize(st));   // the one host sync of the path (as in the reference, A.2)
+            R = (int64_t)ws->h_pinned[0];
+        }
     }
     if ((rc = debug_sync(cam, st, "preprocess/scan")) != G4D_OK) return rc;
-    c->R = R;
-    if ((rc = ensure_bin(c, R)) != G4D_OK) return rc;
-    const int num_tiles = c->grid_x * c->grid_y;
-    int tile_bits = 0;
-    while ((1 << tile_bits) < num_tiles) ++tile_bits;
-    if (R > 0) {
+    if (!nosync) {
+        c->R = R;
+        int64_t want = R;
+        if (!ws->sync_mode) want = R + R / 2;                 // head-room for the asynchronous forwards that follow
+        if (want < ws->min_capacity) want = ws->min_capacity;
+        if ((rc = ensure_bin(c, want)) != G4D_OK) return rc;
+        if (R > 0) {
+            {
+                StageTimer tm(c, G4D_STAGE_EMIT, st);
+                G4D_CUDA(launch_emit_keys(dcam, n, c->g, c->b, c->capacity, ws->tight_cull, st));
+            }
+            const size_t sb = sort_temp_bytes(R);
+            G4D_CUDA(ws->temp.ensure(sb));
+            StageTimer tm(c, G4D_STAGE_SORT, st);
+            G4D_CUDA(launch_sort(c->b, R, 32 + tile_bits, ws->temp.p, sb, st));
+        }
+        {
+            StageTimer tm(c, G4D_STAGE_RANGES, st);
+            G4D_CUDA(launch_tile_ranges(c->b, R, num_tiles, st));
+        }
+    } else {
+        // capacity-bounded, no host round trip: unused slots carry all-ones keys whose tile field (one extra sorted bit)
+        // exceeds every real tile, so they collect behind the last tile and are ignored by the range builder
+        if (ws->min_capacity > c->capacity && (rc = ensure_bin(c, ws->min_capacity)) != G4D_OK) return rc;
+        const int64_t cap = c->capacity;
+        G4D_CUDA(cudaMemcpyAsync(c->h_r, c->g.offsets + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        G4D_CUDA(cudaEventRecord(c->ev_r, st));
+        c->pending = true; c->used_capacity = cap;
         {
             StageTimer tm(c, G4D_STAGE_EMIT, st);
-            G4D_CUDA(launch_emit_keys(dcam, n, c->g, c->b, c->capacity, ws->tight_cull, st));
+            G4D_CUDA(cudaMemsetAsync(c->b.keys_unsorted, 0xFF, (size_t)cap * 8, st));
+            G4D_CUDA(launch_emit_keys(dcam, n, c->g, c->b, cap, ws->tight_cull, st));
         }
-        const size_t sb = sort_temp_bytes(R);
+        const size_t sb = sort_temp_bytes(cap);
         G4D_CUDA(ws->temp.ensure(sb));
-        StageTimer tm(c, G4D_STAGE_SORT, st);
-        G4D_CUDA(launch_sort(c->b, R, tile_bits, ws->temp.p, sb, st));
-    }
-    {
+        {
+            StageTimer tm(c, G4D_STAGE_SORT, st);
+            G4D_CUDA(launch_sort(c->b, cap, 32 + tile_bits + 1, ws->temp.p, sb, st));
+        }
         StageTimer tm(c, G4D_STAGE_RANGES, st);
-        G4D_CUDA(launch_tile_ranges(c->b, R, num_tiles, st));
+        G4D_CUDA(launch_tile_ranges(c->b, cap, num_tiles, st));
     }
     if ((rc = debug_sync(cam, st, "binning")) != G4D_OK) return rc;
     {
@@ -373,6 +425,9 @@ G4DContext* g4d_context_create(G4DWorkspace* ws) {
     G4DContext* c = new G4DContext();
     c->ws = ws;
     if (c->cam.ensure(sizeof(CameraDev)) != cudaSuccess) { delete c; fail(G4D_ERR_NOMEM, "camera buffer"); return nullptr; }
+    if (cudaMallocHost((void**)&c->h_r, 64) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_r, cudaEventDisableTiming) != cudaSuccess) {
+        delete c; fail(G4D_ERR_NOMEM, "pinned scalar / event"); return nullptr;
+    }
     return c;
 }
 
@@ -380,6 +435,8 @@ void g4d_context_destroy(G4DContext* c) {
     if (!c) return;
     cudaSetDevice(c->ws->device);
     if (c->ev_created) for (int i = 0; i < 2 * G4D_STAGE_COUNT; ++i) cudaEventDestroy(c->ev[i]);
+    if (c->ev_r) cudaEventDestroy(c->ev_r);
+    if (c->h_r) cudaFreeHost(c->h_r);
     c->cam.release(); c->geom.release(); c->bin.release(); c->img.release(); c->fused.release(); c->gscratch.release(); c->gdeform.release();
     c->trow.release();
     delete c;
@@ -417,6 +474,7 @@ int g4d_context_stats(G4DContext* c, G4DStats* out) {
     if (!c->has_forward) return fail(G4D_ERR_STATE, "no forward has run on this context");
     cudaSetDevice(c->ws->device);
     G4D_CUDA(cudaDeviceSynchronize());
+    { int rc_ = check_pending(c); if (rc_ != G4D_OK) return rc_; }
     out->num_rendered = c->R; out->instance_capacity = c->capacity; out->tiles_x = c->grid_x; out->tiles_y = c->grid_y;
     std::vector<int32_t> radii((size_t)c->n);
     if (c->n) G4D_CUDA(cudaMemcpy(radii.data(), c->g.radii, (size_t)c->n * 4, cudaMemcpyDeviceToHost));
@@ -466,6 +524,7 @@ int g4d_rasterize_forward(G4DContext* c, const G4DCamera* cam, int64_t n, const 
     if (n >= (1ll << 31)) return fail(G4D_ERR_ARG, "n too large");
     cudaStream_t st = (cudaStream_t)stream;
     G4D_CUDA(cudaSetDevice(c->ws->device));
+    if ((rc = check_pending(c)) != G4D_OK) return rc;
     c->has_forward = false; c->is_fused = false; c->deformed = false;
     if ((rc = ensure_geom(c, n)) != G4D_OK) return rc;
     if ((rc = ensure_image(c, cam->image_height, cam->image_width)) != G4D_OK) return rc;
@@ -495,6 +554,7 @@ int g4d_rasterize_backward(G4DContext* c, const G4DCamera* cam, int64_t n, const
         return fail(G4D_ERR_ARG, "NULL gradient pointer");
     cudaStream_t st = (cudaStream_t)stream;
     G4D_CUDA(cudaSetDevice(c->ws->device));
+    if ((rc = check_pending(c)) != G4D_OK) return rc;
     (void)opacities;
     RasterInputs in{means3D, scales, rotations, opacities, shs, nullptr, nullptr};
     return raster_backward_stages(c, cam, n, in, dL_dcolor, g_means3D, g_means2D, g_shs, nullptr, nullptr, g_opacities,
@@ -506,6 +566,7 @@ int64_t g4d_context_read(G4DContext* c, int which, void* host_dst, int64_t bytes
     if (!c || !c->has_forward) return fail(G4D_ERR_STATE, "no forward has run on this context");
     cudaSetDevice(c->ws->device);
     if (cudaDeviceSynchronize() != cudaSuccess) return fail(G4D_ERR_CUDA, "cudaDeviceSynchronize");
+    { int rc_ = check_pending(c); if (rc_ != G4D_OK) return rc_; }
     const size_t N = (size_t)c->n, P = (size_t)c->H * c->W, R = (size_t)c->R, Tn = (size_t)c->grid_x * c->grid_y;
     std::vector<char> tmp;
     auto pull = [&](const void* src, size_t nbytes) -> bool {
@@ -609,6 +670,7 @@ int g4d_render_forward(G4DContext* c, const G4DCamera* cam, const G4DDeformParam
     cudaStream_t st = (cudaStream_t)stream;
     G4DWorkspace* ws = c->ws;
     G4D_CUDA(cudaSetDevice(ws->device));
+    if ((rc = check_pending(c)) != G4D_OK) return rc;
     c->has_forward = false;
     const bool with_sh = prm && (prm->head_mask & G4D_HEAD_SHS);
     if ((rc = ensure_geom(c, n)) != G4D_OK) return rc;
@@ -666,6 +728,7 @@ int g4d_render_backward(G4DContext* c, const G4DCamera* cam, const G4DDeformPara
     cudaStream_t st = (cudaStream_t)stream;
     G4DWorkspace* ws = c->ws;
     G4D_CUDA(cudaSetDevice(ws->device));
+    if ((rc = check_pending(c)) != G4D_OK) return rc;
     if (n == 0) return G4D_OK;
     const size_t N = (size_t)n;
     const bool split = g->features_rest != nullptr;

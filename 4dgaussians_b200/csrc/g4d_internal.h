@@ -79,7 +79,7 @@ cudaError_t launch_scan(const uint32_t* in, uint32_t* out, int64_t n, void* temp
 cudaError_t launch_cull_count(int64_t n, GeomBuffers g, cudaStream_t st);
 cudaError_t launch_emit_keys(const CameraDev* cam, int64_t n, GeomBuffers g, BinBuffers b, int64_t capacity, int tight,
                              cudaStream_t st);
-cudaError_t launch_sort(BinBuffers b, int64_t r, int tile_bits, void* temp, size_t temp_bytes, cudaStream_t st);
+cudaError_t launch_sort(BinBuffers b, int64_t r, int end_bit, void* temp, size_t temp_bytes, cudaStream_t st);
 cudaError_t launch_tile_ranges(BinBuffers b, int64_t r, int num_tiles, cudaStream_t st);
 cudaError_t launch_blend_forward(const CameraDev* cam, int grid_x, int grid_y, GeomBuffers g, BinBuffers b, ImageBuffers im,
                                  float* out_color, float* out_depth, cudaStream_t st);

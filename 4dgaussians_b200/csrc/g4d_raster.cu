@@ -101,16 +101,18 @@ cudaError_t launch_emit_keys(const CameraDev* cam, int64_t n, GeomBuffers g, Bin
     return cudaGetLastError();
 }
 
-cudaError_t launch_sort(BinBuffers b, int64_t r, int tile_bits, void* temp, size_t temp_bytes, cudaStream_t st) {
+cudaError_t launch_sort(BinBuffers b, int64_t r, int end_bit, void* temp, size_t temp_bytes, cudaStream_t st) {
     if (r == 0) return cudaSuccess;
     return cub::DeviceRadixSort::SortPairs(temp, temp_bytes, b.keys_unsorted, b.keys_sorted, b.ids_unsorted, b.ids_sorted,
-                                           (int)r, 0, 32 + tile_bits, st);
+                                           (int)r, 0, end_bit, st);
 }
 
-__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint64_t* __restrict__ keys, int64_t r, uint2* ranges) {
+__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint64_t* __restrict__ keys, int64_t r, uint2* ranges,
+                                                          uint32_t num_tiles) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= r) return;
     const uint32_t t = (uint32_t)(keys[i] >> 32);
+    if (t >= num_tiles) return;   // padding slots of the capacity-bounded (no-sync) mode
     if (i == 0 || (uint32_t)(keys[i - 1] >> 32) != t) ranges[t].x = (uint32_t)i;
     if (i == r - 1 || (uint32_t)(keys[i + 1] >> 32) != t) ranges[t].y = (uint32_t)(i + 1);
 }
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint64_t* __rest
 cudaError_t launch_tile_ranges(BinBuffers b, int64_t r, int num_tiles, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(b.ranges, 0, sizeof(uint2) * (size_t)num_tiles, st);
     if (e != cudaSuccess || r == 0) return e;
-    tile_ranges_kernel<<<(unsigned)((r + 255) / 256), 256, 0, st>>>(b.keys_sorted, r, b.ranges);
+    tile_ranges_kernel<<<(unsigned)((r + 255) / 256), 256, 0, st>>>(b.keys_sorted, r, b.ranges, (uint32_t)num_tiles);
     return cudaGetLastError();
 }
 

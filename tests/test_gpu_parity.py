@@ -406,3 +406,36 @@ def test_tight_cull_gives_bit_identical_images_with_fewer_instances():
     assert b[3] < 0.9 * a[3], (a[3], b[3])
     for x, y in ((a[4], b[4]), (a[5], b[5])):
         assert float((x - y).abs().max()) <= 1e-4 * max(1e-3, float(x.abs().max()))
+
+
+def test_no_sync_mode_matches_sync_mode_and_reports_overflow():
+    """G4D_OPT_SYNC_MODE=0: capacity-bounded binning without the host round trip gives bit-identical images; a forward
+    that outgrows the capacity is reported by the next call on the context."""
+    ins = [t.float().cuda() for t in raster_inputs(30_000, 6, scale_mean=0.02)]
+    ws = g4d._lib.Workspace.get(0)
+
+    def render(cam):
+        rast = g4d.GaussianRasterizer(_settings(cam, (0.0, 0.1, 0.2)))
+        with torch.no_grad():
+            color, radii, depth = rast(means3D=ins[0], means2D=torch.zeros_like(ins[0]), shs=ins[4], colors_precomp=None,
+                                       opacities=ins[3], scales=ins[1], rotations=ins[2], cov3D_precomp=None)
+        return color.clone(), depth.clone()
+    cams = [synth.make_camera(th, 320, 240, radius=3.0) for th in (0.0, 40.0, 80.0, 120.0)]
+    ref = [render(c) for c in cams]
+    try:
+        ws.set_option(g4d._lib.OPT_SYNC_MODE, 0)
+        got = [render(c) for c in cams]          # first call sizes the buffers synchronously, the rest run without a host sync
+        torch.cuda.synchronize()
+        for (a, b), (c_, d_) in zip(ref, got):
+            assert torch.equal(a, c_) and torch.equal(b, d_)
+        # far camera first (tiny R -> tiny capacity), then a close-up: the close-up must be flagged, not silently truncated
+        ws2_ctx_cam_far = synth.make_camera(0.0, 320, 240, radius=60.0)
+        ws._free_contexts.clear()                 # fresh context => fresh capacity
+        render(ws2_ctx_cam_far); render(ws2_ctx_cam_far)
+        render(synth.make_camera(0.0, 320, 240, radius=2.0))
+        with pytest.raises(g4d._lib.G4DError, match="overflow"):
+            render(ws2_ctx_cam_far)
+    finally:
+        ws.set_option(g4d._lib.OPT_SYNC_MODE, 1)
+        ws.set_option(g4d._lib.OPT_INSTANCE_CAPACITY, 0)
+        ws._free_contexts.clear()
