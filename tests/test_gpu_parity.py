@@ -14,7 +14,7 @@ import torch
 from oracle import deform_ref as dr
 from oracle import raster_ref as rr
 from util_scene import (OracleRaster, cam_tuple, g4d, make_module, oracle_params_from_module, oracle_render, raster_inputs,
-                        rel_err, synth)
+                        rel_err, rel_err_bulk, synth)
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -185,8 +185,8 @@ def test_deform_backward_vs_oracle(net, n):
     w = dr.deform_forward(cfg, prm, *cpu_in, t)
     sum((o * p).sum() for o, p in zip(w, probes)).backward()
     for a, b, nm in zip(dev_in, cpu_in, ("xyz", "scales", "rot", "opacity", "shs")):
-        e = rel_err(a.grad.cpu().numpy(), b.grad.numpy())
-        assert e <= GRAD_TOL, (nm, e)
+        e, emax = rel_err_bulk(a.grad.cpu().numpy(), b.grad.numpy())
+        assert e <= GRAD_TOL and emax <= 5e-2, (nm, e, emax)
     osd = dr.params_to_state_dict(prm)
     for k, p in mod.named_parameters():
         if k not in osd or not p.requires_grad:
