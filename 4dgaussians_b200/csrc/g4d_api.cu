@@ -778,6 +778,10 @@ int g4d_debug_umma(G4DWorkspace* ws, const int* cfg, const float* A, const float
     cudaStream_t st = (cudaStream_t)stream;
     G4D_CUDA(cudaSetDevice(ws->device));
     G4D_CUDA(ws->scratch.ensure((size_t)2 * 128 * 128 * 4 + 256));
+    if (cfg[6] == 16) {   // kind::f16 / bf16x2 variant: cfg = {N, K, a_mode, b_mode, pack_hi_first, single_pass, 16, 0}
+        G4D_CUDA(launch_umma16_selftest(cfg, A, B, D, st));
+        return G4D_OK;
+    }
     G4D_CUDA(launch_umma_selftest(cfg, A, B, ws->scratch.as<float>(), D, st));
     return G4D_OK;
 }

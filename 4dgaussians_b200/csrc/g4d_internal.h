@@ -106,6 +106,7 @@ cudaError_t launch_activate_preprocess(const CameraDev* cam, int64_t n, const fl
 cudaError_t launch_activation_backward(int64_t n, const FusedOutputs& fo, float* g_scales, float* g_rotations,
                                        float* g_opacities, cudaStream_t st);
 
+cudaError_t launch_umma16_selftest(const int cfg[8], const float* A, const float* B, float* D, cudaStream_t st);
 cudaError_t launch_umma_selftest(const int cfg[8], const float* A, const float* B, float* scratch_packed, float* D, cudaStream_t st);
 
 }  // namespace g4d

@@ -135,3 +135,126 @@ cudaError_t launch_umma_selftest(const int cfg[8], const float* A, const float* 
 }
 
 }  // namespace g4d
+
+// ------------------------------------------------------------------------------------------------------
+// Self test #2: kind::f16 (BF16 hi+lo, 3 products) with every operand role the backward kernels use.
+//   D[128 x N] = A[128 x K] * B[N x K]^T
+// a_mode: 0 = TMEM (two bf16 per 32-bit column), 1 = smem K-major image of A[M][K], 2 = smem MN-major image built from
+//         the TRANSPOSED matrix At[K][M] (the layout a [g][j] activation image has when g is the contraction index)
+// b_mode: 0 = smem K-major image of B[N][K], 1 = smem MN-major image built from Bt[K][N]
+// pack_hi_first: TMEM packing order of the two K elements in a column (0: even k in the low half)
+// ------------------------------------------------------------------------------------------------------
+namespace g4d {
+
+struct Umma16Cfg { int N, K, a_mode, b_mode, pack_hi_first, single_pass, r0, r1; };
+
+__global__ void __launch_bounds__(128, 1)
+umma16_selftest_kernel(Umma16Cfg c, const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(8) uint64_t bar_mma;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t N = c.N, K = c.K, M = 128;
+    // images: A hi, A lo (128 x K or K x 128), B hi, B lo
+    uint8_t* a_img[2] = {smem_raw, smem_raw + M * K * 2};
+    uint8_t* b_img[2] = {smem_raw + 2 * M * K * 2, smem_raw + 2 * M * K * 2 + N * K * 2};
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, tc::kTmemCols);
+    if (tid == 0) { mbar_init(&bar_mma, 1); fence_barrier_init(); }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = tmem_base_s;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    // ---- B images
+    for (uint32_t i = tid; i < N * K; i += blockDim.x) {
+        const uint32_t n = i / K, k = i % K;
+        uint16_t hi, lo;
+        tc::bf16_split(B[i], hi, lo);
+        const uint32_t off = c.b_mode == 0 ? tc::img16_off(n, k, K) : tc::img16_off(k, n, N);
+        *reinterpret_cast<uint16_t*>(b_img[0] + off) = hi;
+        *reinterpret_cast<uint16_t*>(b_img[1] + off) = lo;
+    }
+    // ---- A: images or TMEM
+    if (c.a_mode != 0) {
+        for (uint32_t i = tid; i < M * K; i += blockDim.x) {
+            const uint32_t m = i / K, k = i % K;
+            uint16_t hi, lo;
+            tc::bf16_split(A[i], hi, lo);
+            const uint32_t off = c.a_mode == 1 ? tc::img16_off(m, k, K) : tc::img16_off(k, m, M);
+            *reinterpret_cast<uint16_t*>(a_img[0] + off) = hi;
+            *reinterpret_cast<uint16_t*>(a_img[1] + off) = lo;
+        }
+    } else {
+        const int r = tid;
+        for (uint32_t k0 = 0; k0 < K; k0 += 16) {   // 16 K elements = 8 columns
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint16_t h0, l0, h1, l1;
+                tc::bf16_split(A[r * K + k0 + 2 * j], h0, l0);
+                tc::bf16_split(A[r * K + k0 + 2 * j + 1], h1, l1);
+                hi[j] = c.pack_hi_first ? ((uint32_t)h0 << 16 | h1) : ((uint32_t)h1 << 16 | h0);
+                lo[j] = c.pack_hi_first ? ((uint32_t)l0 << 16 | l1) : ((uint32_t)l1 << 16 | l0);
+            }
+            tc::tmem_st8(tbase + lane_base + (k0 >> 1), hi);
+            tc::tmem_st8(tbase + lane_base + 128 + (k0 >> 1), lo);
+        }
+        tc::wait_st();
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t d_col = 256;
+    if (tid == 0) {
+        const uint32_t idesc = tc::make_idesc_bf16(128, N, c.a_mode == 2, c.b_mode == 1);
+        // per-operand descriptor strides and the byte step of one K = 16 MMA
+        const uint32_t a_lbo = c.a_mode == 1 ? 128u : (M >> 3) * 128u, a_sbo = c.a_mode == 1 ? (K >> 3) * 128u : 128u;
+        const uint32_t a_step = c.a_mode == 1 ? 2u * 128u : 2u * (M >> 3) * 128u;
+        const uint32_t b_lbo = c.b_mode == 0 ? 128u : (N >> 3) * 128u, b_sbo = c.b_mode == 0 ? (K >> 3) * 128u : 128u;
+        const uint32_t b_step = c.b_mode == 0 ? 2u * 128u : 2u * (N >> 3) * 128u;
+        bool acc = false;
+        const int passes = c.single_pass ? 1 : 3;
+        for (int p = 0; p < passes; ++p) {
+            const int ai = (!c.single_pass && p == 0) ? 1 : 0, bi = (!c.single_pass && p == 1) ? 1 : 0;
+            for (uint32_t ks = 0; ks < K; ks += 16) {
+                const uint64_t bd = tc::make_smem_desc(tc::smem_addr(b_img[bi]) + (ks >> 4) * b_step, b_lbo, b_sbo);
+                if (c.a_mode == 0) {
+                    tc::umma_bf16_ts(tbase + d_col, tbase + (ai ? 128u : 0u) + (ks >> 1), bd, idesc, acc);
+                } else {
+                    const uint64_t ad = tc::make_smem_desc(tc::smem_addr(a_img[ai]) + (ks >> 4) * a_step, a_lbo, a_sbo);
+                    tc::umma_bf16_ss(tbase + d_col, ad, bd, idesc, acc);
+                }
+                acc = true;
+            }
+        }
+        tc::umma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, 0);
+    tc::fence_after_sync();
+    {
+        const int r = tid;
+        for (uint32_t n0 = 0; n0 < N; n0 += 8) {
+            uint32_t v[8];
+            tc::tmem_ld8(tbase + lane_base + d_col + n0, v);
+            tc::wait_ld();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) D[r * N + n0 + j] = __uint_as_float(v[j]);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, tc::kTmemCols);
+}
+
+cudaError_t launch_umma16_selftest(const int cfg[8], const float* A, const float* B, float* D, cudaStream_t st) {
+    Umma16Cfg c{cfg[0], cfg[1], cfg[2], cfg[3], cfg[4], cfg[5], cfg[6], cfg[7]};
+    if (c.N < 16 || c.N > 128 || (c.N % 16) || c.K < 16 || c.K > 128 || (c.K % 16)) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)2 * 128 * c.K * 2 + (size_t)2 * c.N * c.K * 2 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(umma16_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    umma16_selftest_kernel<<<1, 128, smem, st>>>(c, A, B, D);
+    return cudaGetLastError();
+}
+
+}  // namespace g4d

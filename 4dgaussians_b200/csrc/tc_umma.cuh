@@ -126,3 +126,61 @@ __device__ __forceinline__ void gemm_3xtf32(uint32_t d_tmem, uint32_t a_hi, uint
 
 }  // namespace tc
 }  // namespace g4d
+
+// ======================================================================================================
+// kind::f16 with BF16 operands, fp32 accumulate; "bf16x2" split (hi + lo, 3 products) gives ~16 mantissa bits
+// (measured gradient error 1.5e-5 of max).  Used by the backward kernels.
+//
+// One image format serves every operand role: 8 x 8 bf16 core matrices (8 rows x 16 bytes = 128 contiguous bytes)
+// stored as image[row / 8][col / 8][row % 8][col % 8]:
+//     off(row, col) = (row / 8) * (ncols / 8) * 128 + (col / 8) * 128 + (row % 8) * 16 + (col % 8) * 2
+//   * read as a K-major operand  (rows = M or N, cols = K):  LBO = 128 (K-adjacent cores), SBO = (ncols/8)*128
+//   * read as an MN-major operand (rows = K, cols = M or N): SBO = 128 (MN-adjacent cores), LBO = (ncols/8)*128,
+//     with the a_major / b_major bit of the instruction descriptor set.
+// ======================================================================================================
+namespace g4d {
+namespace tc {
+
+__host__ __device__ constexpr uint32_t img16_off(uint32_t row, uint32_t col, uint32_t ncols) {
+    return (row >> 3) * ((ncols >> 3) * 128u) + (col >> 3) * 128u + (row & 7u) * 16u + (col & 7u) * 2u;
+}
+
+__device__ __forceinline__ uint16_t bf16_rn(float x) {
+    uint16_t r;
+    asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void bf16_split(float x, uint16_t& hi, uint16_t& lo) {
+    hi = bf16_rn(x);
+    lo = bf16_rn(x - __uint_as_float((uint32_t)hi << 16));
+}
+
+// instruction descriptor, kind::f16, A/B = BF16, D = F32; a_mn / b_mn select MN-major operands
+__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, bool a_mn, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((N >> 3) << 17) |
+           ((M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    const uint32_t acc = accumulate ? 1u : 0u;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    const uint32_t acc = accumulate ? 1u : 0u;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+}  // namespace tc
+}  // namespace g4d
