@@ -27,6 +27,7 @@ UNITS = {
     "g4d_api.cu": [],
     "g4d_tc_selftest.cu": [],
     "g4d_deform_tc.cu": ["-fmad=false"],
+    "g4d_deform_tc_bwd.cu": [],
 }
 
 

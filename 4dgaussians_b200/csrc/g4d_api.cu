@@ -59,6 +59,10 @@ struct G4DWorkspace {
     int tensor_cores = 1;
     DevBuf tc_packed;
     TcWeights tcw{};
+    DevBuf tc_bwd_packed;
+    TcBwdWeights tcbw{};
+    uint64_t tc_bwd_version = 0;
+    const void* tc_bwd_key = nullptr;
     uint64_t tc_version = ~0ull;
     const void* tc_key = nullptr;
     DevBuf tc_dbg;
@@ -210,6 +214,32 @@ int refresh_tc(G4DWorkspace* ws, const G4DDeformParams* p, cudaStream_t st) {
     G4D_CUDA(launch_tc_pack_weights(*p, ws->tc_packed.as<float>(), &ws->tcw, st));
     ws->tc_version = p->version;
     ws->tc_key = (const void*)p->w0;
+    return G4D_OK;
+}
+
+int refresh_tc_bwd(G4DWorkspace* ws, const G4DDeformParams* p, cudaStream_t st) {
+    if (ws->tc_bwd_version == p->version && ws->tc_bwd_key == (const void*)p->w0 && ws->tc_bwd_packed.p) return G4D_OK;
+    G4D_CUDA(ws->tc_bwd_packed.ensure(tc_bwd_weight_bytes(*p)));
+    G4D_CUDA(launch_tc_bwd_pack_weights(*p, ws->tc_bwd_packed.as<uint8_t>(), &ws->tcbw, st));
+    ws->tc_bwd_version = p->version;
+    ws->tc_bwd_key = (const void*)p->w0;
+    return G4D_OK;
+}
+
+// backward of the deformation network: tensor-core path when the configuration allows, FFMA path otherwise
+int deform_backward_dispatch(G4DWorkspace* ws, const DeformDesc& d, const G4DDeformParams* prm, const G4DDeformGrads* grads,
+                             float time, int64_t n, const float* xyz, const float* const go[G4D_NUM_HEADS],
+                             float* const gi[G4D_NUM_HEADS], cudaStream_t st) {
+    int rc;
+    if (ws->tensor_cores && tc_deform_supported(d)) {
+        if ((rc = refresh_tc_bwd(ws, prm, st)) != G4D_OK) return rc;
+        G4D_CUDA(ws->scratch.ensure(tc_deform_backward_scratch_bytes(d, n)));
+        G4D_CUDA(launch_deform_backward_tc(d, *prm, *grads, ws->tcbw, time, n, xyz, go, gi, ws->scratch.as<uint8_t>(), ws->sm_count, st));
+        return G4D_OK;
+    }
+    if ((rc = refresh_packed(ws, prm, st)) != G4D_OK) return rc;
+    G4D_CUDA(ws->scratch.ensure(deform_backward_scratch_bytes(d, n)));
+    G4D_CUDA(launch_deform_backward(d, *prm, *grads, time, n, xyz, go, gi, ws->scratch.as<float>(), ws->sm_count, st));
     return G4D_OK;
 }
 
@@ -414,7 +444,7 @@ G4DWorkspace* g4d_workspace_create(int device) {
 void g4d_workspace_destroy(G4DWorkspace* ws) {
     if (!ws) return;
     cudaSetDevice(ws->device);
-    ws->packed.release(); ws->tc_packed.release(); ws->trow.release(); ws->temp.release(); ws->scratch.release();
+    ws->packed.release(); ws->tc_packed.release(); ws->tc_bwd_packed.release(); ws->trow.release(); ws->temp.release(); ws->scratch.release();
     if (ws->h_pinned) cudaFreeHost(ws->h_pinned);
     delete ws;
 }
@@ -649,11 +679,9 @@ int g4d_deform_backward(G4DWorkspace* ws, const G4DDeformParams* prm, G4DDeformG
     if ((rc = setup_trow(ws->trow, trow, prm)) != G4D_OK) return rc;
     G4D_CUDA(launch_collapse_time_rows(*prm, nullptr, time, false, trow, st));
     const DeformDesc d = make_desc(ws, prm, trow);
-    G4D_CUDA(ws->scratch.ensure(deform_backward_scratch_bytes(d, n)));
     const float* go[G4D_NUM_HEADS] = {g_out_xyz, g_out_scaling, g_out_rotation, g_out_opacity, g_out_shs};
     float* gi[G4D_NUM_HEADS] = {g_in_xyz, g_in_scaling, g_in_rotation, g_in_opacity, g_in_shs};
-    G4D_CUDA(launch_deform_backward(d, *prm, *grads, time, n, xyz, go, gi, ws->scratch.as<float>(), ws->sm_count, st));
-    return G4D_OK;
+    return deform_backward_dispatch(ws, d, prm, grads, time, n, xyz, go, gi, st);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -762,13 +790,11 @@ int g4d_render_backward(G4DContext* c, const G4DCamera* cam, const G4DDeformPara
     if (c->fused_sh && !split) G4D_CUDA(cudaMemcpyAsync(gg->features_dc, gd_sh, N * 192, cudaMemcpyDeviceToDevice, st));
     G4D_CUDA(launch_activation_backward(n, c->fo, gd_sc, gd_rot, gd_op, st));
     const DeformDesc d = make_desc(ws, prm, c->trow_ptr);
-    if ((rc = refresh_packed(ws, prm, st)) != G4D_OK) return rc;
-    G4D_CUDA(ws->scratch.ensure(deform_backward_scratch_bytes(d, n)));
     const float* go[G4D_NUM_HEADS] = {gd_xyz, gd_sc, gd_rot, gd_op, gd_sh};
     float* gi[G4D_NUM_HEADS] = {gg->xyz, gg->scaling, gg->rotation, gg->opacity, nullptr};
     {
         StageTimer tm(c, G4D_STAGE_DEFORM_BWD, st);
-        G4D_CUDA(launch_deform_backward(d, *prm, *pgrads, cam->time, n, g->xyz, go, gi, ws->scratch.as<float>(), ws->sm_count, st));
+        if ((rc = deform_backward_dispatch(ws, d, prm, pgrads, cam->time, n, g->xyz, go, gi, st)) != G4D_OK) return rc;
     }
     return debug_sync(cam, st, "deform_backward");
 }

@@ -2,7 +2,7 @@
 // network (HexPlane scatter + MLP dgrad/wgrad).
 // Reference autograd path replaced: loss.backward() at /root/reference/train.py:219 through
 // _RasterizeGaussians.backward, F.normalize/exp/sigmoid, nn.Linear, F.grid_sample.
-#include "g4d_internal.h"
+#include "deform_bwd_common.cuh"
 #include "g4d_math.cuh"
 
 namespace g4d {
@@ -86,25 +86,6 @@ cudaError_t launch_preprocess_backward(const CameraDev* cam, int64_t n, const Ra
 //                  residual-path input gradients.
 //   T  distributes the collapsed time-row gradients onto the two time rows of each time plane.
 // ======================================================================================================
-
-struct DeformBwdBuffers {
-    float* feat;                      // [N][F]
-    float* a1;                        // [N][WD]
-    float* da1[G4D_NUM_HEADS];        // [N][WD] per active head
-    float* trow_grad[G4D_MAX_LEVELS][3];
-};
-
-struct DeformBwdDesc {
-    DeformDesc d;
-    const float* w0;                  // torch layout [WD][F]
-    const float* w1[G4D_NUM_HEADS];   // torch layout [WD][WD]
-    float* g_w0; float* g_b0;
-    float* g_w1[G4D_NUM_HEADS]; float* g_b1[G4D_NUM_HEADS];
-    float* g_w2[G4D_NUM_HEADS]; float* g_b2[G4D_NUM_HEADS];
-    float* g_planes[G4D_MAX_LEVELS][6];
-    const float* go[G4D_NUM_HEADS];   // dL/d(out) per head: xyz[N,3], scaling[N,3], rotation[N,4], opacity[N,1], shs[N,48] (NULL = 0)
-    float* gi[G4D_NUM_HEADS];         // dL/d(in), same shapes (NULL = not wanted)
-};
 
 // acc[r][c] += sum_k A[ty*RM + r][k] * Bt[tx + 16*c][k]       (both operands K-contiguous in shared memory)
 template <int RM, int CN>
@@ -392,24 +373,6 @@ inline FinalSmem final_smem_layout(int TG, int F, int WD) {
     return s;
 }
 
-G4D_D void red_add_v4(float* addr, float4 v) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-
-// border-clamped tap with the coordinate-gradient multiplier ATen uses (0 where the coordinate was clipped)
-struct TapG { int i0, i1; float w0, w1, gmul; };
-G4D_D TapG make_tap_g(float u, int size) {
-    float x = ((u + 1.f) / 2.f) * (float)(size - 1);
-    TapG t;
-    const float hi = (float)(size - 1);
-    t.gmul = (x > 0.f && x < hi) ? 0.5f * hi : 0.f;
-    x = fminf(fmaxf(x, 0.f), hi);
-    const float x0 = floorf(x);
-    t.i0 = (int)x0; t.i1 = min(t.i0 + 1, size - 1);
-    t.w0 = (x0 + 1.f) - x; t.w1 = x - x0;
-    return t;
-}
-
 template <int TG, int WD, int FM>
 __global__ void __launch_bounds__(kDeformThreads, 1)
 deform_bwd_final_kernel(DeformBwdDesc bd, FinalSmem L, float time, int64_t n, const float* __restrict__ xyz,
@@ -625,6 +588,24 @@ __global__ void distribute_time_grad_kernel(TimeGradDesc d, float time) {
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
+cudaError_t launch_distribute_time_grad(const DeformDesc& d, float* const (*trow_grad)[3], float* const (*g_planes)[6], float time,
+                                        cudaStream_t st) {
+    TimeGradDesc t{};
+    t.levels = d.levels; t.C = d.C;
+    const int tk[3] = {2, 4, 5};
+    int total = 0;
+    for (int l = 0; l < d.levels; ++l) {
+        for (int a = 0; a < 4; ++a) t.res[l][a] = d.res[l][a];
+        for (int a = 0; a < 3; ++a) {
+            t.row_grad[l][a] = trow_grad[l][a]; t.plane_grad[l][a] = g_planes[l][tk[a]];
+            t.start[l * 3 + a] = total; total += d.res[l][a] * d.C;
+        }
+    }
+    t.start[d.levels * 3] = total;
+    distribute_time_grad_kernel<<<(total + 255) / 256, 256, 0, st>>>(t, time);
+    return cudaGetLastError();
+}
+
 size_t deform_backward_scratch_bytes(const DeformDesc& d, int64_t n) {
     int active = 0;
     for (int h = 0; h < G4D_NUM_HEADS; ++h) active += (d.head_mask >> h) & 1;
@@ -700,22 +681,7 @@ static cudaError_t launch_deform_backward_t(const DeformBwdDesc& bd, float time,
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     // T
-    {
-        TimeGradDesc t{};
-        t.levels = d.levels; t.C = d.C;
-        const int tk[3] = {2, 4, 5};
-        int total = 0;
-        for (int l = 0; l < d.levels; ++l) {
-            for (int a = 0; a < 4; ++a) t.res[l][a] = d.res[l][a];
-            for (int a = 0; a < 3; ++a) {
-                t.row_grad[l][a] = buf.trow_grad[l][a]; t.plane_grad[l][a] = bd.g_planes[l][tk[a]];
-                t.start[l * 3 + a] = total; total += d.res[l][a] * d.C;
-            }
-        }
-        t.start[d.levels * 3] = total;
-        distribute_time_grad_kernel<<<(total + 255) / 256, 256, 0, st>>>(t, time);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    }
+    if ((e = launch_distribute_time_grad(d, buf.trow_grad, bd.g_planes, time, st)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 

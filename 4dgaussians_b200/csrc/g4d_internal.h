@@ -59,6 +59,22 @@ size_t tc_packed_floats(const G4DDeformParams& prm);
 cudaError_t launch_tc_pack_weights(const G4DDeformParams& prm, float* blob, TcWeights* out, cudaStream_t st);
 bool tc_deform_supported(const DeformDesc& d);
 
+// tensor-core backward (g4d_deform_tc_bwd.cu): BF16 (hi | lo) weight images in the 8x8-core layout of tc_umma.cuh
+struct TcBwdWeights {
+    const uint8_t* w0;                    // image [128][F]
+    const uint8_t* w1[G4D_NUM_HEADS];     // image [128][128]
+};
+size_t tc_bwd_weight_bytes(const G4DDeformParams& prm);
+cudaError_t launch_tc_bwd_pack_weights(const G4DDeformParams& prm, uint8_t* blob, TcBwdWeights* out, cudaStream_t st);
+size_t tc_deform_backward_scratch_bytes(const DeformDesc& d, int64_t n);
+cudaError_t launch_deform_backward_tc(const DeformDesc& d, const G4DDeformParams& prm, const G4DDeformGrads& grads,
+                                      const TcBwdWeights& w, float time, int64_t n, const float* xyz,
+                                      const float* const go[G4D_NUM_HEADS], float* const gi[G4D_NUM_HEADS], uint8_t* scratch,
+                                      int sm_count, cudaStream_t st);
+// collapsed time-row gradients -> the two time rows of each (axis, t) plane (g4d_backward.cu)
+cudaError_t launch_distribute_time_grad(const DeformDesc& d, float* const (*trow_grad)[3], float* const (*g_planes)[6], float time,
+                                        cudaStream_t st);
+
 // ---- launchers (defined in g4d_geom.cu / g4d_raster.cu / g4d_backward.cu) -----------------------------
 cudaError_t launch_pack_camera(const G4DCamera& cam, CameraDev* dst, cudaStream_t st);
 cudaError_t launch_pack_weights(const G4DDeformParams& p, float* w0t, float* const* w1t, cudaStream_t st);

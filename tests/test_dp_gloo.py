@@ -34,7 +34,8 @@ def _worker(rank, world, port, q):
     assert bucket.flat.data_ptr() == flat_ptr and xyz.grad.data_ptr() == flat_ptr     # grads are still views of the bucket
     gn = torch.full((7, 1), float(rank + 1)); den = torch.full((7, 1), 1.0); rad = torch.arange(7, dtype=torch.float32) * (rank + 1)
     dp.allreduce_densification_stats(dist, world, gn, den, rad)
-    q.put((rank, views, xyz.grad.clone(), plane.grad.clone(), w.grad.clone(), gn.clone(), den.clone(), rad.clone()))
+    # plain numpy payloads: torch tensors travel through a queue as shared-memory handles that die with the sender
+    q.put((rank, views) + tuple(x.detach().contiguous().numpy().copy() for x in (xyz.grad, plane.grad, w.grad, gn, den, rad)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -51,6 +52,7 @@ def test_flat_bucket_allreduce_two_ranks():
     for p in procs:
         p.join(30)
         assert p.exitcode == 0
+    res = [t[:2] + tuple(torch.from_numpy(x) for x in t[2:]) for t in res]
     (r0, v0, gx0, gp0, gw0, gn0, den0, rad0), (r1, v1, gx1, gp1, gw1, gn1, den1, rad1) = res
     assert v0 == [0, 2, 4] and v1 == [1, 3, 5]
     # mean over the 6 views of (v+1) = 3.5

@@ -380,6 +380,36 @@ def test_tensor_core_mlp_matches_ffma_path(net, n):
         assert float((x - y).abs().max()) <= 5e-6, (nm, float((x - y).abs().max()))
 
 
+@pytest.mark.parametrize("net,n", [("small128", 700), ("dynerf", 21000), ("hypernerf", 40000)])
+def test_tensor_core_backward_matches_ffma_path(net, n):
+    """BF16x2 tcgen05 backward (dgrad + wgrad kernels) against the FP32 FFMA backward: same gradients for every input
+    and every parameter.  n is chosen so that some CTAs own one tile and others two or three (persistent loop)."""
+    mod = make_module(net, seed=5)
+    ins, probes = _deform_inputs(n, 3)
+    ws = g4d._lib.Workspace.get(0)
+    t = torch.tensor(0.27).repeat(n, 1).cuda()
+    res = []
+    try:
+        for tc in (1, 0):
+            ws.set_option(g4d._lib.OPT_TENSOR_CORES, tc)
+            mod.zero_grad(set_to_none=True)
+            dev_in = [x.clone().requires_grad_(True) for x in ins]
+            outs = mod(*dev_in, t)
+            sum((o * p.cuda()).sum() for o, p in zip(outs, probes)).backward()
+            res.append(([x.grad.clone() for x in dev_in],
+                        {k: p.grad.clone() for k, p in mod.named_parameters() if p.grad is not None}))
+    finally:
+        ws.set_option(g4d._lib.OPT_TENSOR_CORES, 1)
+    (gi_tc, gp_tc), (gi_ff, gp_ff) = res
+    for a, b, nm in zip(gi_tc, gi_ff, ("xyz", "scales", "rot", "opacity", "shs")):
+        e, emax = rel_err_bulk(a.cpu().numpy(), b.cpu().numpy())
+        assert e <= 2e-4 and emax <= 5e-2, (nm, e, emax)
+    assert gp_tc.keys() == gp_ff.keys()
+    for k in gp_ff:
+        e = rel_err(gp_tc[k].cpu().numpy(), gp_ff[k].cpu().numpy())
+        assert e <= 2e-4, (k, e)
+
+
 def test_tight_cull_gives_bit_identical_images_with_fewer_instances():
     """G4D_OPT_TIGHT_CULL drops (Gaussian, tile) pairs whose best alpha over the tile is < 1/255: same pixels, smaller R."""
     cam = synth.make_camera(35.0, 640, 480, radius=2.2, focal=400.0)
