@@ -33,6 +33,13 @@ ABI_SYMBOLS = [
 ]
 
 fp = C.c_void_p   # device pointers travel as integers
+ABI_VERSION = 2
+CAM_DEBUG, CAM_NO_GRAD = 1, 2      # G4DCamera.debug bits
+
+
+def relu_bits_words(n: int) -> int:
+    """G4D_RELU_BITS_WORDS (include/g4d.h)"""
+    return 24 * int(n) + 4
 
 
 class Camera(C.Structure):
@@ -106,16 +113,16 @@ def load():
         lib.g4d_debug_umma.argtypes = [C.c_void_p, C.POINTER(C.c_int), fp, fp, fp, C.c_void_p]
         lib.g4d_debug_tc_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         lib.g4d_deform_forward.argtypes = [C.c_void_p, C.POINTER(DeformParams), C.c_int64] + [fp] * 5 + [C.c_float] + \
-            [fp] * 5 + [C.c_void_p]
+            [fp] * 6 + [C.c_void_p]
         lib.g4d_deform_backward.argtypes = [C.c_void_p, C.POINTER(DeformParams), C.POINTER(DeformGrads), C.c_int64, fp,
-                                            C.c_float] + [fp] * 10 + [C.c_void_p]
+                                            C.c_float] + [fp] * 11 + [C.c_void_p]
         lib.g4d_rasterize_forward.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_int64] + [fp] * 8 + [C.c_void_p]
         lib.g4d_rasterize_backward.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_int64] + [fp] * 12 + [C.c_void_p]
         lib.g4d_render_forward.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(DeformParams), C.POINTER(Gaussians),
                                            fp, fp, fp, C.c_void_p]
         lib.g4d_render_backward.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(DeformParams), C.POINTER(DeformGrads),
                                             C.POINTER(Gaussians), fp, C.POINTER(GaussianGrads), C.c_void_p]
-        if lib.g4d_abi_version() != 1:
+        if lib.g4d_abi_version() != ABI_VERSION:
             raise G4DError("libg4d.so ABI version mismatch")
         _lib = lib
         return lib

@@ -81,7 +81,8 @@ struct G4DWorkspace {
 
 struct G4DContext {
     G4DWorkspace* ws = nullptr;
-    DevBuf cam, geom, bin, img, fused, gscratch, gdeform, trow;
+    DevBuf cam, geom, bin, img, fused, gscratch, gdeform, trow, relu;
+    bool relu_saved = false;
     int64_t n = 0;
     int H = 0, W = 0, grid_x = 0, grid_y = 0;
     int64_t R = 0, capacity = 0;
@@ -229,17 +230,25 @@ int refresh_tc_bwd(G4DWorkspace* ws, const G4DDeformParams* p, cudaStream_t st) 
 // backward of the deformation network: tensor-core path when the configuration allows, FFMA path otherwise
 int deform_backward_dispatch(G4DWorkspace* ws, const DeformDesc& d, const G4DDeformParams* prm, const G4DDeformGrads* grads,
                              float time, int64_t n, const float* xyz, const float* const go[G4D_NUM_HEADS],
-                             float* const gi[G4D_NUM_HEADS], cudaStream_t st) {
+                             float* const gi[G4D_NUM_HEADS], const uint32_t* relu_bits, cudaStream_t st) {
     int rc;
     if (ws->tensor_cores && tc_deform_supported(d)) {
         if ((rc = refresh_tc_bwd(ws, prm, st)) != G4D_OK) return rc;
         G4D_CUDA(ws->scratch.ensure(tc_deform_backward_scratch_bytes(d, n)));
-        G4D_CUDA(launch_deform_backward_tc(d, *prm, *grads, ws->tcbw, time, n, xyz, go, gi, ws->scratch.as<uint8_t>(), ws->sm_count, st));
+        G4D_CUDA(launch_deform_backward_tc(d, *prm, *grads, ws->tcbw, time, n, xyz, go, gi, relu_bits, ws->scratch.as<uint8_t>(), ws->sm_count, st));
         return G4D_OK;
     }
     if ((rc = refresh_packed(ws, prm, st)) != G4D_OK) return rc;
     G4D_CUDA(ws->scratch.ensure(deform_backward_scratch_bytes(d, n)));
     G4D_CUDA(launch_deform_backward(d, *prm, *grads, time, n, xyz, go, gi, ws->scratch.as<float>(), ws->sm_count, st));
+    return G4D_OK;
+}
+
+// ReLU sign bits saved by the tensor-core forward for its backward; the trailing tag word says whether they were written
+constexpr int kReluTagByte = 0x5A;
+int attach_relu_bits(G4DWorkspace* ws, bool use_tc, uint32_t* relu_bits, int64_t n, cudaStream_t st) {
+    ws->tcw.relu_bits = use_tc ? relu_bits : nullptr;
+    if (relu_bits) G4D_CUDA(cudaMemsetAsync(relu_bits + (size_t)24 * (size_t)n, use_tc ? kReluTagByte : 0, 16, st));
     return G4D_OK;
 }
 
@@ -287,7 +296,7 @@ int check_camera(const G4DCamera* cam) {
 }
 
 int debug_sync(const G4DCamera* cam, cudaStream_t st, const char* stage) {
-    if (!cam->debug) return G4D_OK;
+    if (!(cam->debug & G4D_CAM_DEBUG)) return G4D_OK;
     cudaError_t e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(G4D_ERR_CUDA, stage, cudaGetErrorString(e));
@@ -322,7 +331,7 @@ int bin_and_blend(G4DContext* c, const G4DCamera* cam, int64_t n, float* out_col
     int tile_bits = 0;
     while ((1 << tile_bits) < num_tiles) ++tile_bits;
     // no-sync needs a capacity learnt from an earlier (synchronous) forward on this context
-    const bool nosync = !ws->sync_mode && !cam->debug && c->capacity > 0 && c->R > 0 && n > 0;
+    const bool nosync = !ws->sync_mode && !(cam->debug & G4D_CAM_DEBUG) && c->capacity > 0 && c->R > 0 && n > 0;
     if (n > 0) {
         const size_t tb = scan_temp_bytes(n);
         G4D_CUDA(ws->temp.ensure(tb));
@@ -467,7 +476,7 @@ void g4d_context_destroy(G4DContext* c) {
     if (c->ev_created) for (int i = 0; i < 2 * G4D_STAGE_COUNT; ++i) cudaEventDestroy(c->ev[i]);
     if (c->ev_r) cudaEventDestroy(c->ev_r);
     if (c->h_r) cudaFreeHost(c->h_r);
-    c->cam.release(); c->geom.release(); c->bin.release(); c->img.release(); c->fused.release(); c->gscratch.release(); c->gdeform.release();
+    c->cam.release(); c->geom.release(); c->bin.release(); c->img.release(); c->fused.release(); c->gscratch.release(); c->gdeform.release(); c->relu.release();
     c->trow.release();
     delete c;
 }
@@ -517,7 +526,7 @@ int g4d_context_stats(G4DContext* c, G4DStats* out) {
 // ------------------------------------------------------------------------------------------------------
 int g4d_deform_forward(G4DWorkspace* ws, const G4DDeformParams* prm, int64_t n, const float* xyz, const float* scaling,
                        const float* rotation, const float* opacity, const float* shs, float time, float* out_xyz,
-                       float* out_scaling, float* out_rotation, float* out_opacity, float* out_shs, void* stream) {
+                       float* out_scaling, float* out_rotation, float* out_opacity, float* out_shs, uint32_t* relu_bits, void* stream) {
     if (!ws) return fail(G4D_ERR_ARG, "workspace is NULL");
     int rc = check_params(prm);
     if (rc != G4D_OK) return rc;
@@ -535,6 +544,7 @@ int g4d_deform_forward(G4DWorkspace* ws, const G4DDeformParams* prm, int64_t n, 
     const bool use_tc = ws->tensor_cores && tc_deform_supported(d);
     if (use_tc && (rc = refresh_tc(ws, prm, st)) != G4D_OK) return rc;
     if (use_tc && (rc = attach_tc_debug(ws, st)) != G4D_OK) return rc;
+    if ((rc = attach_relu_bits(ws, use_tc, relu_bits, n, st)) != G4D_OK) return rc;
     G4D_CUDA(launch_deform(d, 0, nullptr, time, false, n, xyz, scaling, rotation, opacity, shs, nullptr, nullptr, out_xyz,
                            out_scaling, out_rotation, out_opacity, out_shs, g, fo, nullptr, ws->sm_count, st,
                            use_tc ? &ws->tcw : nullptr));
@@ -666,7 +676,7 @@ int64_t g4d_context_read(G4DContext* c, int which, void* host_dst, int64_t bytes
 int g4d_deform_backward(G4DWorkspace* ws, const G4DDeformParams* prm, G4DDeformGrads* grads, int64_t n, const float* xyz,
                         float time, const float* g_out_xyz, const float* g_out_scaling, const float* g_out_rotation,
                         const float* g_out_opacity, const float* g_out_shs, float* g_in_xyz, float* g_in_scaling,
-                        float* g_in_rotation, float* g_in_opacity, float* g_in_shs, void* stream) {
+                        float* g_in_rotation, float* g_in_opacity, float* g_in_shs, const uint32_t* relu_bits, void* stream) {
     if (!ws) return fail(G4D_ERR_ARG, "workspace is NULL");
     int rc = check_params(prm);
     if (rc != G4D_OK) return rc;
@@ -681,7 +691,7 @@ int g4d_deform_backward(G4DWorkspace* ws, const G4DDeformParams* prm, G4DDeformG
     const DeformDesc d = make_desc(ws, prm, trow);
     const float* go[G4D_NUM_HEADS] = {g_out_xyz, g_out_scaling, g_out_rotation, g_out_opacity, g_out_shs};
     float* gi[G4D_NUM_HEADS] = {g_in_xyz, g_in_scaling, g_in_rotation, g_in_opacity, g_in_shs};
-    return deform_backward_dispatch(ws, d, prm, grads, time, n, xyz, go, gi, st);
+    return deform_backward_dispatch(ws, d, prm, grads, time, n, xyz, go, gi, relu_bits, st);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -724,6 +734,9 @@ int g4d_render_forward(G4DContext* c, const G4DCamera* cam, const G4DDeformParam
         const bool use_tc = ws->tensor_cores && tc_deform_supported(d);
         if (use_tc && (rc = refresh_tc(ws, prm, st)) != G4D_OK) return rc;
         if (use_tc && (rc = attach_tc_debug(ws, st)) != G4D_OK) return rc;
+        c->relu_saved = use_tc && !(cam->debug & G4D_CAM_NO_GRAD);
+        if (c->relu_saved) G4D_CUDA(c->relu.ensure(G4D_RELU_BITS_WORDS(n) * 4));
+        if ((rc = attach_relu_bits(ws, c->relu_saved, c->relu_saved ? c->relu.as<uint32_t>() : nullptr, n, st)) != G4D_OK) return rc;
         G4D_CUDA(launch_deform(d, 1, dcam, cam->time, false, n, g->xyz, g->scaling, g->rotation, g->opacity, shs, dc,
                                g->features_rest, nullptr, nullptr, nullptr, nullptr, nullptr, c->g, c->fo, out_radii,
                                ws->sm_count, st, use_tc ? &ws->tcw : nullptr));
@@ -794,7 +807,7 @@ int g4d_render_backward(G4DContext* c, const G4DCamera* cam, const G4DDeformPara
     float* gi[G4D_NUM_HEADS] = {gg->xyz, gg->scaling, gg->rotation, gg->opacity, nullptr};
     {
         StageTimer tm(c, G4D_STAGE_DEFORM_BWD, st);
-        if ((rc = deform_backward_dispatch(ws, d, prm, pgrads, cam->time, n, g->xyz, go, gi, st)) != G4D_OK) return rc;
+        if ((rc = deform_backward_dispatch(ws, d, prm, pgrads, cam->time, n, g->xyz, go, gi, c->relu_saved ? c->relu.as<uint32_t>() : nullptr, st)) != G4D_OK) return rc;
     }
     return debug_sync(cam, st, "deform_backward");
 }

@@ -162,7 +162,13 @@ __device__ __forceinline__ void sample_features_regs(const DeformDesc* d, const 
     }
 }
 
-template <int MODE, int C, int L>
+// ReLU sign bits of one Gaussian for one layer (slot 0 = hidden, 1 + h = head h): [slot][N] x 128 bits
+__device__ __forceinline__ void store_relu_bits(uint32_t* base, int slot, int64_t n, int64_t gi, uint64_t lo, uint64_t hi) {
+    *reinterpret_cast<uint4*>(base + ((size_t)slot * (size_t)n + (size_t)gi) * 4) =
+        make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+}
+
+template <int MODE, int C, int L, bool SAVE>
 __global__ void __launch_bounds__(256, 1)
 deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restrict__ camp, float time_arg, int use_cam_time,
                  int64_t n, DeformIO io) {
@@ -270,6 +276,7 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
             if (!first) { bar_sync(kBarScratchFree, 256); tc::fence_after_sync(); }   // G has read the previous tile's scratch (A1 region)
             G4D_CYC(3);   // wait scratch free
             // ---- epilogue 0: a1 = relu(D + b0) -> A1 (hi | lo)
+            uint64_t rb0 = 0ull, rb1 = 0ull;   // ReLU sign bits of this row, saved for the backward (bit j <=> pre-activation j > 0)
 #pragma unroll 1
             for (int ch = 0; ch < 8; ++ch) {
                 const uint32_t c0 = (uint32_t)(ch * 16);
@@ -282,11 +289,18 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                     const float4 b4 = *reinterpret_cast<const float4*>(sBias + c0 + j);
                     bb[j] = b4.x; bb[j + 1] = b4.y; bb[j + 2] = b4.z; bb[j + 3] = b4.w;
                 }
+                uint32_t bits = 0;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) tc::tf32_split(fmaxf(__uint_as_float(v[j]) + bb[j], 0.f), hi[j], lo[j]);
+                for (int j = 0; j < 16; ++j) {
+                    const float x = __uint_as_float(v[j]) + bb[j];
+                    if (SAVE && x > 0.f) bits |= 1u << j;
+                    tc::tf32_split(fmaxf(x, 0.f), hi[j], lo[j]);
+                }
+                if (ch < 4) rb0 |= (uint64_t)bits << (ch * 16); else rb1 |= (uint64_t)bits << ((ch - 4) * 16);
                 tc::tmem_st16(lane_base + kColA1Hi + c0, hi);
                 tc::tmem_st16(lane_base + kColA1Lo + c0, lo);
             }
+            if (SAVE && valid) store_relu_bits(tw.relu_bits, 0, n, gi, rb0, rb1);
             tc::wait_st();
             tc::fence_before_sync();
             bar_sync(kBarM, 128);
@@ -331,6 +345,7 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                     //      tensor-core round trips for a 128 x 4 x 128 GEMM
                     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                     const float4* w2 = sW2s + h * 128;
+                    rb0 = rb1 = 0ull;
 #pragma unroll 1
                     for (int ch = 0; ch < 8; ++ch) {
                         uint32_t v[16];
@@ -342,20 +357,26 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                             const float4 b4 = *reinterpret_cast<const float4*>(b1 + ch * 16 + j);
                             bb[j] = b4.x; bb[j + 1] = b4.y; bb[j + 2] = b4.z; bb[j + 3] = b4.w;
                         }
+                        uint32_t bits = 0;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const float a2 = fmaxf(__uint_as_float(v[j]) + bb[j], 0.f);
+                            const float x = __uint_as_float(v[j]) + bb[j];
+                            if (SAVE && x > 0.f) bits |= 1u << j;
+                            const float a2 = fmaxf(x, 0.f);
                             const float4 w = w2[ch * 16 + j];
                             acc.x = fmaf(a2, w.x, acc.x); acc.y = fmaf(a2, w.y, acc.y);
                             acc.z = fmaf(a2, w.z, acc.z); acc.w = fmaf(a2, w.w, acc.w);
                         }
+                        if (ch < 4) rb0 |= (uint64_t)bits << (ch * 16); else rb1 |= (uint64_t)bits << ((ch - 4) * 16);
                     }
+                    if (SAVE && valid) store_relu_bits(tw.relu_bits, 1 + h, n, gi, rb0, rb1);
                     if (h == 0) { dl[0] = acc.x + b2[0]; dl[1] = acc.y + b2[1]; dl[2] = acc.z + b2[2]; }
                     else if (h == 1) { dl[3] = acc.x + b2[0]; dl[4] = acc.y + b2[1]; dl[5] = acc.z + b2[2]; }
                     else if (h == 2) { dl[6] = acc.x + b2[0]; dl[7] = acc.y + b2[1]; dl[8] = acc.z + b2[2]; dl[9] = acc.w + b2[3]; }
                     else { dl[10] = acc.x + b2[0]; }
                     G4D_CYC(8);   // small-head epilogue + fp32 layer 2
                 } else {
+                    rb0 = rb1 = 0ull;
 #pragma unroll 1
                     for (int hh = 0; hh < 2; ++hh) {
                         // hidden half hh: a2 = relu(D[:, 64hh : 64hh+64] + b1) -> X (hi | lo)
@@ -372,11 +393,18 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                                 const float4 b4 = *reinterpret_cast<const float4*>(b1 + cg + j);
                                 bb[j] = b4.x; bb[j + 1] = b4.y; bb[j + 2] = b4.z; bb[j + 3] = b4.w;
                             }
+                            uint32_t bits = 0;
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) tc::tf32_split(fmaxf(__uint_as_float(v[j]) + bb[j], 0.f), hi[j], lo[j]);
+                            for (int j = 0; j < 16; ++j) {
+                                const float x = __uint_as_float(v[j]) + bb[j];
+                                if (SAVE && x > 0.f) bits |= 1u << j;
+                                tc::tf32_split(fmaxf(x, 0.f), hi[j], lo[j]);
+                            }
+                            if (hh == 0) rb0 |= (uint64_t)bits << (ch * 16); else rb1 |= (uint64_t)bits << (ch * 16);
                             tc::tmem_st16(lane_base + kColX + cl, hi);
                             tc::tmem_st16(lane_base + kColXLo + cl, lo);
                         }
+                        if (SAVE && hh == 1 && valid) store_relu_bits(tw.relu_bits, 1 + h, n, gi, rb0, rb1);
                         tc::wait_st();
                         tc::fence_before_sync();
                         bar_sync(kBarM, 128);
@@ -531,9 +559,16 @@ template <int MODE, int C, int L>
 static cudaError_t launch_deform_tc_t(const DeformDesc& d, const TcWeights& tw, const TcSmem& Ls, size_t bytes, int grid,
                                       const CameraDev* cam, float time, bool use_cam_time, int64_t n, const DeformIO& io,
                                       cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(deform_tc_kernel<MODE, C, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) return e;
-    deform_tc_kernel<MODE, C, L><<<grid, 256, bytes, st>>>(d, tw, Ls, cam, time, use_cam_time ? 1 : 0, n, io);
+    cudaError_t e;
+    if (tw.relu_bits) {
+        e = cudaFuncSetAttribute(deform_tc_kernel<MODE, C, L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        deform_tc_kernel<MODE, C, L, true><<<grid, 256, bytes, st>>>(d, tw, Ls, cam, time, use_cam_time ? 1 : 0, n, io);
+    } else {
+        e = cudaFuncSetAttribute(deform_tc_kernel<MODE, C, L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        deform_tc_kernel<MODE, C, L, false><<<grid, 256, bytes, st>>>(d, tw, Ls, cam, time, use_cam_time ? 1 : 0, n, io);
+    }
     return cudaGetLastError();
 }
 

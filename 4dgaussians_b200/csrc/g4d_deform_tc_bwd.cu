@@ -175,6 +175,7 @@ struct BwdADesc {
     float* g_b2[G4D_NUM_HEADS];
     float* g_planes[G4D_MAX_LEVELS][6];
     float* trow_grad[G4D_MAX_LEVELS][3];
+    const uint32_t* relu_bits;   // [6][N][4] + tag (g4d.h G4D_RELU_BITS_WORDS) or NULL
 };
 
 template <int C, int L>
@@ -228,6 +229,14 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
     for (int a = 0; a < 3; ++a) { amax[a] = __ldg(d.aabb + a); ascale[a] = 2.0f / (__ldg(d.aabb + 3 + a) - amax[a]); }
     int nheads = 0;
     for (int h = 0; h < G4D_NUM_HEADS; ++h) nheads += (d.head_mask >> h) & 1;
+    // saved ReLU signs are used when the forward that produced them says so (tag word behind the bits)
+    const bool use_bits = bd.relu_bits && __ldg(bd.relu_bits + (size_t)24 * (size_t)n) == 0x5A5A5A5Au;
+    auto load_bits = [&](int slot, int64_t gi, bool valid, uint64_t& lo, uint64_t& hi) {
+        uint4 m = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) m = __ldg(reinterpret_cast<const uint4*>(bd.relu_bits + ((size_t)slot * (size_t)n + (size_t)gi) * 4));
+        lo = (uint64_t)m.x | ((uint64_t)m.y << 32);
+        hi = (uint64_t)m.z | ((uint64_t)m.w << 32);
+    };
 
     if (is_m) {
         // =========================================== M group ===========================================
@@ -269,6 +278,7 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
             tc::fence_after_sync();
             if (!first) { bar_sync(kBarScratchFree, 256); tc::fence_after_sync(); }   // previous tile's d(feat) scratch (A1 region) consumed
             uint64_t hm0 = 0ull, hm1 = 0ull;   // bit j set <=> hidden[j] > 0
+            if (use_bits) load_bits(0, gi, valid, hm0, hm1);
             uint8_t* img_a1 = bd.img.a1 + (size_t)tile * 2 * kImg128;
 #pragma unroll 1
             for (int ch = 0; ch < 8; ++ch) {
@@ -283,7 +293,12 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
                     if (hpre > 0.f) bits |= 1u << j;
                     a1v[j] = fmaxf(hpre, 0.f);
                 }
-                if (ch < 4) hm0 |= (uint64_t)bits << (ch * 16); else hm1 |= (uint64_t)bits << ((ch - 4) * 16);
+                if (use_bits) {
+                    const uint32_t sb = (uint32_t)((ch < 4 ? hm0 : hm1) >> ((ch & 3) * 16)) & 0xffffu;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) a1v[j] = ((sb >> j) & 1u) ? a1v[j] : 0.f;
+                } else if (ch < 4) hm0 |= (uint64_t)bits << (ch * 16);
+                else hm1 |= (uint64_t)bits << ((ch - 4) * 16);
                 Split16 s;
                 split16(a1v, s);
                 tc::tmem_st8(lane_base + kA1 + ch * 8, s.hi);
@@ -360,6 +375,8 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
                 // ---- wait for z = a1 W1^T
                 mbar_wait(bar_mma, ph_mma); ph_mma ^= 1u;
                 tc::fence_after_sync();
+                uint64_t zm0 = 0ull, zm1 = 0ull;
+                if (use_bits) load_bits(1 + h, gi, valid, zm0, zm1);
                 uint8_t* img_a2 = bd.img.a2[h] + (size_t)tile * 2 * kImg128;
                 uint8_t* img_dz = bd.img.dz[h] + (size_t)tile * 2 * kImg128;
 #pragma unroll 1
@@ -368,14 +385,16 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
                     tc::tmem_ld16(lane_base + kD + ch * 16, v);
                     tc::wait_ld();
                     float a2v[16], dzv[16];
+                    const uint32_t sb = (uint32_t)((ch < 4 ? zm0 : zm1) >> ((ch & 3) * 16)) & 0xffffu;
                     if (h < 4) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const float zc = __uint_as_float(v[j]) + b1[ch * 16 + j];
                             const float4 w = sW2s[h * 128 + ch * 16 + j];
                             const float da2 = dout[0] * w.x + dout[1] * w.y + dout[2] * w.z + dout[3] * w.w;
-                            a2v[j] = fmaxf(zc, 0.f);
-                            dzv[j] = zc > 0.f ? da2 : 0.f;
+                            const bool on = use_bits ? ((sb >> j) & 1u) != 0u : zc > 0.f;
+                            a2v[j] = on ? fmaxf(zc, 0.f) : 0.f;
+                            dzv[j] = on ? da2 : 0.f;
                         }
                     } else {
                         float da2[16];
@@ -394,8 +413,9 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const float zc = __uint_as_float(v[j]) + b1[ch * 16 + j];
-                            a2v[j] = fmaxf(zc, 0.f);
-                            dzv[j] = zc > 0.f ? da2[j] : 0.f;
+                            const bool on = use_bits ? ((sb >> j) & 1u) != 0u : zc > 0.f;
+                            a2v[j] = on ? fmaxf(zc, 0.f) : 0.f;
+                            dzv[j] = on ? da2[j] : 0.f;
                         }
                     }
                     Split16 s;
@@ -730,12 +750,12 @@ static cudaError_t launch_a(const BwdADesc& bd, float time, int64_t n, const flo
 
 cudaError_t launch_deform_backward_tc(const DeformDesc& d, const G4DDeformParams& prm, const G4DDeformGrads& grads,
                                       const TcBwdWeights& w, float time, int64_t n, const float* xyz,
-                                      const float* const go[G4D_NUM_HEADS], float* const gi[G4D_NUM_HEADS], uint8_t* scratch,
-                                      int sm_count, cudaStream_t st) {
+                                      const float* const go[G4D_NUM_HEADS], float* const gi[G4D_NUM_HEADS],
+                                      const uint32_t* relu_bits, uint8_t* scratch, int sm_count, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     const int64_t ntiles = (n + 127) / 128;
     BwdADesc a{};
-    a.d = d; a.w = w;
+    a.d = d; a.w = w; a.relu_bits = relu_bits;
     uint8_t* p = scratch;
     auto take = [&](size_t bytes) { uint8_t* o = p; p += (bytes + 255) & ~(size_t)255; return o; };
     a.img.feat_bytes = 2u * 128 * d.F * 2;

@@ -53,6 +53,7 @@ struct TcWeights {
     const float* w2[G4D_NUM_HEADS];    // packed (hi | lo), [kp16][128]
     int kp16[G4D_NUM_HEADS];
     long long* dbg;                    // optional [grid][12] per-phase cycle counters (debug)
+    uint32_t* relu_bits;               // optional [6][N][4]: ReLU sign bits saved for the backward (G4D_RELU_BITS_WORDS)
 };
 
 size_t tc_packed_floats(const G4DDeformParams& prm);
@@ -69,8 +70,8 @@ cudaError_t launch_tc_bwd_pack_weights(const G4DDeformParams& prm, uint8_t* blob
 size_t tc_deform_backward_scratch_bytes(const DeformDesc& d, int64_t n);
 cudaError_t launch_deform_backward_tc(const DeformDesc& d, const G4DDeformParams& prm, const G4DDeformGrads& grads,
                                       const TcBwdWeights& w, float time, int64_t n, const float* xyz,
-                                      const float* const go[G4D_NUM_HEADS], float* const gi[G4D_NUM_HEADS], uint8_t* scratch,
-                                      int sm_count, cudaStream_t st);
+                                      const float* const go[G4D_NUM_HEADS], float* const gi[G4D_NUM_HEADS],
+                                      const uint32_t* relu_bits, uint8_t* scratch, int sm_count, cudaStream_t st);
 // collapsed time-row gradients -> the two time rows of each (axis, t) plane (g4d_backward.cu)
 cudaError_t launch_distribute_time_grad(const DeformDesc& d, float* const (*trow_grad)[3], float* const (*g_planes)[6], float time,
                                         cudaStream_t st);

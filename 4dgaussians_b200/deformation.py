@@ -146,7 +146,7 @@ class deform_network(nn.Module):
     def forward_dynamic(self, point, scales=None, rotations=None, opacity=None, shs=None, times_sel=None):
         t = scalar_time(times_sel)
         flat = self.flat_parameters()
-        outs = _DeformFunction.apply(self, t, point, scales, rotations, opacity, shs, *flat)
+        outs = _DeformFunction.apply(self, t, torch.is_grad_enabled(), point, scales, rotations, opacity, shs, *flat)
         pts, sc, rot, op, sh = outs
         a = self.args
         # inactive heads hand the input tensor back, exactly like the reference (deformation.py:106-145)
@@ -278,7 +278,7 @@ def _f32c(t: Optional[torch.Tensor], what: str) -> Optional[torch.Tensor]:
 
 class _DeformFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module: deform_network, t: float, xyz, scales, rotations, opacity, shs, *params):
+    def forward(ctx, module: deform_network, t: float, grad_mode: bool, xyz, scales, rotations, opacity, shs, *params):
         lib = _lib.load()
         dev = xyz.device
         n = xyz.shape[0]
@@ -293,12 +293,16 @@ class _DeformFunction(torch.autograd.Function):
         oo = torch.empty_like(o) if o is not None else None
         osh = torch.empty_like(sh) if (sh is not None and (hm & _lib.HEAD_SHS)) else None
         ptr = lambda v: v.data_ptr() if v is not None else None
+        # what autograd would save for the ReLU backward: one sign bit per hidden unit (only when a backward can follow)
+        needs_bwd = grad_mode and any(ctx.needs_input_grad)      # (grad mode is always off INSIDE Function.forward)
+        relu_bits = torch.empty(_lib.relu_bits_words(n), device=dev, dtype=torch.int32) if needs_bwd else None
         with torch.cuda.device(dev):
             ws = _lib.Workspace.get(dev.index if dev.index is not None else torch.cuda.current_device())
             _lib.check(lib.g4d_deform_forward(ws.handle, C.byref(prm), n, ptr(x), ptr(s), ptr(r), ptr(o), ptr(sh), float(t),
-                                              ptr(ox), ptr(os_), ptr(orr), ptr(oo), ptr(osh),
+                                              ptr(ox), ptr(os_), ptr(orr), ptr(oo), ptr(osh), ptr(relu_bits),
                                               int(torch.cuda.current_stream(dev).cuda_stream)), "g4d_deform_forward")
         ctx.module, ctx.t, ctx.n = module, float(t), n
+        ctx.relu_bits = relu_bits
         ctx.save_for_backward(x)
         ctx.has = (s is not None, r is not None, o is not None, sh is not None)
         outs = (ox, os_ if os_ is not None else x.new_zeros(0), orr if orr is not None else x.new_zeros(0),
@@ -336,6 +340,7 @@ class _DeformFunction(torch.autograd.Function):
             ws = _lib.Workspace.get(dev.index if dev.index is not None else torch.cuda.current_device())
             _lib.check(lib.g4d_deform_backward(ws.handle, C.byref(prm), C.byref(cg), n, ptr(x), float(t), ptr(go_x), ptr(go_s),
                                                ptr(go_r), ptr(go_o), ptr(go_sh), ptr(gi_x), ptr(gi_s), ptr(gi_r), ptr(gi_o),
-                                               ptr(gi_sh), int(torch.cuda.current_stream(dev).cuda_stream)),
-                       "g4d_deform_backward")
-        return (None, None, gi_x, gi_s, gi_r, gi_o, gi_sh) + tuple(pgrads)
+                                               ptr(gi_sh), ptr(ctx.relu_bits),
+                                               int(torch.cuda.current_stream(dev).cuda_stream)), "g4d_deform_backward")
+        ctx.relu_bits = None
+        return (None, None, None, gi_x, gi_s, gi_r, gi_o, gi_sh) + tuple(pgrads)

@@ -42,7 +42,7 @@ class _FusedRender(torch.autograd.Function):
     """inputs: xyz, scaling, rotation, opacity, features_dc, features_rest, means2D, *deform parameters"""
 
     @staticmethod
-    def forward(ctx, module: Optional[deform_network], rs, t, xyz, scaling, rotation, opacity, f_dc, f_rest, means2D, *params):
+    def forward(ctx, module: Optional[deform_network], rs, t, grad_mode, xyz, scaling, rotation, opacity, f_dc, f_rest, means2D, *params):
         lib = _lib.load()
         dev = xyz.device
         n = xyz.shape[0]
@@ -54,6 +54,8 @@ class _FusedRender(torch.autograd.Function):
         radii = torch.empty(n, device=dev, dtype=torch.int32)
         keep = []
         cam = camera_from_settings(rs, time=t, keep=keep)
+        if not (grad_mode and any(ctx.needs_input_grad)):      # (grad mode is always off INSIDE Function.forward)
+            cam.debug |= _lib.CAM_NO_GRAD      # torch.no_grad() rendering: nothing is saved for a backward
         prm = module.c_params(keep) if module is not None else None
         g = _lib.Gaussians(n, x.data_ptr(), s.data_ptr(), r.data_ptr(), o.data_ptr(), dc.data_ptr(), rest.data_ptr())
         with torch.cuda.device(dev):
@@ -94,7 +96,7 @@ class _FusedRender(torch.autograd.Function):
                                                C.byref(gg), _stream_ptr(dev)), "g4d_render_backward")
         lease.release()
         ctx.lease = None
-        return (None, None, None, gx, gs, gr, go, gdc, grest, gm2) + tuple(pgrads)
+        return (None, None, None, None, gx, gs, gr, go, gdc, grest, gm2) + tuple(pgrads)
 
 
 def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None, stage="fine",
@@ -118,7 +120,7 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
         raise NotImplementedError
     if module is None or isinstance(module, deform_network):
         params = tuple(module.flat_parameters()) if module is not None else ()
-        rendered_image, radii, depth = _FusedRender.apply(module, rs, t, xyz, pc._scaling, pc._rotation, pc._opacity,
+        rendered_image, radii, depth = _FusedRender.apply(module, rs, t, torch.is_grad_enabled(), xyz, pc._scaling, pc._rotation, pc._opacity,
                                                           pc._features_dc, pc._features_rest, screenspace_points, *params)
     else:
         # a foreign (e.g. the reference's own PyTorch) deformation module: keep its semantics, still rasterize with g4d

@@ -34,7 +34,9 @@
 extern "C" {
 #endif
 
-#define G4D_ABI_VERSION 1
+#define G4D_ABI_VERSION 2
+#define G4D_CAM_DEBUG 1
+#define G4D_CAM_NO_GRAD 2
 #define G4D_MAX_LEVELS 4
 #define G4D_NUM_HEADS 5 /* pos, scales, rotations, opacity, shs (scene/deformation.py:61-65) */
 
@@ -57,7 +59,9 @@ typedef struct G4DContext G4DContext;     /* state one forward keeps for its bac
 typedef struct G4DCamera {
     int32_t image_height, image_width;
     int32_t sh_degree; /* active SH degree 0..3 */
-    int32_t debug;     /* !=0: synchronise + check after every stage (settings.debug) */
+    int32_t debug;     /* bit 0: synchronise + check after every stage (settings.debug);
+                        * bit 1 (G4D_CAM_NO_GRAD): no backward will follow this forward (torch.no_grad rendering):
+                        *        g4d_render_forward skips saving state that only the backward reads */
     float tanfovx, tanfovy, scale_modifier;
     float time;        /* viewpoint_camera.time; ignored by the plain rasterizer entry points */
     float viewmatrix[16]; /* world_view_transform, row-vector convention (scene/cameras.py:59) */
@@ -131,14 +135,19 @@ int g4d_context_stats(G4DContext *ctx, G4DStats *out);
 int g4d_deform_forward(G4DWorkspace *ws, const G4DDeformParams *prm, int64_t n, const float *xyz,
                        const float *scaling, const float *rotation, const float *opacity, const float *shs,
                        float time, float *out_xyz, float *out_scaling, float *out_rotation, float *out_opacity,
-                       float *out_shs, void *stream);
+                       float *out_shs, uint32_t *relu_bits, void *stream);
 /* g_out_* are dL/d(outputs) (NULL = zero).  g_in_* are OVERWRITTEN with dL/d(inputs) including the
- * residual path; weight/plane gradients are ACCUMULATED into `grads`. */
+ * residual path; weight/plane gradients are ACCUMULATED into `grads`.
+ * relu_bits (optional, G4D_RELU_BITS_WORDS(n) uint32 of device memory): what autograd would save for the
+ * backward of the six ReLUs (deformation.py:85-148) -- one sign bit per hidden unit, written by the forward,
+ * read by the backward, so that the gradient is the gradient of the forward that actually ran.  NULL on
+ * either side: the backward derives the signs from its own recomputation of the pre-activations. */
 int g4d_deform_backward(G4DWorkspace *ws, const G4DDeformParams *prm, G4DDeformGrads *grads, int64_t n,
                         const float *xyz, float time, const float *g_out_xyz, const float *g_out_scaling,
                         const float *g_out_rotation, const float *g_out_opacity, const float *g_out_shs,
                         float *g_in_xyz, float *g_in_scaling, float *g_in_rotation, float *g_in_opacity,
-                        float *g_in_shs, void *stream);
+                        float *g_in_shs, const uint32_t *relu_bits, void *stream);
+#define G4D_RELU_BITS_WORDS(n) ((size_t)24 * (size_t)(n) + 4) /* [6 layers][n][4 words] + validity tag */
 
 /* ---- rasterizer (drop-in for GaussianRasterizer) ------------------------------------------------
  * Inputs are POST-activation (scales = exp, rotations normalised, opacities = sigmoid), shs [N,16,3].

@@ -171,7 +171,7 @@ def test_deform_forward_vs_reference_golden(name):
             assert float((o.cpu() - torch.from_numpy(z[f"t{ti}_{nm}"])).abs().max()) <= 3e-5, (name, nm)
 
 
-@pytest.mark.parametrize("net,n", [("small64", 700), ("small128", 517), ("dynerf", 1500), ("dnerf", 1300)])
+@pytest.mark.parametrize("net,n", [("small64", 700), ("small128", 517), ("dynerf", 1500), ("dnerf", 1300), ("hypernerf", 2050)])
 def test_deform_backward_vs_oracle(net, n):
     t = 0.61
     mod = make_module(net, seed=4)
@@ -405,9 +405,14 @@ def test_tensor_core_backward_matches_ffma_path(net, n):
         e, emax = rel_err_bulk(a.cpu().numpy(), b.cpu().numpy())
         assert e <= 2e-4 and emax <= 5e-2, (nm, e, emax)
     assert gp_tc.keys() == gp_ff.keys()
+    # the FFMA backward re-derives the ReLU signs from its own fp32 recomputation while the tensor-core backward uses the
+    # signs its forward saved: a unit whose pre-activation is within rounding of 0 may differ, which moves the norm-wise
+    # error by ~1/sqrt(n) per such unit; the element-wise bulk must agree to BF16x2 accuracy
     for k in gp_ff:
-        e = rel_err(gp_tc[k].cpu().numpy(), gp_ff[k].cpu().numpy())
-        assert e <= 2e-4, (k, e)
+        a, b = gp_tc[k].cpu().numpy(), gp_ff[k].cpu().numpy()
+        e = rel_err(a, b)
+        eb, _ = rel_err_bulk(a, b)
+        assert e <= 3 * GRAD_TOL and eb <= 2e-4, (k, e, eb)
 
 
 def test_tight_cull_gives_bit_identical_images_with_fewer_instances():
