@@ -129,6 +129,8 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (the version banner goes to stdout)
         dist.init_process_group("nccl", device_id=dev)
     g4d, synth, w, scene, mod = build_scene(dev)
     lib = g4d._lib
