@@ -21,7 +21,7 @@ namespace g4d {
 namespace {
 
 constexpr uint32_t kA1 = 0, kA1Lo = 64, kD = 128, kDZ = 256, kDZLo = 320, kDA1 = 384;   // TMEM columns (kernel A)
-constexpr int kBarFeat = 1, kBarXFree = 2, kBarScratch = 3, kBarScratchFree = 4, kBarM = 5;
+constexpr int kBarFeat = 1, kBarXFree = 2, kBarScratch = 3, kBarScratchFree = 4, kBarM = 5, kBarE = 6;
 constexpr uint32_t kImg128 = 128u * 128u * 2u;   // bytes of one 128x128 bf16 part (hi or lo)
 
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -198,7 +198,7 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
     float4* sW2s = reinterpret_cast<float4*>(smem + Ls.w2s);           // small heads: (W2[0][j], W2[1][j], W2[2][j], W2[3][j])
     float* sW2sh = reinterpret_cast<float*>(smem + Ls.w2sh);           // SH head: W2 [48][128] fp32
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Ls.bars);
-    uint64_t *bar_w0 = bars, *bar_w1 = bars + 1 /* [2] */, *bar_mma = bars + 3, *bar_da1 = bars + 4;
+    uint64_t *bar_w0 = bars, *bar_w1 = bars + 1 /* [2] */, *bar_mma = bars + 3, *bar_da1 = bars + 4, *bar_l1 = bars + 5;
     const bool hsh = d.head_mask & G4D_HEAD_SHS;
     for (int i = tid; i < 128; i += 256) sBias[i] = __ldg(d.b0 + i);
     for (int h = 0; h < G4D_NUM_HEADS; ++h) {
@@ -215,7 +215,7 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
     }
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, tc::kTmemCols);
     if (tid == 0) {
-        mbar_init(bar_w0, 1); mbar_init(bar_w1, 1); mbar_init(bar_w1 + 1, 1); mbar_init(bar_mma, 1); mbar_init(bar_da1, 1);
+        mbar_init(bar_w0, 1); mbar_init(bar_w1, 1); mbar_init(bar_w1 + 1, 1); mbar_init(bar_mma, 1); mbar_init(bar_da1, 1); mbar_init(bar_l1, 1);
         fence_barrier_init();
     }
     tc::fence_before_sync();
@@ -238,35 +238,111 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
         hi = (uint64_t)m.z | ((uint64_t)m.w << 32);
     };
 
-    if (is_m) {
-        // =========================================== M group ===========================================
-        // W1 images are double-buffered: head number k (in issue order over the whole kernel) uses buffer k & 1
-        auto load_w1 = [&](int h, int buf) {
-            mbar_expect_tx(bar_w1 + buf, 2u * kImg128);
-            tma_bulk_g2s(smem + Ls.w1 + buf * 2u * kImg128, bd.w.w1[h], 2u * kImg128, bar_w1 + buf);
-        };
-        // the k-th (tile, head) pair this CTA processes uses W1 buffer k & 1; pair k + 2 is loaded when pair k retires
-        auto nth_head = [&](int idx) {
-            int m = d.head_mask;
-            for (int i = 0; i < idx; ++i) m &= m - 1;
-            return __ffs(m) - 1;
-        };
-        const int first_h = __ffs(d.head_mask) - 1;
-        const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-        const int64_t total_uses = my_tiles * nheads;
-        if (issuer) {
-            mbar_expect_tx(bar_w0, 2u * 128 * F * 2);
-            tma_bulk_g2s(smem + Ls.w0, bd.w.w0, 2u * 128 * F * 2, bar_w0);
-            load_w1(first_h, 0);
-            if (total_uses > 1) load_w1(nth_head(1 % nheads), 1);
+    // W1 images are double-buffered: the k-th (tile, head) pair this CTA processes uses buffer k & 1; pair k + 2 is loaded
+    // when pair k retires
+    auto load_w1 = [&](int h, int buf) {
+        mbar_expect_tx(bar_w1 + buf, 2u * kImg128);
+        tma_bulk_g2s(smem + Ls.w1 + buf * 2u * kImg128, bd.w.w1[h], 2u * kImg128, bar_w1 + buf);
+    };
+    auto nth_head = [&](int idx) {
+        int m = d.head_mask;
+        for (int i = 0; i < idx; ++i) m &= m - 1;
+        return __ffs(m) - 1;
+    };
+    const int first_h = __ffs(d.head_mask) - 1;
+    const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const int64_t total_uses = my_tiles * nheads;
+    if (issuer) {
+        mbar_expect_tx(bar_w0, 2u * 128 * F * 2);
+        tma_bulk_g2s(smem + Ls.w0, bd.w.w0, 2u * 128 * F * 2, bar_w0);
+        load_w1(first_h, 0);
+        if (total_uses > 1) load_w1(nth_head(1 % nheads), 1);
+    }
+    if (is_m) mbar_wait(bar_w0, 0);
+    uint32_t ph_w1_0 = 0, ph_w1_1 = 0, ph_mma = 0, ph_l1 = 0, ph_da1 = 0;
+    int64_t seq = 0;      // running (tile, head) counter -> W1 buffer
+    // head epilogues are shared: the G group takes column chunks [0, kGChunks), the M group the rest
+    constexpr int kGChunks = 4;
+    const int ch_lo = is_m ? kGChunks : 0, ch_hi = is_m ? 8 : kGChunks;
+
+    // ---- G-group helpers -------------------------------------------------------------------------------------
+    float feat[F];
+    float pcs[3] = {0.f, 0.f, 0.f};
+    auto sample_tile = [&](int64_t tl) {
+        const int64_t gs = tl * 128 + row;
+        pcs[0] = pcs[1] = pcs[2] = 0.f;
+        if (gs < n) {
+            pcs[0] = (xyz[3 * gs] - amax[0]) * ascale[0] - 1.0f;
+            pcs[1] = (xyz[3 * gs + 1] - amax[1]) * ascale[1] - 1.0f;
+            pcs[2] = (xyz[3 * gs + 2] - amax[2]) * ascale[2] - 1.0f;
         }
-        mbar_wait(bar_w0, 0);
-        uint32_t ph_w1_0 = 0, ph_w1_1 = 0, ph_mma = 0, ph_da1 = 0;
-        int64_t seq = 0;      // running (tile, head) counter -> W1 buffer
-        bool first = true;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
-            const int64_t gi = tile * 128 + row;
-            const bool valid = gi < n;
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            Tap1D tx[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) tx[a] = make_tap(pcs[a], sd.res[l][a]);
+#pragma unroll
+            for (int v = 0; v < C4; ++v) {
+                float4 prod = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const int c0 = plane_axis0(k), c1 = plane_axis1(k);
+                    float4 sv;
+                    if (c1 == 3) {
+                        const float4* rowp = reinterpret_cast<const float4*>(sd.trow[l][c0]);
+                        const float4 r0 = __ldg(rowp + tx[c0].i0 * C4 + v), r1 = __ldg(rowp + tx[c0].i1 * C4 + v);
+                        const float w0 = tx[c0].w0, w1 = tx[c0].w1;
+                        sv = make_float4(fmaf(r1.x, w1, r0.x * w0), fmaf(r1.y, w1, r0.y * w0), fmaf(r1.z, w1, r0.z * w0), fmaf(r1.w, w1, r0.w * w0));
+                    } else {
+                        const int W = sd.res[l][c0];
+                        const float4* pl = reinterpret_cast<const float4*>(sd.planes[l][k]);
+                        const Tap1D &X = tx[c0], &Y = tx[c1];
+                        const float4 nw = __ldg(pl + (Y.i0 * W + X.i0) * C4 + v), ne = __ldg(pl + (Y.i0 * W + X.i1) * C4 + v);
+                        const float4 sw = __ldg(pl + (Y.i1 * W + X.i0) * C4 + v), se = __ldg(pl + (Y.i1 * W + X.i1) * C4 + v);
+                        const float wnw = X.w0 * Y.w0, wne = X.w1 * Y.w0, wsw = X.w0 * Y.w1, wse = X.w1 * Y.w1;
+                        sv = make_float4(fmaf(se.x, wse, fmaf(sw.x, wsw, fmaf(ne.x, wne, nw.x * wnw))),
+                                         fmaf(se.y, wse, fmaf(sw.y, wsw, fmaf(ne.y, wne, nw.y * wnw))),
+                                         fmaf(se.z, wse, fmaf(sw.z, wsw, fmaf(ne.z, wne, nw.z * wnw))),
+                                         fmaf(se.w, wse, fmaf(sw.w, wsw, fmaf(ne.w, wne, nw.w * wnw))));
+                    }
+                    prod.x *= sv.x; prod.y *= sv.y; prod.z *= sv.z; prod.w *= sv.w;
+                }
+                feat[l * C + 4 * v + 0] = prod.x; feat[l * C + 4 * v + 1] = prod.y;
+                feat[l * C + 4 * v + 2] = prod.z; feat[l * C + 4 * v + 3] = prod.w;
+            }
+        }
+    };
+    // features -> A operand of layer 0 (DZ region of TMEM) + FEAT image (operand of dW0)
+    auto write_features = [&](int64_t tl) {
+        uint8_t* img_f = bd.img.feat + (size_t)tl * bd.img.feat_bytes;
+#pragma unroll
+        for (int c0 = 0; c0 < F; c0 += 16) {
+            float x[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = feat[c0 + j];
+            Split16 s;
+            split16(x, s);
+            tc::tmem_st8(lane_base + kDZ + (c0 >> 1), s.hi);
+            tc::tmem_st8(lane_base + kDZLo + (c0 >> 1), s.lo);
+            store_img16(img_f, 128u * F * 2u, (uint32_t)F, (uint32_t)row, (uint32_t)c0, s);
+        }
+        tc::wait_st();
+        tc::fence_before_sync();
+        bar_arrive(kBarFeat, 256);
+    };
+    if (!is_m && blockIdx.x < ntiles) {
+        sample_tile(blockIdx.x);
+        write_features(blockIdx.x);
+    }
+
+    bool first = true;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
+        const int64_t gi = tile * 128 + row;
+        const bool valid = gi < n;
+        const bool has_next = tile + gridDim.x < ntiles;
+        uint64_t hm0 = 0ull, hm1 = 0ull;   // (M) bit j set <=> hidden[j] > 0
+        float my_pcs[3] = {pcs[0], pcs[1], pcs[2]};   // (G) coordinates of THIS tile's Gaussian (pcs moves on to the next tile)
+        if (is_m) {
             // ---- layer 0 recompute: D = feat W0^T
             bar_sync(kBarFeat, 256);
             if (issuer) {
@@ -277,7 +353,6 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
             mbar_wait(bar_mma, ph_mma); ph_mma ^= 1u;
             tc::fence_after_sync();
             if (!first) { bar_sync(kBarScratchFree, 256); tc::fence_after_sync(); }   // previous tile's d(feat) scratch (A1 region) consumed
-            uint64_t hm0 = 0ull, hm1 = 0ull;   // bit j set <=> hidden[j] > 0
             if (use_bits) load_bits(0, gi, valid, hm0, hm1);
             uint8_t* img_a1 = bd.img.a1 + (size_t)tile * 2 * kImg128;
 #pragma unroll 1
@@ -308,151 +383,154 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
             tc::wait_st();
             tc::fence_before_sync();
             bar_sync(kBarM, 128);
-            bool da1_started = false;
             // ---- first layer-1 GEMM of the tile
-            int h = first_h;
+            const int buf = (int)(seq & 1);
+            if (buf == 0) { mbar_wait(bar_w1, ph_w1_0); ph_w1_0 ^= 1u; } else { mbar_wait(bar_w1 + 1, ph_w1_1); ph_w1_1 ^= 1u; }
+            if (issuer) {
+                tc::fence_after_sync();
+                const uint32_t w = sW1 + buf * 2u * kImg128;
+                gemm_bf16x2_ts<128>(tbase + kD, tbase + kA1, tbase + kA1Lo, w, w + kImg128, 128, 128, false, false);
+                tc::umma_commit(bar_l1);
+            }
+        }
+
+        // ================= heads: both groups, column chunks split =================
+        bool da1_started = false;
+        int h = first_h;
+#pragma unroll 1
+        for (int hc = 0; hc < nheads; ++hc) {
+            const int buf = (int)(seq & 1);
+            const float* b1 = sBias + 128 + h * 128;
+            const int ko = head_out(h);
+            int next_h = -1;
             {
-                const int buf = (int)(seq & 1);
-                if (buf == 0) { mbar_wait(bar_w1, ph_w1_0); ph_w1_0 ^= 1u; } else { mbar_wait(bar_w1 + 1, ph_w1_1); ph_w1_1 ^= 1u; }
-                if (issuer) {
-                    tc::fence_after_sync();
-                    const uint32_t w = sW1 + buf * 2u * kImg128;
-                    gemm_bf16x2_ts<128>(tbase + kD, tbase + kA1, tbase + kA1Lo, w, w + kImg128, 128, 128, false, false);
-                    tc::umma_commit(bar_mma);
+                const int later = d.head_mask >> (h + 1);
+                if (later) next_h = h + 1 + (__ffs(later) - 1);
+            }
+            // my row of dL/d(out_h)
+            float dout[48];
+#pragma unroll
+            for (int o = 0; o < 48; ++o) dout[o] = 0.f;
+            if (valid && bd.go[h]) {
+                const float* gp = bd.go[h] + gi * ko;
+                if (h == 4) {
+#pragma unroll
+                    for (int o = 0; o < 48; o += 4) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(gp + o);
+                        dout[o] = t4.x; dout[o + 1] = t4.y; dout[o + 2] = t4.z; dout[o + 3] = t4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int o = 0; o < 4; ++o)
+                        if (o < ko) dout[o] = gp[o];
                 }
             }
-#pragma unroll 1
-            for (int hc = 0; hc < nheads; ++hc) {
-                const int buf = (int)(seq & 1);
-                const float* b1 = sBias + 128 + h * 128;
-                const int ko = head_out(h);
-                int next_h = -1;
-                {
-                    const int later = d.head_mask >> (h + 1);
-                    if (later) next_h = h + 1 + (__ffs(later) - 1);
-                }
-                // my row of dL/d(out_h)
-                float dout[48];
-#pragma unroll
-                for (int o = 0; o < 48; ++o) dout[o] = 0.f;
-                if (valid && bd.go[h]) {
-                    const float* gp = bd.go[h] + gi * ko;
-                    if (h == 4) {
-#pragma unroll
-                        for (int o = 0; o < 48; o += 4) {
-                            const float4 t4 = *reinterpret_cast<const float4*>(gp + o);
-                            dout[o] = t4.x; dout[o + 1] = t4.y; dout[o + 2] = t4.z; dout[o + 3] = t4.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int o = 0; o < 4; ++o)
-                            if (o < ko) dout[o] = gp[o];
-                    }
-                }
+            if (is_m) {
                 // DOUT image (operand of dW2) and db2 (warp-shuffle column sums)
-                {
-                    const uint32_t kp16 = (h == 4) ? 48u : 16u;
-                    uint8_t* img = bd.img.dout[h] + (size_t)tile * 2 * 128 * kp16 * 2;
+                const uint32_t kp16 = (h == 4) ? 48u : 16u;
+                uint8_t* img = bd.img.dout[h] + (size_t)tile * 2 * 128 * kp16 * 2;
 #pragma unroll
-                    for (int c0 = 0; c0 < 48; c0 += 16) {
-                        if (c0 > 0 && h != 4) break;
-                        float x[16];
+                for (int c0 = 0; c0 < 48; c0 += 16) {
+                    if (c0 > 0 && h != 4) break;
+                    float x[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) x[j] = dout[c0 + j];
-                        Split16 s;
-                        split16(x, s);
-                        store_img16(img, 128u * kp16 * 2u, kp16, (uint32_t)row, (uint32_t)c0, s);
-                    }
-#pragma unroll
-                    for (int o = 0; o < 48; ++o) {
-                        if (o >= ko) break;
-                        float s = dout[o];
-#pragma unroll
-                        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-                        if ((tid & 31) == 0) atomicAdd(bd.g_b2[h] + o, s);
-                    }
-                }
-                // ---- wait for z = a1 W1^T
-                mbar_wait(bar_mma, ph_mma); ph_mma ^= 1u;
-                tc::fence_after_sync();
-                uint64_t zm0 = 0ull, zm1 = 0ull;
-                if (use_bits) load_bits(1 + h, gi, valid, zm0, zm1);
-                uint8_t* img_a2 = bd.img.a2[h] + (size_t)tile * 2 * kImg128;
-                uint8_t* img_dz = bd.img.dz[h] + (size_t)tile * 2 * kImg128;
-#pragma unroll 1
-                for (int ch = 0; ch < 8; ++ch) {
-                    uint32_t v[16];
-                    tc::tmem_ld16(lane_base + kD + ch * 16, v);
-                    tc::wait_ld();
-                    float a2v[16], dzv[16];
-                    const uint32_t sb = (uint32_t)((ch < 4 ? zm0 : zm1) >> ((ch & 3) * 16)) & 0xffffu;
-                    if (h < 4) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float zc = __uint_as_float(v[j]) + b1[ch * 16 + j];
-                            const float4 w = sW2s[h * 128 + ch * 16 + j];
-                            const float da2 = dout[0] * w.x + dout[1] * w.y + dout[2] * w.z + dout[3] * w.w;
-                            const bool on = use_bits ? ((sb >> j) & 1u) != 0u : zc > 0.f;
-                            a2v[j] = on ? fmaxf(zc, 0.f) : 0.f;
-                            dzv[j] = on ? da2 : 0.f;
-                        }
-                    } else {
-                        float da2[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) da2[j] = 0.f;
-#pragma unroll 4
-                        for (int o = 0; o < 48; ++o) {
-                            const float* wr = sW2sh + o * 128 + ch * 16;
-#pragma unroll
-                            for (int j = 0; j < 16; j += 4) {
-                                const float4 w = *reinterpret_cast<const float4*>(wr + j);
-                                da2[j] = fmaf(dout[o], w.x, da2[j]); da2[j + 1] = fmaf(dout[o], w.y, da2[j + 1]);
-                                da2[j + 2] = fmaf(dout[o], w.z, da2[j + 2]); da2[j + 3] = fmaf(dout[o], w.w, da2[j + 3]);
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float zc = __uint_as_float(v[j]) + b1[ch * 16 + j];
-                            const bool on = use_bits ? ((sb >> j) & 1u) != 0u : zc > 0.f;
-                            a2v[j] = on ? fmaxf(zc, 0.f) : 0.f;
-                            dzv[j] = on ? da2[j] : 0.f;
-                        }
-                    }
+                    for (int j = 0; j < 16; ++j) x[j] = dout[c0 + j];
                     Split16 s;
-                    split16(a2v, s);
-                    store_img16(img_a2, kImg128, 128, (uint32_t)row, (uint32_t)(ch * 16), s);
-                    split16(dzv, s);
-                    store_img16(img_dz, kImg128, 128, (uint32_t)row, (uint32_t)(ch * 16), s);
-                    tc::tmem_st8(lane_base + kDZ + ch * 8, s.hi);
-                    tc::tmem_st8(lane_base + kDZLo + ch * 8, s.lo);
+                    split16(x, s);
+                    store_img16(img, 128u * kp16 * 2u, kp16, (uint32_t)row, (uint32_t)c0, s);
                 }
-                tc::wait_st();
-                tc::fence_before_sync();
-                bar_sync(kBarM, 128);
-                // ---- d(a1) += dz W1 (W1 image read MN-major), then the next head's layer 1 straight behind it
-                if (issuer) {
-                    tc::fence_after_sync();
-                    const uint32_t w = sW1 + buf * 2u * kImg128;
-                    gemm_bf16x2_ts<128>(tbase + kDA1, tbase + kDZ, tbase + kDZLo, w, w + kImg128, 128, 128, true, da1_started);
-                    tc::umma_commit(bar_da1);
+#pragma unroll
+                for (int o = 0; o < 48; ++o) {
+                    if (o >= ko) break;
+                    float s = dout[o];
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                    if ((tid & 31) == 0) atomicAdd(bd.g_b2[h] + o, s);
                 }
-                da1_started = true;
-                ++seq;
-                if (next_h >= 0) {
-                    const int nbuf = (int)(seq & 1);
-                    if (nbuf == 0) { mbar_wait(bar_w1, ph_w1_0); ph_w1_0 ^= 1u; } else { mbar_wait(bar_w1 + 1, ph_w1_1); ph_w1_1 ^= 1u; }
-                    if (issuer) {
-                        const uint32_t w = sW1 + nbuf * 2u * kImg128;
-                        gemm_bf16x2_ts<128>(tbase + kD, tbase + kA1, tbase + kA1Lo, w, w + kImg128, 128, 128, false, false);
-                        tc::umma_commit(bar_mma);
+            }
+            uint64_t zm0 = 0ull, zm1 = 0ull;
+            if (use_bits) load_bits(1 + h, gi, valid, zm0, zm1);
+            // ---- wait for z = a1 W1^T
+            mbar_wait(bar_l1, ph_l1); ph_l1 ^= 1u;
+            tc::fence_after_sync();
+            uint8_t* img_a2 = bd.img.a2[h] + (size_t)tile * 2 * kImg128;
+            uint8_t* img_dz = bd.img.dz[h] + (size_t)tile * 2 * kImg128;
+#pragma unroll 1
+            for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                uint32_t v[16];
+                tc::tmem_ld16(lane_base + kD + ch * 16, v);
+                tc::wait_ld();
+                float a2v[16], dzv[16];
+                const uint32_t sb = (uint32_t)((ch < 4 ? zm0 : zm1) >> ((ch & 3) * 16)) & 0xffffu;
+                if (h < 4) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float zc = __uint_as_float(v[j]) + b1[ch * 16 + j];
+                        const float4 w = sW2s[h * 128 + ch * 16 + j];
+                        const float da2 = dout[0] * w.x + dout[1] * w.y + dout[2] * w.z + dout[3] * w.w;
+                        const bool on = use_bits ? ((sb >> j) & 1u) != 0u : zc > 0.f;
+                        a2v[j] = on ? fmaxf(zc, 0.f) : 0.f;
+                        dzv[j] = on ? da2 : 0.f;
+                    }
+                } else {
+                    float da2[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) da2[j] = 0.f;
+#pragma unroll 4
+                    for (int o = 0; o < 48; ++o) {
+                        const float* wr = sW2sh + o * 128 + ch * 16;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 w = *reinterpret_cast<const float4*>(wr + j);
+                            da2[j] = fmaf(dout[o], w.x, da2[j]); da2[j + 1] = fmaf(dout[o], w.y, da2[j + 1]);
+                            da2[j + 2] = fmaf(dout[o], w.z, da2[j + 2]); da2[j + 3] = fmaf(dout[o], w.w, da2[j + 3]);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float zc = __uint_as_float(v[j]) + b1[ch * 16 + j];
+                        const bool on = use_bits ? ((sb >> j) & 1u) != 0u : zc > 0.f;
+                        a2v[j] = on ? fmaxf(zc, 0.f) : 0.f;
+                        dzv[j] = on ? da2[j] : 0.f;
                     }
                 }
-                // the dz W1 chain has retired: DZ may be overwritten, and W1 buffer `buf` takes the pair after next
-                mbar_wait(bar_da1, ph_da1); ph_da1 ^= 1u;
-                tc::fence_after_sync();
-                if (issuer && seq + 1 < total_uses) load_w1(nth_head((int)((seq + 1) % nheads)), buf);
-                h = next_h;
+                Split16 s;
+                split16(a2v, s);
+                store_img16(img_a2, kImg128, 128, (uint32_t)row, (uint32_t)(ch * 16), s);
+                split16(dzv, s);
+                store_img16(img_dz, kImg128, 128, (uint32_t)row, (uint32_t)(ch * 16), s);
+                tc::tmem_st8(lane_base + kDZ + ch * 8, s.hi);
+                tc::tmem_st8(lane_base + kDZLo + ch * 8, s.lo);
             }
+            tc::wait_st();
+            tc::fence_before_sync();
+            bar_sync(kBarE, 256);
+            // ---- d(a1) += dz W1 (W1 image read MN-major), then the next head's layer 1 straight behind it
+            if (issuer) {
+                tc::fence_after_sync();
+                const uint32_t w = sW1 + buf * 2u * kImg128;
+                gemm_bf16x2_ts<128>(tbase + kDA1, tbase + kDZ, tbase + kDZLo, w, w + kImg128, 128, 128, true, da1_started);
+                tc::umma_commit(bar_da1);
+            }
+            da1_started = true;
+            ++seq;
+            if (next_h >= 0 && is_m) {
+                const int nbuf = (int)(seq & 1);
+                if (nbuf == 0) { mbar_wait(bar_w1, ph_w1_0); ph_w1_0 ^= 1u; } else { mbar_wait(bar_w1 + 1, ph_w1_1); ph_w1_1 ^= 1u; }
+                if (issuer) {
+                    const uint32_t w = sW1 + nbuf * 2u * kImg128;
+                    gemm_bf16x2_ts<128>(tbase + kD, tbase + kA1, tbase + kA1Lo, w, w + kImg128, 128, 128, false, false);
+                    tc::umma_commit(bar_l1);
+                }
+            }
+            // the dz W1 chain has retired: DZ may be overwritten, and W1 buffer `buf` takes the pair after next
+            mbar_wait(bar_da1, ph_da1); ph_da1 ^= 1u;
+            tc::fence_after_sync();
+            if (issuer && seq + 1 < total_uses) load_w1(nth_head((int)((seq + 1) % nheads)), buf);
+            h = next_h;
+        }
+
+        if (is_m) {
             // ---- dh = d(a1) * (hidden > 0) -> A operand (DZ region) + DH image
             uint8_t* img_dh = bd.img.dh + (size_t)tile * 2 * kImg128;
 #pragma unroll 1
@@ -481,7 +559,7 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
             }
             mbar_wait(bar_mma, ph_mma); ph_mma ^= 1u;
             tc::fence_after_sync();
-            if (tile + gridDim.x < ntiles) bar_arrive(kBarXFree, 256);   // the DZ region (next tile's feature operand) is free
+            if (has_next) bar_arrive(kBarXFree, 256);   // the DZ region (next tile's feature operand) is free
             // hand d(feat) to the gather thread of this lane through the (now dead) A1 region
 #pragma unroll
             for (int c0 = 0; c0 < F; c0 += 16) {
@@ -493,89 +571,10 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
             tc::wait_st();
             tc::fence_before_sync();
             bar_arrive(kBarScratch, 256);
-        }
-        if (!first) bar_sync(kBarScratchFree, 256);
-    } else {
-        // =========================================== G group ===========================================
-        float feat[F];
-        float pcs[3] = {0.f, 0.f, 0.f};
-        auto sample_tile = [&](int64_t tl, float (&pc)[3]) {
-            const int64_t gi = tl * 128 + row;
-            pc[0] = pc[1] = pc[2] = 0.f;
-            if (gi < n) {
-                pc[0] = (xyz[3 * gi] - amax[0]) * ascale[0] - 1.0f;
-                pc[1] = (xyz[3 * gi + 1] - amax[1]) * ascale[1] - 1.0f;
-                pc[2] = (xyz[3 * gi + 2] - amax[2]) * ascale[2] - 1.0f;
-            }
-#pragma unroll
-            for (int l = 0; l < L; ++l) {
-                Tap1D tx[3];
-#pragma unroll
-                for (int a = 0; a < 3; ++a) tx[a] = make_tap(pc[a], sd.res[l][a]);
-#pragma unroll
-                for (int v = 0; v < C4; ++v) {
-                    float4 prod = make_float4(1.f, 1.f, 1.f, 1.f);
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) {
-                        const int c0 = plane_axis0(k), c1 = plane_axis1(k);
-                        float4 s;
-                        if (c1 == 3) {
-                            const float4* rowp = reinterpret_cast<const float4*>(sd.trow[l][c0]);
-                            const float4 r0 = __ldg(rowp + tx[c0].i0 * C4 + v), r1 = __ldg(rowp + tx[c0].i1 * C4 + v);
-                            const float w0 = tx[c0].w0, w1 = tx[c0].w1;
-                            s = make_float4(fmaf(r1.x, w1, r0.x * w0), fmaf(r1.y, w1, r0.y * w0), fmaf(r1.z, w1, r0.z * w0), fmaf(r1.w, w1, r0.w * w0));
-                        } else {
-                            const int W = sd.res[l][c0];
-                            const float4* pl = reinterpret_cast<const float4*>(sd.planes[l][k]);
-                            const Tap1D &X = tx[c0], &Y = tx[c1];
-                            const float4 nw = __ldg(pl + (Y.i0 * W + X.i0) * C4 + v), ne = __ldg(pl + (Y.i0 * W + X.i1) * C4 + v);
-                            const float4 sw = __ldg(pl + (Y.i1 * W + X.i0) * C4 + v), se = __ldg(pl + (Y.i1 * W + X.i1) * C4 + v);
-                            const float wnw = X.w0 * Y.w0, wne = X.w1 * Y.w0, wsw = X.w0 * Y.w1, wse = X.w1 * Y.w1;
-                            s = make_float4(fmaf(se.x, wse, fmaf(sw.x, wsw, fmaf(ne.x, wne, nw.x * wnw))),
-                                            fmaf(se.y, wse, fmaf(sw.y, wsw, fmaf(ne.y, wne, nw.y * wnw))),
-                                            fmaf(se.z, wse, fmaf(sw.z, wsw, fmaf(ne.z, wne, nw.z * wnw))),
-                                            fmaf(se.w, wse, fmaf(sw.w, wsw, fmaf(ne.w, wne, nw.w * wnw))));
-                        }
-                        prod.x *= s.x; prod.y *= s.y; prod.z *= s.z; prod.w *= s.w;
-                    }
-                    feat[l * C + 4 * v + 0] = prod.x; feat[l * C + 4 * v + 1] = prod.y;
-                    feat[l * C + 4 * v + 2] = prod.z; feat[l * C + 4 * v + 3] = prod.w;
-                }
-            }
-        };
-        int64_t tile = blockIdx.x;
-        if (tile < ntiles) sample_tile(tile, pcs);
-        bool first = true;
-        for (; tile < ntiles; tile += gridDim.x, first = false) {
-            const int64_t gi = tile * 128 + row;
-            const bool valid = gi < n;
-            if (!first) { bar_sync(kBarXFree, 256); tc::fence_after_sync(); }
-            uint8_t* img_f = bd.img.feat + (size_t)tile * bd.img.feat_bytes;
-#pragma unroll
-            for (int c0 = 0; c0 < F; c0 += 16) {
-                float x[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) x[j] = feat[c0 + j];
-                Split16 s;
-                split16(x, s);
-                tc::tmem_st8(lane_base + kDZ + (c0 >> 1), s.hi);
-                tc::tmem_st8(lane_base + kDZLo + (c0 >> 1), s.lo);
-                store_img16(img_f, 128u * F * 2u, (uint32_t)F, (uint32_t)row, (uint32_t)c0, s);
-            }
-            tc::wait_st();
-            tc::fence_before_sync();
-            bar_arrive(kBarFeat, 256);
-            const float my_pcs[3] = {pcs[0], pcs[1], pcs[2]};
-            // residual path: d(out)/d(in) = identity for scaling / rotation / opacity / shs
-            if (valid) {
-                for (int hh = 1; hh < G4D_NUM_HEADS; ++hh) {
-                    if (!bd.gi[hh]) continue;
-                    const int ko = head_out(hh);
-                    for (int o = 0; o < ko; ++o) bd.gi[hh][gi * ko + o] = bd.go[hh] ? bd.go[hh][gi * ko + o] : 0.f;
-                }
-            }
-            if (tile + gridDim.x < ntiles) sample_tile(tile + gridDim.x, pcs);   // next tile's gathers overlap the MMAs
-            // ---- d(feat) of my Gaussian -> plane gradients (vector RED) and d(xyz)
+        } else {
+            // ---- G tail: next tile's gathers (overlap the dh epilogue + last MMA), then this tile's scatter (overlaps the
+            //      M group's layer 0 + epilogue 0 of the next tile)
+            if (has_next) sample_tile(tile + gridDim.x);
             bar_sync(kBarScratch, 256);
             tc::fence_after_sync();
             float dfeat[F];
@@ -589,7 +588,19 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
             }
             tc::fence_before_sync();
             bar_arrive(kBarScratchFree, 256);
+            if (has_next) {
+                bar_sync(kBarXFree, 256);
+                tc::fence_after_sync();
+                write_features(tile + gridDim.x);
+            }
             if (valid) {
+                // residual path: d(out)/d(in) = identity for scaling / rotation / opacity / shs
+                for (int hh = 1; hh < G4D_NUM_HEADS; ++hh) {
+                    if (!bd.gi[hh]) continue;
+                    const int ko = head_out(hh);
+                    for (int o = 0; o < ko; ++o) bd.gi[hh][gi * ko + o] = bd.go[hh] ? bd.go[hh][gi * ko + o] : 0.f;
+                }
+                // d(feat) of my Gaussian -> plane gradients (vector RED) and d(xyz)
                 float gpix[3] = {0.f, 0.f, 0.f};
 #pragma unroll
                 for (int l = 0; l < L; ++l)
@@ -605,6 +616,7 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
             }
         }
     }
+    if (is_m && !first) bar_sync(kBarScratchFree, 256);
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tbase, tc::kTmemCols);

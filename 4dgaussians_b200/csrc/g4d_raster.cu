@@ -242,6 +242,13 @@ blend_backward_kernel(const CameraDev* __restrict__ cam, GeomBuffers g, const ui
 #pragma unroll
     for (int w = 0; w < kTilePixels / 32; ++w) tile_last = max(tile_last, s_max[w]);
     const int lane = threadIdx.x & 31;
+    // warp-level reduction plan: after the butterfly lane l holds value (l >> 2) of {mean2D.xy, conic.xyz, rgb}; lanes
+    // 0,4,..,28 add one value each, lane 1 adds the opacity gradient -- one predicated RED instruction per Gaussian
+    const bool hi16 = lane & 16, hi8 = lane & 8, hi4 = lane & 4;
+    const int vidx = lane >> 2;
+    const bool red_lane = (lane & 3) == 0 || lane == 1;
+    float* red_base = lane == 1 ? g_opacity : vidx < 2 ? g_mean2D + vidx : vidx < 5 ? g_conic + (vidx - 2) : g_rgb + (vidx - 5);
+    const uint32_t red_stride = lane == 1 ? 1u : vidx < 2 ? 2u : 3u;
 
     for (int i = 0; i < rounds; ++i) {
         // batch i covers list positions [total - (i+1)*256, total - i*256) traversed from the back
@@ -270,38 +277,50 @@ blend_backward_kernel(const CameraDev* __restrict__ cam, GeomBuffers g, const ui
             const float alpha = fminf(kAlphaMax, b.y * G);
             valid = valid && power <= 0.f && alpha >= kAlphaMin;
             if (!__any_sync(0xffffffffu, valid)) continue;
-            float v_mx = 0.f, v_my = 0.f, v_cx = 0.f, v_cy = 0.f, v_cz = 0.f, v_op = 0.f, v_r = 0.f, v_g = 0.f, v_b = 0.f;
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // mean2D.xy, conic.xyz, rgb
+            float v_op = 0.f;
             if (valid) {
-                T = T / (1.f - alpha);
+                const float ra = 1.f / (1.f - alpha);
+                T = T * ra;
                 const float w = alpha * T;
                 const float c0 = b.z, c1 = b.w, c2 = s2[j];
                 ac0 = last_alpha * lc0 + (1.f - last_alpha) * ac0; lc0 = c0;
                 ac1 = last_alpha * lc1 + (1.f - last_alpha) * ac1; lc1 = c1;
                 ac2 = last_alpha * lc2 + (1.f - last_alpha) * ac2; lc2 = c2;
                 float dL_dalpha = (c0 - ac0) * dp0 + (c1 - ac1) * dp1 + (c2 - ac2) * dp2;
-                v_r = w * dp0; v_g = w * dp1; v_b = w * dp2;
+                v[5] = w * dp0; v[6] = w * dp1; v[7] = w * dp2;
                 dL_dalpha *= T;
                 last_alpha = alpha;
-                dL_dalpha += (-Tfin / (1.f - alpha)) * bgdot;
+                dL_dalpha += (-Tfin * ra) * bgdot;
                 const float dL_dG = b.y * dL_dalpha;
                 const float gdx = G * dx, gdy = G * dy;
-                v_mx = dL_dG * (-gdx * a.z - gdy * a.w) * ddx;
-                v_my = dL_dG * (-gdy * b.x - gdx * a.w) * ddy;
-                v_cx = -0.5f * gdx * dx * dL_dG;
-                v_cy = -gdx * dy * dL_dG;
-                v_cz = -0.5f * gdy * dy * dL_dG;
+                v[0] = dL_dG * (-gdx * a.z - gdy * a.w) * ddx;
+                v[1] = dL_dG * (-gdy * b.x - gdx * a.w) * ddy;
+                v[2] = -0.5f * gdx * dx * dL_dG;
+                v[3] = -gdx * dy * dL_dG;
+                v[4] = -0.5f * gdy * dy * dL_dG;
                 v_op = G * dL_dalpha;
             }
-            v_mx = warp_sum(v_mx); v_my = warp_sum(v_my);
-            v_cx = warp_sum(v_cx); v_cy = warp_sum(v_cy); v_cz = warp_sum(v_cz);
+            // transposing butterfly: 8 values x 32 lanes -> value (lane >> 2) summed over the warp in 9 shuffles
+            float u[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float send = hi16 ? v[k] : v[k + 4];
+                u[k] = (hi16 ? v[k + 4] : v[k]) + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+            float x2[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const float send = hi8 ? u[k] : u[k + 2];
+                x2[k] = (hi8 ? u[k + 2] : u[k]) + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            float x = (hi4 ? x2[1] : x2[0]) + __shfl_xor_sync(0xffffffffu, hi4 ? x2[0] : x2[1], 4);
+            x += __shfl_xor_sync(0xffffffffu, x, 2);
+            x += __shfl_xor_sync(0xffffffffu, x, 1);
             v_op = warp_sum(v_op);
-            v_r = warp_sum(v_r); v_g = warp_sum(v_g); v_b = warp_sum(v_b);
-            if (lane == 0) {
+            if (red_lane) {
                 const uint32_t id = sid[j];
-                atomicAdd(g_mean2D + 2 * id, v_mx); atomicAdd(g_mean2D + 2 * id + 1, v_my);
-                atomicAdd(g_conic + 3 * id, v_cx); atomicAdd(g_conic + 3 * id + 1, v_cy); atomicAdd(g_conic + 3 * id + 2, v_cz);
-                atomicAdd(g_opacity + id, v_op);
-                atomicAdd(g_rgb + 3 * id, v_r); atomicAdd(g_rgb + 3 * id + 1, v_g); atomicAdd(g_rgb + 3 * id + 2, v_b);
+                atomicAdd(red_base + red_stride * id, lane == 1 ? v_op : x);
             }
         }
     }

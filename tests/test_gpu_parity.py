@@ -411,8 +411,8 @@ def test_tensor_core_backward_matches_ffma_path(net, n):
     for k in gp_ff:
         a, b = gp_tc[k].cpu().numpy(), gp_ff[k].cpu().numpy()
         e = rel_err(a, b)
-        eb, _ = rel_err_bulk(a, b)
-        assert e <= 3 * GRAD_TOL and eb <= 2e-4, (k, e, eb)
+        eb, _ = rel_err_bulk(a, b, q=90)        # one flipped unit touches one row of dW1 / one entry of db1: p90, not p99.9
+        assert e <= 3 * GRAD_TOL and eb <= 1e-4, (k, e, eb)
 
 
 def test_tight_cull_gives_bit_identical_images_with_fewer_instances():
