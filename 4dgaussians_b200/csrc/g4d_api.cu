@@ -234,8 +234,10 @@ int deform_backward_dispatch(G4DWorkspace* ws, const DeformDesc& d, const G4DDef
     int rc;
     if (ws->tensor_cores && tc_deform_supported(d)) {
         if ((rc = refresh_tc_bwd(ws, prm, st)) != G4D_OK) return rc;
+        if (ws->tc_debug) G4D_CUDA(ws->tc_dbg.ensure((size_t)ws->sm_count * 12 * 8));
         G4D_CUDA(ws->scratch.ensure(tc_deform_backward_scratch_bytes(d, n)));
-        G4D_CUDA(launch_deform_backward_tc(d, *prm, *grads, ws->tcbw, time, n, xyz, go, gi, relu_bits, ws->scratch.as<uint8_t>(), ws->sm_count, st));
+        G4D_CUDA(launch_deform_backward_tc(d, *prm, *grads, ws->tcbw, time, n, xyz, go, gi, relu_bits, ws->tc_debug ? ws->tc_dbg.as<long long>() : nullptr,
+                                           ws->scratch.as<uint8_t>(), ws->sm_count, st));
         return G4D_OK;
     }
     if ((rc = refresh_packed(ws, prm, st)) != G4D_OK) return rc;

@@ -68,6 +68,17 @@ __device__ __forceinline__ void gemm_bf16x2_ss_mn(uint32_t d_tmem, uint32_t a_hi
     }
 }
 
+// one stage of a transposing butterfly: N values per lane -> N/2 (lanes with `hi` keep the upper half), summed with the partner lane
+template <int N, int CAP>
+__device__ __forceinline__ void halve(float (&v)[CAP], bool hi, int lane_mask) {
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k) {
+        const float send = hi ? v[k] : v[k + N / 2];
+        const float keep = hi ? v[k + N / 2] : v[k];
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, lane_mask);
+    }
+}
+
 __device__ __forceinline__ uint32_t pack2(uint16_t even_k, uint16_t odd_k) { return (uint32_t)even_k | ((uint32_t)odd_k << 16); }
 
 // 16 consecutive values of row `g` -> (hi | lo) bf16: packed TMEM words (8 + 8) and two 16-byte image core rows each
@@ -173,9 +184,10 @@ struct BwdADesc {
     const float* go[G4D_NUM_HEADS];
     float* gi[G4D_NUM_HEADS];
     float* g_b2[G4D_NUM_HEADS];
-    float* g_planes[G4D_MAX_LEVELS][6];
-    float* trow_grad[G4D_MAX_LEVELS][3];
+    const float* feat;           // [N][F] fp32 (bwd_features_kernel)
+    float* dfeat;                // [N][F] fp32 -> bwd_scatter_kernel
     const uint32_t* relu_bits;   // [6][N][4] + tag (g4d.h G4D_RELU_BITS_WORDS) or NULL
+    long long* dbg;              // optional [grid][12] per-phase cycle counters (G4D_OPT_TC_DEBUG)
 };
 
 template <int C, int L>
@@ -198,7 +210,7 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
     float4* sW2s = reinterpret_cast<float4*>(smem + Ls.w2s);           // small heads: (W2[0][j], W2[1][j], W2[2][j], W2[3][j])
     float* sW2sh = reinterpret_cast<float*>(smem + Ls.w2sh);           // SH head: W2 [48][128] fp32
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Ls.bars);
-    uint64_t *bar_w0 = bars, *bar_w1 = bars + 1 /* [2] */, *bar_mma = bars + 3, *bar_da1 = bars + 4, *bar_l1 = bars + 5;
+    uint64_t *bar_w0 = bars, *bar_w1 = bars + 1 /* [2] */, *bar_l0 = bars + 3, *bar_da1 = bars + 4, *bar_l1 = bars + 5, *bar_g6 = bars + 6;
     const bool hsh = d.head_mask & G4D_HEAD_SHS;
     for (int i = tid; i < 128; i += 256) sBias[i] = __ldg(d.b0 + i);
     for (int h = 0; h < G4D_NUM_HEADS; ++h) {
@@ -215,7 +227,7 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
     }
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, tc::kTmemCols);
     if (tid == 0) {
-        mbar_init(bar_w0, 1); mbar_init(bar_w1, 1); mbar_init(bar_w1 + 1, 1); mbar_init(bar_mma, 1); mbar_init(bar_da1, 1); mbar_init(bar_l1, 1);
+        mbar_init(bar_w0, 1); mbar_init(bar_w1, 1); mbar_init(bar_w1 + 1, 1); mbar_init(bar_l0, 1); mbar_init(bar_da1, 1); mbar_init(bar_l1, 1); mbar_init(bar_g6, 1);
         fence_barrier_init();
     }
     tc::fence_before_sync();
@@ -259,60 +271,28 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
         if (total_uses > 1) load_w1(nth_head(1 % nheads), 1);
     }
     if (is_m) mbar_wait(bar_w0, 0);
-    uint32_t ph_w1_0 = 0, ph_w1_1 = 0, ph_mma = 0, ph_l1 = 0, ph_da1 = 0;
+    uint32_t ph_w1_0 = 0, ph_w1_1 = 0, ph_l0 = 0, ph_g6 = 0, ph_l1 = 0, ph_da1 = 0;
     int64_t seq = 0;      // running (tile, head) counter -> W1 buffer
     // head epilogues are shared: the G group takes column chunks [0, kGChunks), the M group the rest
     constexpr int kGChunks = 4;
     const int ch_lo = is_m ? kGChunks : 0, ch_hi = is_m ? 8 : kGChunks;
 
-    // ---- G-group helpers -------------------------------------------------------------------------------------
+    // ---- features of a tile: [N][F] fp32 from bwd_features_kernel -> A operand of layer 0 (DZ region) + FEAT image
     float feat[F];
-    float pcs[3] = {0.f, 0.f, 0.f};
-    auto sample_tile = [&](int64_t tl) {
+    auto load_features = [&](int64_t tl) {
         const int64_t gs = tl * 128 + row;
-        pcs[0] = pcs[1] = pcs[2] = 0.f;
         if (gs < n) {
-            pcs[0] = (xyz[3 * gs] - amax[0]) * ascale[0] - 1.0f;
-            pcs[1] = (xyz[3 * gs + 1] - amax[1]) * ascale[1] - 1.0f;
-            pcs[2] = (xyz[3 * gs + 2] - amax[2]) * ascale[2] - 1.0f;
-        }
+            const float4* src = reinterpret_cast<const float4*>(bd.feat + gs * F);
 #pragma unroll
-        for (int l = 0; l < L; ++l) {
-            Tap1D tx[3];
-#pragma unroll
-            for (int a = 0; a < 3; ++a) tx[a] = make_tap(pcs[a], sd.res[l][a]);
-#pragma unroll
-            for (int v = 0; v < C4; ++v) {
-                float4 prod = make_float4(1.f, 1.f, 1.f, 1.f);
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    const int c0 = plane_axis0(k), c1 = plane_axis1(k);
-                    float4 sv;
-                    if (c1 == 3) {
-                        const float4* rowp = reinterpret_cast<const float4*>(sd.trow[l][c0]);
-                        const float4 r0 = __ldg(rowp + tx[c0].i0 * C4 + v), r1 = __ldg(rowp + tx[c0].i1 * C4 + v);
-                        const float w0 = tx[c0].w0, w1 = tx[c0].w1;
-                        sv = make_float4(fmaf(r1.x, w1, r0.x * w0), fmaf(r1.y, w1, r0.y * w0), fmaf(r1.z, w1, r0.z * w0), fmaf(r1.w, w1, r0.w * w0));
-                    } else {
-                        const int W = sd.res[l][c0];
-                        const float4* pl = reinterpret_cast<const float4*>(sd.planes[l][k]);
-                        const Tap1D &X = tx[c0], &Y = tx[c1];
-                        const float4 nw = __ldg(pl + (Y.i0 * W + X.i0) * C4 + v), ne = __ldg(pl + (Y.i0 * W + X.i1) * C4 + v);
-                        const float4 sw = __ldg(pl + (Y.i1 * W + X.i0) * C4 + v), se = __ldg(pl + (Y.i1 * W + X.i1) * C4 + v);
-                        const float wnw = X.w0 * Y.w0, wne = X.w1 * Y.w0, wsw = X.w0 * Y.w1, wse = X.w1 * Y.w1;
-                        sv = make_float4(fmaf(se.x, wse, fmaf(sw.x, wsw, fmaf(ne.x, wne, nw.x * wnw))),
-                                         fmaf(se.y, wse, fmaf(sw.y, wsw, fmaf(ne.y, wne, nw.y * wnw))),
-                                         fmaf(se.z, wse, fmaf(sw.z, wsw, fmaf(ne.z, wne, nw.z * wnw))),
-                                         fmaf(se.w, wse, fmaf(sw.w, wsw, fmaf(ne.w, wne, nw.w * wnw))));
-                    }
-                    prod.x *= sv.x; prod.y *= sv.y; prod.z *= sv.z; prod.w *= sv.w;
-                }
-                feat[l * C + 4 * v + 0] = prod.x; feat[l * C + 4 * v + 1] = prod.y;
-                feat[l * C + 4 * v + 2] = prod.z; feat[l * C + 4 * v + 3] = prod.w;
+            for (int c = 0; c < F; c += 4) {
+                const float4 t4 = __ldg(src + (c >> 2));
+                feat[c] = t4.x; feat[c + 1] = t4.y; feat[c + 2] = t4.z; feat[c + 3] = t4.w;
             }
+        } else {
+#pragma unroll
+            for (int c = 0; c < F; ++c) feat[c] = 0.f;
         }
     };
-    // features -> A operand of layer 0 (DZ region of TMEM) + FEAT image (operand of dW0)
     auto write_features = [&](int64_t tl) {
         uint8_t* img_f = bd.img.feat + (size_t)tl * bd.img.feat_bytes;
 #pragma unroll
@@ -331,32 +311,60 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
         bar_arrive(kBarFeat, 256);
     };
     if (!is_m && blockIdx.x < ntiles) {
-        sample_tile(blockIdx.x);
+        load_features(blockIdx.x);
         write_features(blockIdx.x);
     }
 
-    bool first = true;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
+    float acc_b2s[4] = {0.f, 0.f, 0.f, 0.f};   // (M) db2 partial sums of the small heads (butterfly-distributed over lanes)
+    float acc_b2sh[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int lane = tid & 31;
+    long long cyc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
+    const bool prober = bd.dbg && (tid == 128 || tid == 0);
+#define G4D_CYC(i) do { if (prober) { const long long tn_ = clock64(); cyc[(i) + (is_m ? 0 : 6)] += tn_ - tprev; tprev = tn_; } } while (0)
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t gi = tile * 128 + row;
         const bool valid = gi < n;
         const bool has_next = tile + gridDim.x < ntiles;
-        uint64_t hm0 = 0ull, hm1 = 0ull;   // (M) bit j set <=> hidden[j] > 0
-        float my_pcs[3] = {pcs[0], pcs[1], pcs[2]};   // (G) coordinates of THIS tile's Gaussian (pcs moves on to the next tile)
+        auto load_dout = [&](int hh, float (&dst)[48]) {
+#pragma unroll
+            for (int o = 0; o < 48; ++o) dst[o] = 0.f;
+            if (valid && bd.go[hh]) {
+                const int kk = head_out(hh);
+                const float* gp = bd.go[hh] + gi * kk;
+                if (hh == 4) {
+#pragma unroll
+                    for (int o = 0; o < 48; o += 4) {
+                        const float4 t4 = __ldg(reinterpret_cast<const float4*>(gp + o));
+                        dst[o] = t4.x; dst[o + 1] = t4.y; dst[o + 2] = t4.z; dst[o + 3] = t4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int o = 0; o < 4; ++o)
+                        if (o < kk) dst[o] = __ldg(gp + o);
+                }
+            }
+        };
+        float dn[48];
+        load_dout(first_h, dn);
+        uint64_t hm0 = 0ull, hm1 = 0ull;   // bit j set <=> hidden[j] > 0 (only this thread's own chunks when recomputed)
+        if (use_bits) load_bits(0, gi, valid, hm0, hm1);
+        // ---- layer 0 recompute: D = feat W0^T
         if (is_m) {
-            // ---- layer 0 recompute: D = feat W0^T
             bar_sync(kBarFeat, 256);
             if (issuer) {
                 tc::fence_after_sync();
                 gemm_bf16x2_ts<F>(tbase + kD, tbase + kDZ, tbase + kDZLo, sW0, sW0 + 128u * F * 2, 128, F, false, false);
-                tc::umma_commit(bar_mma);
+                tc::umma_commit(bar_l0);
             }
-            mbar_wait(bar_mma, ph_mma); ph_mma ^= 1u;
-            tc::fence_after_sync();
-            if (!first) { bar_sync(kBarScratchFree, 256); tc::fence_after_sync(); }   // previous tile's d(feat) scratch (A1 region) consumed
-            if (use_bits) load_bits(0, gi, valid, hm0, hm1);
+        }
+        mbar_wait(bar_l0, ph_l0); ph_l0 ^= 1u;
+        tc::fence_after_sync();
+        G4D_CYC(0);   // wait features + layer 0
+        {
             uint8_t* img_a1 = bd.img.a1 + (size_t)tile * 2 * kImg128;
 #pragma unroll 1
-            for (int ch = 0; ch < 8; ++ch) {
+            for (int ch = ch_lo; ch < ch_hi; ++ch) {
                 uint32_t v[16];
                 tc::tmem_ld16(lane_base + kD + ch * 16, v);
                 tc::wait_ld();
@@ -382,7 +390,11 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
             }
             tc::wait_st();
             tc::fence_before_sync();
-            bar_sync(kBarM, 128);
+            G4D_CYC(1);   // epilogue 0 (+ dh epilogue below)
+            bar_sync(kBarE, 256);
+            G4D_CYC(4);   // wait for the other group
+        }
+        if (is_m) {
             // ---- first layer-1 GEMM of the tile
             const int buf = (int)(seq & 1);
             if (buf == 0) { mbar_wait(bar_w1, ph_w1_0); ph_w1_0 ^= 1u; } else { mbar_wait(bar_w1 + 1, ph_w1_1); ph_w1_1 ^= 1u; }
@@ -401,32 +413,18 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
         for (int hc = 0; hc < nheads; ++hc) {
             const int buf = (int)(seq & 1);
             const float* b1 = sBias + 128 + h * 128;
-            const int ko = head_out(h);
             int next_h = -1;
             {
                 const int later = d.head_mask >> (h + 1);
                 if (later) next_h = h + 1 + (__ffs(later) - 1);
             }
-            // my row of dL/d(out_h)
+            // my row of dL/d(out_h): fetched one head ahead (the loads fly during the previous head's epilogue)
             float dout[48];
 #pragma unroll
-            for (int o = 0; o < 48; ++o) dout[o] = 0.f;
-            if (valid && bd.go[h]) {
-                const float* gp = bd.go[h] + gi * ko;
-                if (h == 4) {
-#pragma unroll
-                    for (int o = 0; o < 48; o += 4) {
-                        const float4 t4 = *reinterpret_cast<const float4*>(gp + o);
-                        dout[o] = t4.x; dout[o + 1] = t4.y; dout[o + 2] = t4.z; dout[o + 3] = t4.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int o = 0; o < 4; ++o)
-                        if (o < ko) dout[o] = gp[o];
-                }
-            }
+            for (int o = 0; o < 48; ++o) dout[o] = dn[o];
+            if (next_h >= 0) load_dout(next_h, dn);
             if (is_m) {
-                // DOUT image (operand of dW2) and db2 (warp-shuffle column sums)
+                // DOUT image (operand of dW2)
                 const uint32_t kp16 = (h == 4) ? 48u : 16u;
                 uint8_t* img = bd.img.dout[h] + (size_t)tile * 2 * 128 * kp16 * 2;
 #pragma unroll
@@ -439,20 +437,28 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
                     split16(x, s);
                     store_img16(img, 128u * kp16 * 2u, kp16, (uint32_t)row, (uint32_t)c0, s);
                 }
+                // db2: transposing butterfly over the warp, partial sums stay distributed over the lanes until the end
+                if (h == 4) {
+                    float t[48];
 #pragma unroll
-                for (int o = 0; o < 48; ++o) {
-                    if (o >= ko) break;
-                    float s = dout[o];
+                    for (int o = 0; o < 48; ++o) t[o] = dout[o];
+                    halve<48>(t, lane & 16, 16); halve<24>(t, lane & 8, 8); halve<12>(t, lane & 4, 4);
 #pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-                    if ((tid & 31) == 0) atomicAdd(bd.g_b2[h] + o, s);
+                    for (int k = 0; k < 6; ++k) acc_b2sh[k] += t[k];
+                } else {
+                    float t[4] = {dout[0], dout[1], dout[2], dout[3]};
+                    halve<4>(t, lane & 16, 16); halve<2>(t, lane & 8, 8);
+                    if (h == 0) acc_b2s[0] += t[0]; else if (h == 1) acc_b2s[1] += t[0];
+                    else if (h == 2) acc_b2s[2] += t[0]; else acc_b2s[3] += t[0];
                 }
             }
             uint64_t zm0 = 0ull, zm1 = 0ull;
             if (use_bits) load_bits(1 + h, gi, valid, zm0, zm1);
+            G4D_CYC(2);   // dout / DOUT image / db2
             // ---- wait for z = a1 W1^T
             mbar_wait(bar_l1, ph_l1); ph_l1 ^= 1u;
             tc::fence_after_sync();
+            G4D_CYC(5);   // MMA waits
             uint8_t* img_a2 = bd.img.a2[h] + (size_t)tile * 2 * kImg128;
             uint8_t* img_dz = bd.img.dz[h] + (size_t)tile * 2 * kImg128;
 #pragma unroll 1
@@ -504,7 +510,9 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
             }
             tc::wait_st();
             tc::fence_before_sync();
+            G4D_CYC(3);   // head epilogue (my chunks)
             bar_sync(kBarE, 256);
+            G4D_CYC(4);   // wait for the other group
             // ---- d(a1) += dz W1 (W1 image read MN-major), then the next head's layer 1 straight behind it
             if (issuer) {
                 tc::fence_after_sync();
@@ -528,13 +536,14 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
             tc::fence_after_sync();
             if (issuer && seq + 1 < total_uses) load_w1(nth_head((int)((seq + 1) % nheads)), buf);
             h = next_h;
+            G4D_CYC(5);   // MMA waits
         }
 
-        if (is_m) {
-            // ---- dh = d(a1) * (hidden > 0) -> A operand (DZ region) + DH image
+        // ---- dh = d(a1) * (hidden > 0) -> A operand (DZ region) + DH image
+        {
             uint8_t* img_dh = bd.img.dh + (size_t)tile * 2 * kImg128;
 #pragma unroll 1
-            for (int ch = 0; ch < 8; ++ch) {
+            for (int ch = ch_lo; ch < ch_hi; ++ch) {
                 uint32_t v[16];
                 tc::tmem_ld16(lane_base + kDA1 + ch * 16, v);
                 tc::wait_ld();
@@ -550,76 +559,167 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
             }
             tc::wait_st();
             tc::fence_before_sync();
-            bar_sync(kBarM, 128);
-            // ---- d(feat) = dh W0  (W0 image read MN-major: rows = hidden j = K, cols = feature f = N)
+            G4D_CYC(1);
+            bar_sync(kBarE, 256);
+            G4D_CYC(4);
+        }
+        if (is_m) {
+            // ---- d(feat) = dh W0  (W0 image read MN-major: rows = hidden j = K, cols = feature f = N) -> [N][F] fp32
             if (issuer) {
                 tc::fence_after_sync();
                 gemm_bf16x2_ts<128>(tbase + kD, tbase + kDZ, tbase + kDZLo, sW0, sW0 + 128u * F * 2, F, F, true, false);
-                tc::umma_commit(bar_mma);
+                tc::umma_commit(bar_g6);
             }
-            mbar_wait(bar_mma, ph_mma); ph_mma ^= 1u;
+            mbar_wait(bar_g6, ph_g6); ph_g6 ^= 1u;
             tc::fence_after_sync();
             if (has_next) bar_arrive(kBarXFree, 256);   // the DZ region (next tile's feature operand) is free
-            // hand d(feat) to the gather thread of this lane through the (now dead) A1 region
 #pragma unroll
             for (int c0 = 0; c0 < F; c0 += 16) {
                 uint32_t v[16];
                 tc::tmem_ld16(lane_base + kD + c0, v);
                 tc::wait_ld();
-                tc::tmem_st16(lane_base + kA1 + c0, v);
+                if (valid) {
+                    float4* dst = reinterpret_cast<float4*>(bd.dfeat + gi * F + c0);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                             __uint_as_float(v[4 * q + 3]));
+                }
             }
-            tc::wait_st();
             tc::fence_before_sync();
-            bar_arrive(kBarScratch, 256);
-        } else {
-            // ---- G tail: next tile's gathers (overlap the dh epilogue + last MMA), then this tile's scatter (overlaps the
-            //      M group's layer 0 + epilogue 0 of the next tile)
-            if (has_next) sample_tile(tile + gridDim.x);
-            bar_sync(kBarScratch, 256);
+            G4D_CYC(5);
+        } else if (has_next) {
+            load_features(tile + gridDim.x);
+            bar_sync(kBarXFree, 256);
             tc::fence_after_sync();
-            float dfeat[F];
+            write_features(tile + gridDim.x);
+            G4D_CYC(5);
+        }
+    }
+    if (is_m) {
+        // db2 flush: finish the butterflies (remaining lane bits) and add once per warp
 #pragma unroll
-            for (int c0 = 0; c0 < F; c0 += 16) {
-                uint32_t v[16];
-                tc::tmem_ld16(lane_base + kA1 + c0, v);
-                tc::wait_ld();
+        for (int hh = 0; hh < 4; ++hh) {
+            float x = acc_b2s[hh];
+            x += __shfl_xor_sync(0xffffffffu, x, 4); x += __shfl_xor_sync(0xffffffffu, x, 2); x += __shfl_xor_sync(0xffffffffu, x, 1);
+            const int idx = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+            if ((d.head_mask & (1 << hh)) && (lane & 7) == 0 && idx < head_out(hh)) atomicAdd(bd.g_b2[hh] + idx, x);
+        }
+        if (d.head_mask & G4D_HEAD_SHS) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) dfeat[c0 + j] = __uint_as_float(v[j]);
-            }
-            tc::fence_before_sync();
-            bar_arrive(kBarScratchFree, 256);
-            if (has_next) {
-                bar_sync(kBarXFree, 256);
-                tc::fence_after_sync();
-                write_features(tile + gridDim.x);
-            }
-            if (valid) {
-                // residual path: d(out)/d(in) = identity for scaling / rotation / opacity / shs
-                for (int hh = 1; hh < G4D_NUM_HEADS; ++hh) {
-                    if (!bd.gi[hh]) continue;
-                    const int ko = head_out(hh);
-                    for (int o = 0; o < ko; ++o) bd.gi[hh][gi * ko + o] = bd.go[hh] ? bd.go[hh][gi * ko + o] : 0.f;
-                }
-                // d(feat) of my Gaussian -> plane gradients (vector RED) and d(xyz)
-                float gpix[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-                for (int l = 0; l < L; ++l)
-#pragma unroll
-                    for (int v = 0; v < C4; ++v)
-                        scatter_vector(sd, bd.g_planes, bd.trow_grad, l, v, C4, my_pcs,
-                                       make_float4(dfeat[l * C + 4 * v], dfeat[l * C + 4 * v + 1], dfeat[l * C + 4 * v + 2], dfeat[l * C + 4 * v + 3]),
-                                       gpix);
-                if (bd.gi[0]) {
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) bd.gi[0][gi * 3 + a] = (bd.go[0] ? bd.go[0][gi * 3 + a] : 0.f) + gpix[a] * ascale[a];
-                }
+            for (int k = 0; k < 6; ++k) {
+                float x = acc_b2sh[k];
+                x += __shfl_xor_sync(0xffffffffu, x, 2); x += __shfl_xor_sync(0xffffffffu, x, 1);
+                const int idx = ((lane >> 4) & 1) * 24 + ((lane >> 3) & 1) * 12 + ((lane >> 2) & 1) * 6 + k;
+                if ((lane & 3) == 0) atomicAdd(bd.g_b2[4] + idx, x);
             }
         }
     }
-    if (is_m && !first) bar_sync(kBarScratchFree, 256);
+    if (prober) {
+        // slots (M: 0..5, G: 6..11): 0 wait features + layer 0, 1 epilogue 0 + dh epilogue, 2 dout/DOUT/db2, 3 head epilogues,
+        //                           4 waiting for the other group, 5 MMA waits + tile tail
+        for (int i = 0; i < 6; ++i) bd.dbg[blockIdx.x * 12 + i + (is_m ? 0 : 6)] = cyc[i + (is_m ? 0 : 6)];
+    }
+#undef G4D_CYC
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tbase, tc::kTmemCols);
+}
+
+// ---- HexPlane gather / scatter at full occupancy (C/4 threads per Gaussian, one channel vector each) ---------------
+G4D_D float4 hexplane_vector(const DeformDesc& d, int l, int v, int C4, const float pcs[3]) {
+    Tap1D tx[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) tx[a] = make_tap(pcs[a], d.res[l][a]);
+    float4 prod = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const int c0 = plane_axis0(k), c1 = plane_axis1(k);
+        float4 sv;
+        if (c1 == 3) {
+            const float4* rowp = reinterpret_cast<const float4*>(d.trow[l][c0]);
+            const float4 r0 = __ldg(rowp + tx[c0].i0 * C4 + v), r1 = __ldg(rowp + tx[c0].i1 * C4 + v);
+            const float w0 = tx[c0].w0, w1 = tx[c0].w1;
+            sv = make_float4(fmaf(r1.x, w1, r0.x * w0), fmaf(r1.y, w1, r0.y * w0), fmaf(r1.z, w1, r0.z * w0), fmaf(r1.w, w1, r0.w * w0));
+        } else {
+            const int W = d.res[l][c0];
+            const float4* pl = reinterpret_cast<const float4*>(d.planes[l][k]);
+            const Tap1D &X = tx[c0], &Y = tx[c1];
+            const float4 nw = __ldg(pl + (Y.i0 * W + X.i0) * C4 + v), ne = __ldg(pl + (Y.i0 * W + X.i1) * C4 + v);
+            const float4 sw = __ldg(pl + (Y.i1 * W + X.i0) * C4 + v), se = __ldg(pl + (Y.i1 * W + X.i1) * C4 + v);
+            const float wnw = X.w0 * Y.w0, wne = X.w1 * Y.w0, wsw = X.w0 * Y.w1, wse = X.w1 * Y.w1;
+            sv = make_float4(fmaf(se.x, wse, fmaf(sw.x, wsw, fmaf(ne.x, wne, nw.x * wnw))),
+                             fmaf(se.y, wse, fmaf(sw.y, wsw, fmaf(ne.y, wne, nw.y * wnw))),
+                             fmaf(se.z, wse, fmaf(sw.z, wsw, fmaf(ne.z, wne, nw.z * wnw))),
+                             fmaf(se.w, wse, fmaf(sw.w, wsw, fmaf(ne.w, wne, nw.w * wnw))));
+        }
+        prod.x *= sv.x; prod.y *= sv.y; prod.z *= sv.z; prod.w *= sv.w;
+    }
+    return prod;
+}
+
+template <int C4>
+__global__ void __launch_bounds__(256) bwd_features_kernel(DeformDesc d, int64_t n, const float* __restrict__ xyz, float* __restrict__ feat) {
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t g = t / C4;
+    const int v = (int)(t % C4);
+    if (g >= n) return;
+    float pcs[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float amax = __ldg(d.aabb + a), ascale = 2.0f / (__ldg(d.aabb + 3 + a) - amax);
+        pcs[a] = (xyz[3 * g + a] - amax) * ascale - 1.0f;
+    }
+    for (int l = 0; l < d.levels; ++l)
+        *reinterpret_cast<float4*>(feat + g * d.F + l * d.C + 4 * v) = hexplane_vector(d, l, v, C4, pcs);
+}
+
+struct BwdScatterDesc {
+    DeformDesc d;
+    const float* dfeat;                     // [N][F]
+    float* g_planes[G4D_MAX_LEVELS][6];
+    float* trow_grad[G4D_MAX_LEVELS][3];
+    const float* go[G4D_NUM_HEADS];
+    float* gi[G4D_NUM_HEADS];
+};
+
+template <int C4>
+__global__ void __launch_bounds__(256, 2) bwd_scatter_kernel(BwdScatterDesc sd, int64_t n, const float* __restrict__ xyz) {
+    const DeformDesc& d = sd.d;
+    constexpr int GPB = 256 / C4;           // Gaussians per block
+    const int64_t g0 = (int64_t)blockIdx.x * GPB;
+    const int64_t g = g0 + threadIdx.x / C4;
+    const int v = threadIdx.x % C4;
+    // residual path: d(out)/d(in) = identity for scaling / rotation / opacity / shs (contiguous ranges, coalesced)
+    for (int hh = 1; hh < G4D_NUM_HEADS; ++hh) {
+        if (!sd.gi[hh]) continue;
+        const int ko = head_out(hh);
+        const int64_t lo = g0 * ko, hi = (g0 + GPB < n ? g0 + GPB : n) * ko;
+        for (int64_t i = lo + threadIdx.x; i < hi; i += 256) sd.gi[hh][i] = sd.go[hh] ? sd.go[hh][i] : 0.f;
+    }
+    float gpix[3] = {0.f, 0.f, 0.f};
+    float ascale[3] = {0.f, 0.f, 0.f};
+    if (g < n) {
+        float pcs[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float amax = __ldg(d.aabb + a);
+            ascale[a] = 2.0f / (__ldg(d.aabb + 3 + a) - amax);
+            pcs[a] = (xyz[3 * g + a] - amax) * ascale[a] - 1.0f;
+        }
+        for (int l = 0; l < d.levels; ++l) {
+            const float4 df = __ldg(reinterpret_cast<const float4*>(sd.dfeat + g * d.F + l * d.C + 4 * v));
+            scatter_vector(d, sd.g_planes, sd.trow_grad, l, v, C4, pcs, df, gpix);
+        }
+    }
+    // the C4 threads of a Gaussian are adjacent lanes
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+        for (int o = 1; o < C4; o <<= 1) gpix[a] += __shfl_xor_sync(0xffffffffu, gpix[a], o);
+    if (g < n && v == 0 && sd.gi[0]) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) sd.gi[0][g * 3 + a] = (sd.go[0] ? sd.go[0][g * 3 + a] : 0.f) + gpix[a] * ascale[a];
+    }
 }
 
 // ======================================================================================================
@@ -745,7 +845,7 @@ size_t tc_deform_backward_scratch_bytes(const DeformDesc& d, int64_t n) {
     size_t rows = 0;
     for (int l = 0; l < d.levels; ++l)
         for (int a = 0; a < 3; ++a) rows += (size_t)d.res[l][a] * d.C;
-    return ntiles * per_tile + rows * 4 + 8192;
+    return ntiles * per_tile + rows * 4 + (size_t)2 * ntiles * 128 * d.F * 4 + 16384;
 }
 
 template <int C, int L>
@@ -763,11 +863,11 @@ static cudaError_t launch_a(const BwdADesc& bd, float time, int64_t n, const flo
 cudaError_t launch_deform_backward_tc(const DeformDesc& d, const G4DDeformParams& prm, const G4DDeformGrads& grads,
                                       const TcBwdWeights& w, float time, int64_t n, const float* xyz,
                                       const float* const go[G4D_NUM_HEADS], float* const gi[G4D_NUM_HEADS],
-                                      const uint32_t* relu_bits, uint8_t* scratch, int sm_count, cudaStream_t st) {
+                                      const uint32_t* relu_bits, long long* dbg, uint8_t* scratch, int sm_count, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     const int64_t ntiles = (n + 127) / 128;
     BwdADesc a{};
-    a.d = d; a.w = w; a.relu_bits = relu_bits;
+    a.d = d; a.w = w; a.relu_bits = relu_bits; a.dbg = dbg;
     uint8_t* p = scratch;
     auto take = [&](size_t bytes) { uint8_t* o = p; p += (bytes + 255) & ~(size_t)255; return o; };
     a.img.feat_bytes = 2u * 128 * d.F * 2;
@@ -781,24 +881,48 @@ cudaError_t launch_deform_backward_tc(const DeformDesc& d, const G4DDeformParams
         a.img.a2[h] = take((size_t)ntiles * 2 * kImg128);
         a.img.dout[h] = take((size_t)ntiles * 2 * 128 * (h == 4 ? 48 : 16) * 2);
     }
+    float* feat = reinterpret_cast<float*>(take((size_t)ntiles * 128 * d.F * 4));
+    float* dfeat = reinterpret_cast<float*>(take((size_t)ntiles * 128 * d.F * 4));
+    a.feat = feat; a.dfeat = dfeat;
     size_t row_floats = 0;
     for (int l = 0; l < d.levels; ++l)
         for (int k = 0; k < 3; ++k) row_floats += (size_t)d.res[l][k] * d.C;
     float* rows = reinterpret_cast<float*>(take(row_floats * 4));
+    BwdScatterDesc sc{};
+    sc.d = d; sc.dfeat = dfeat;
     {
         float* q = rows;
         for (int l = 0; l < d.levels; ++l) {
-            for (int k = 0; k < 6; ++k) a.g_planes[l][k] = grads.planes[l][k];
-            for (int k = 0; k < 3; ++k) { a.trow_grad[l][k] = q; q += (size_t)d.res[l][k] * d.C; }
+            for (int k = 0; k < 6; ++k) sc.g_planes[l][k] = grads.planes[l][k];
+            for (int k = 0; k < 3; ++k) { sc.trow_grad[l][k] = q; q += (size_t)d.res[l][k] * d.C; }
         }
     }
+    for (int h = 0; h < G4D_NUM_HEADS; ++h) { sc.go[h] = go[h]; sc.gi[h] = gi[h]; }
     cudaError_t e = cudaMemsetAsync(rows, 0, row_floats * 4, st);
     if (e != cudaSuccess) return e;
+    const int C4 = d.C / 4;
+    // gather at full occupancy
+    {
+        const int64_t threads = n * C4;
+        const unsigned grid = (unsigned)((threads + 255) / 256);
+        if (C4 == 4) bwd_features_kernel<4><<<grid, 256, 0, st>>>(d, n, xyz, feat);
+        else if (C4 == 8) bwd_features_kernel<8><<<grid, 256, 0, st>>>(d, n, xyz, feat);
+        else return cudaErrorInvalidValue;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
     if (d.C == 16 && d.levels == 2) e = launch_a<16, 2>(a, time, n, xyz, sm_count, st);
     else if (d.C == 16 && d.levels == 3) e = launch_a<16, 3>(a, time, n, xyz, sm_count, st);
     else if (d.C == 32 && d.levels == 2) e = launch_a<32, 2>(a, time, n, xyz, sm_count, st);
     else return cudaErrorInvalidValue;
     if (e != cudaSuccess) return e;
+    // scatter d(feat) into the planes, d(xyz), residual copies
+    {
+        const int gpb = 256 / C4;
+        const unsigned grid = (unsigned)((n + gpb - 1) / gpb);
+        if (C4 == 4) bwd_scatter_kernel<4><<<grid, 256, 0, st>>>(sc, n, xyz);
+        else bwd_scatter_kernel<8><<<grid, 256, 0, st>>>(sc, n, xyz);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
     // kernel B
     BwdBDesc b{};
     b.img = a.img; b.head_mask = d.head_mask; b.F = d.F; b.ntiles = ntiles;
@@ -811,7 +935,7 @@ cudaError_t launch_deform_backward_tc(const DeformDesc& d, const G4DDeformParams
     if (e != cudaSuccess) return e;
     deform_tc_bwd_wgrad_kernel<<<6 * b.nchunks, 128, smem_b, st>>>(b);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    return launch_distribute_time_grad(d, a.trow_grad, a.g_planes, time, st);
+    return launch_distribute_time_grad(d, sc.trow_grad, sc.g_planes, time, st);
 }
 
 }  // namespace g4d

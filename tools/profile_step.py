@@ -58,7 +58,10 @@ def main():
             g4d._lib.load().g4d_debug_tc_cycles(ws.handle, arr)
             names = ["inputs", "wait_feat", "L0_mma", "wait_scratch_free", "epi0", "wait_W1", "L1_mma", "wait_W2", "epi_half",
                      "L2_mma", "head_out", "tail"]
-            print("tc cycles/CTA:", {k: int(arr[i]) for i, k in enumerate(names)}, "total", int(sum(arr)), flush=True)
+            if a.backward:   # the backward kernel ran last and overwrote the slots (g4d_deform_tc_bwd.cu)
+                ph = ["feat+L0", "epi0+dh", "dout", "head_epi", "wait_other", "mma+tail"]
+                names = ["M:" + x for x in ph] + ["G:" + x for x in ph]
+            print("tc cycles/CTA:", {k: int(arr[i]) for i, k in enumerate(names)}, flush=True)
         if a.stage_times and ws._free_contexts:
             c = ws._free_contexts[-1]
             s = c.stats()
