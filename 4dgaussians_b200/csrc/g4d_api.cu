@@ -59,7 +59,7 @@ struct G4DWorkspace {
     int tensor_cores = 1;
     DevBuf tc_packed;
     TcWeights tcw{};
-    DevBuf tc_bwd_packed;
+    DevBuf tc_bwd_packed, tc_feat;
     TcBwdWeights tcbw{};
     uint64_t tc_bwd_version = 0;
     const void* tc_bwd_key = nullptr;
@@ -248,8 +248,15 @@ int deform_backward_dispatch(G4DWorkspace* ws, const DeformDesc& d, const G4DDef
 
 // ReLU sign bits saved by the tensor-core forward for its backward; the trailing tag word says whether they were written
 constexpr int kReluTagByte = 0x5A;
-int attach_relu_bits(G4DWorkspace* ws, bool use_tc, uint32_t* relu_bits, int64_t n, cudaStream_t st) {
+int attach_relu_bits(G4DWorkspace* ws, bool use_tc, bool save, uint32_t* relu_bits, int64_t n, cudaStream_t st) {
+    const bool tc = use_tc;
+    use_tc = use_tc && save;
     ws->tcw.relu_bits = use_tc ? relu_bits : nullptr;
+    ws->tcw.feat = nullptr;
+    if (tc) {   // feature staging buffer of the tensor-core forward
+        G4D_CUDA(ws->tc_feat.ensure((size_t)(n > 0 ? n : 1) * 64 * 4 + 256));
+        ws->tcw.feat = ws->tc_feat.as<float>();
+    }
     if (relu_bits) G4D_CUDA(cudaMemsetAsync(relu_bits + (size_t)24 * (size_t)n, use_tc ? kReluTagByte : 0, 16, st));
     return G4D_OK;
 }
@@ -455,7 +462,7 @@ G4DWorkspace* g4d_workspace_create(int device) {
 void g4d_workspace_destroy(G4DWorkspace* ws) {
     if (!ws) return;
     cudaSetDevice(ws->device);
-    ws->packed.release(); ws->tc_packed.release(); ws->tc_bwd_packed.release(); ws->trow.release(); ws->temp.release(); ws->scratch.release();
+    ws->packed.release(); ws->tc_packed.release(); ws->tc_bwd_packed.release(); ws->tc_feat.release(); ws->trow.release(); ws->temp.release(); ws->scratch.release();
     if (ws->h_pinned) cudaFreeHost(ws->h_pinned);
     delete ws;
 }
@@ -546,7 +553,7 @@ int g4d_deform_forward(G4DWorkspace* ws, const G4DDeformParams* prm, int64_t n, 
     const bool use_tc = ws->tensor_cores && tc_deform_supported(d);
     if (use_tc && (rc = refresh_tc(ws, prm, st)) != G4D_OK) return rc;
     if (use_tc && (rc = attach_tc_debug(ws, st)) != G4D_OK) return rc;
-    if ((rc = attach_relu_bits(ws, use_tc, relu_bits, n, st)) != G4D_OK) return rc;
+    if ((rc = attach_relu_bits(ws, use_tc, true, relu_bits, n, st)) != G4D_OK) return rc;
     G4D_CUDA(launch_deform(d, 0, nullptr, time, false, n, xyz, scaling, rotation, opacity, shs, nullptr, nullptr, out_xyz,
                            out_scaling, out_rotation, out_opacity, out_shs, g, fo, nullptr, ws->sm_count, st,
                            use_tc ? &ws->tcw : nullptr));
@@ -738,7 +745,7 @@ int g4d_render_forward(G4DContext* c, const G4DCamera* cam, const G4DDeformParam
         if (use_tc && (rc = attach_tc_debug(ws, st)) != G4D_OK) return rc;
         c->relu_saved = use_tc && !(cam->debug & G4D_CAM_NO_GRAD);
         if (c->relu_saved) G4D_CUDA(c->relu.ensure(G4D_RELU_BITS_WORDS(n) * 4));
-        if ((rc = attach_relu_bits(ws, c->relu_saved, c->relu_saved ? c->relu.as<uint32_t>() : nullptr, n, st)) != G4D_OK) return rc;
+        if ((rc = attach_relu_bits(ws, use_tc, c->relu_saved, c->relu_saved ? c->relu.as<uint32_t>() : nullptr, n, st)) != G4D_OK) return rc;
         G4D_CUDA(launch_deform(d, 1, dcam, cam->time, false, n, g->xyz, g->scaling, g->rotation, g->opacity, shs, dc,
                                g->features_rest, nullptr, nullptr, nullptr, nullptr, nullptr, c->g, c->fo, out_radii,
                                ws->sm_count, st, use_tc ? &ws->tcw : nullptr));

@@ -23,7 +23,7 @@ namespace g4d {
 
 constexpr uint32_t kColA1Hi = 0, kColA1Lo = 128, kColD = 256, kColX = 384, kColXLo = 448;
 
-struct TcSmem { uint32_t w1, w2, w0, bias, w2s, bars, total; };
+struct TcSmem { uint32_t w1, w2, w0, bias, w2s, bars, acc, total; };
 
 inline TcSmem tc_smem_layout(int F, int max_kp16) {
     TcSmem s{};
@@ -35,6 +35,7 @@ inline TcSmem tc_smem_layout(int F, int max_kp16) {
     s.bias = take((128 + G4D_NUM_HEADS * 128 + 64) * 4);
     s.w2s = take(4 * 128 * 16);
     s.bars = take(64);
+    s.acc = take(2 * 128 * 16);
     s.total = off;
     return s;
 }
@@ -110,7 +111,7 @@ __device__ __forceinline__ int b2off_of(int mask, int h) {
     return o;
 }
 
-constexpr int kBarFeat = 1, kBarXFree = 2, kBarScratch = 3, kBarScratchFree = 4, kBarM = 5;
+constexpr int kBarFeat = 1, kBarXFree = 2, kBarScratch = 3, kBarScratchFree = 4, kBarM = 5, kBarE = 6;
 constexpr uint32_t kColScratch = kColA1Hi;   // p(3) + dsh(48) handed from M to G after the last head (A1 is dead then)
 
 // One channel vector (4 channels) of one level: product over the 6 planes of the bilinear samples.
@@ -168,6 +169,11 @@ __device__ __forceinline__ void store_relu_bits(uint32_t* base, int slot, int64_
         make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
 }
 
+// one 64-bit half of a row's sign bits (word0 = 0 for hidden units 0..63, 2 for 64..127)
+__device__ __forceinline__ void store_relu_half(uint32_t* base, int slot, int64_t n, int64_t gi, int word0, uint32_t lo, uint32_t hi) {
+    *reinterpret_cast<uint2*>(base + ((size_t)slot * (size_t)n + (size_t)gi) * 4 + word0) = make_uint2(lo, hi);
+}
+
 template <int MODE, int C, int L, bool SAVE>
 __global__ void __launch_bounds__(256, 1)
 deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restrict__ camp, float time_arg, int use_cam_time,
@@ -192,7 +198,7 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
     float* sBias = reinterpret_cast<float*>(smem + Ls.bias);     // b0[128] | b1[5][128] | b2[64]
     float4* sW2s = reinterpret_cast<float4*>(smem + Ls.w2s);     // [4 small heads][128 hidden]: (W2[0][j], W2[1][j], W2[2][j], W2[3][j])
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Ls.bars);
-    uint64_t *bar_w0 = bars, *bar_w1 = bars + 1, *bar_mma = bars + 3;
+    uint64_t *bar_w0 = bars, *bar_w1 = bars + 1, *bar_l0 = bars + 3, *bar_l1 = bars + 4, *bar_l2 = bars + 5;
     int b2off[G4D_NUM_HEADS];
     {
         int o = 0;
@@ -213,7 +219,7 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
     }
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, tc::kTmemCols);
     if (tid == 0) {
-        mbar_init(bar_w0, 1); mbar_init(bar_w1, 1); mbar_init(bar_mma, 1);
+        mbar_init(bar_w0, 1); mbar_init(bar_w1, 1); mbar_init(bar_l0, 1); mbar_init(bar_l1, 1); mbar_init(bar_l2, 1);
         fence_barrier_init();
     }
     tc::fence_before_sync();
@@ -228,133 +234,217 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
 #pragma unroll
     for (int a = 0; a < 3; ++a) { amax[a] = __ldg(d.aabb + a); ascale[a] = 2.0f / (__ldg(d.aabb + 3 + a) - amax[a]); }
 
-    if (is_m) {
-        // =========================================== M group ===========================================
-        if (issuer) {
-            // resident operands: W0 and (when active) the SH head's W2 image
-            const uint32_t w2b = hsh ? 2u * 48 * 128 * 4 : 0u;
-            mbar_expect_tx(bar_w0, 2u * 128 * F * 4 + w2b);
-            tma_bulk_g2s(smem + Ls.w0, tw.w0, 2u * 128 * F * 4, bar_w0);
-            if (hsh) tma_bulk_g2s(smem + Ls.w2, tw.w2[4], w2b, bar_w0);
-            if (d.head_mask) {
-                const int h0 = __ffs(d.head_mask) - 1;
-                mbar_expect_tx(bar_w1, 2u * 65536);
-                tma_bulk_g2s(smem + Ls.w1, tw.w1[h0], 65536, bar_w1);
-                tma_bulk_g2s(smem + Ls.w1 + 65536, tw.w1[h0] + 16384, 65536, bar_w1);
-            }
+    // ---- resident operands: W0 and (when active) the SH head's W2 image; first head's W1
+    if (issuer) {
+        const uint32_t w2b = hsh ? 2u * 48 * 128 * 4 : 0u;
+        mbar_expect_tx(bar_w0, 2u * 128 * F * 4 + w2b);
+        tma_bulk_g2s(smem + Ls.w0, tw.w0, 2u * 128 * F * 4, bar_w0);
+        if (hsh) tma_bulk_g2s(smem + Ls.w2, tw.w2[4], w2b, bar_w0);
+        if (d.head_mask) {
+            const int h0 = __ffs(d.head_mask) - 1;
+            mbar_expect_tx(bar_w1, 2u * 65536);
+            tma_bulk_g2s(smem + Ls.w1, tw.w1[h0], 65536, bar_w1);
+            tma_bulk_g2s(smem + Ls.w1 + 65536, tw.w1[h0] + 16384, 65536, bar_w1);
         }
-        mbar_wait(bar_w0, 0);
-        uint32_t ph_w1 = 0, ph_mma = 0;
-        bool first = true;
-        // optional per-phase cycle accounting (issuer thread; G4D debug only)
-        long long cyc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        long long tprev = clock64();
-#define G4D_CYC(i) do { if (tw.dbg && issuer) { const long long tn_ = clock64(); cyc[i] += tn_ - tprev; tprev = tn_; } } while (0)
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
-            const int64_t gi = tile * 128 + row;
-            const bool valid = gi < n;
-            Vec3 p{0.f, 0.f, 0.f};
-            float sl[3] = {0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f}, ol = 0.f;
-            if (valid) {
-                p = Vec3{io.xyz[3 * gi], io.xyz[3 * gi + 1], io.xyz[3 * gi + 2]};
-                if (io.scaling) { sl[0] = io.scaling[3 * gi]; sl[1] = io.scaling[3 * gi + 1]; sl[2] = io.scaling[3 * gi + 2]; }
-                if (io.rotation) { const float4 r4 = *reinterpret_cast<const float4*>(io.rotation + 4 * gi); q[0] = r4.x; q[1] = r4.y; q[2] = r4.z; q[3] = r4.w; }
-                if (io.opacity) ol = io.opacity[gi];
+    }
+    if (is_m) mbar_wait(bar_w0, 0);
+    uint32_t ph_w1 = 0, ph_l0 = 0, ph_l1 = 0, ph_l2 = 0;
+    // column chunks (16 hidden units each) of every epilogue are split between the two thread groups
+    const int ch_lo = is_m ? 4 : 0, ch_hi = is_m ? 8 : 4;        // full-width epilogues (8 chunks)
+    const int hc_lo = is_m ? 2 : 0, hc_hi = is_m ? 4 : 2;        // half-width epilogues of the SH head (4 chunks)
+    float4* sAcc = reinterpret_cast<float4*>(smem + Ls.acc);     // [2][128]: G group's partial layer-2 sums of a small head
+
+    // features of a tile ([N][F] fp32, written by deform_features_kernel at full occupancy) -> A operand X (hi | lo)
+    auto stage_features = [&](int64_t tl) {
+        const int64_t gs = tl * 128 + row;
+        float feat[F];
+        if (gs < n) {
+            const float4* src = reinterpret_cast<const float4*>(tw.feat + gs * F);
+#pragma unroll
+            for (int c = 0; c < F; c += 4) {
+                const float4 t4 = __ldg(src + (c >> 2));
+                feat[c] = t4.x; feat[c + 1] = t4.y; feat[c + 2] = t4.z; feat[c + 3] = t4.w;
             }
-            G4D_CYC(0);   // input loads
-            // ---- layer 0: D = feat * W0^T   (features were put into X by the G group)
+        } else {
+#pragma unroll
+            for (int c = 0; c < F; ++c) feat[c] = 0.f;
+        }
+        if (tl != (int64_t)blockIdx.x) { bar_sync(kBarXFree, 256); tc::fence_after_sync(); }
+#pragma unroll
+        for (int c0 = 0; c0 < F; c0 += 8) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tc::tf32_split(feat[c0 + j], hi[j], lo[j]);
+            tc::tmem_st8(lane_base + kColX + c0, hi);
+            tc::tmem_st8(lane_base + kColXLo + c0, lo);
+        }
+        tc::wait_st();
+        tc::fence_before_sync();
+        bar_arrive(kBarFeat, 256);
+    };
+    if (!is_m && blockIdx.x < ntiles) stage_features(blockIdx.x);
+
+    // optional per-phase cycle accounting (issuer thread; G4D debug only)
+    long long cyc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
+#define G4D_CYC(i) do { if (tw.dbg && issuer) { const long long tn_ = clock64(); cyc[i] += tn_ - tprev; tprev = tn_; } } while (0)
+    bool first = true;
+    int hseq = 0;   // running small-head counter -> sAcc buffer
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
+        const int64_t gi = tile * 128 + row;
+        const bool valid = gi < n;
+        const bool has_next = tile + gridDim.x < ntiles;
+        Vec3 p{0.f, 0.f, 0.f};
+        float sl[3] = {0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f}, ol = 0.f;
+        if (is_m && valid) {
+            p = Vec3{io.xyz[3 * gi], io.xyz[3 * gi + 1], io.xyz[3 * gi + 2]};
+            if (io.scaling) { sl[0] = io.scaling[3 * gi]; sl[1] = io.scaling[3 * gi + 1]; sl[2] = io.scaling[3 * gi + 2]; }
+            if (io.rotation) { const float4 r4 = *reinterpret_cast<const float4*>(io.rotation + 4 * gi); q[0] = r4.x; q[1] = r4.y; q[2] = r4.z; q[3] = r4.w; }
+            if (io.opacity) ol = io.opacity[gi];
+        }
+        G4D_CYC(0);   // input loads
+        // ---- layer 0: D = feat * W0^T   (features were put into X by the G group)
+        if (is_m) {
             bar_sync(kBarFeat, 256);
             G4D_CYC(1);   // wait for the features
             if (issuer) {
                 tc::fence_after_sync();
                 tc::gemm_3xtf32<F>(tbase + kColD, tbase + kColX, tbase + kColXLo, sW0, sW0 + 128u * F * 4, 128, F, 0, false);
-                tc::umma_commit(bar_mma);
+                tc::umma_commit(bar_l0);
             }
-            mbar_wait(bar_mma, ph_mma); ph_mma ^= 1u;
-            tc::fence_after_sync();
-            G4D_CYC(2);   // layer-0 MMA
-            if (!first) { bar_sync(kBarScratchFree, 256); tc::fence_after_sync(); }   // G has read the previous tile's scratch (A1 region)
-            G4D_CYC(3);   // wait scratch free
-            // ---- epilogue 0: a1 = relu(D + b0) -> A1 (hi | lo)
-            uint64_t rb0 = 0ull, rb1 = 0ull;   // ReLU sign bits of this row, saved for the backward (bit j <=> pre-activation j > 0)
+        }
+        mbar_wait(bar_l0, ph_l0); ph_l0 ^= 1u;
+        tc::fence_after_sync();
+        G4D_CYC(2);   // layer-0 MMA
+        if (is_m && !first) { bar_sync(kBarScratchFree, 256); tc::fence_after_sync(); }   // G has read the previous tile's scratch (A1 region)
+        G4D_CYC(3);   // wait scratch free
+        // ---- epilogue 0: a1 = relu(D + b0) -> A1 (hi | lo); ReLU sign bits saved for the backward
+        uint32_t rb[4] = {0u, 0u, 0u, 0u};   // my chunks' sign bits: 2 chunks per word
 #pragma unroll 1
-            for (int ch = 0; ch < 8; ++ch) {
-                const uint32_t c0 = (uint32_t)(ch * 16);
-                uint32_t v[16], hi[16], lo[16];
-                tc::tmem_ld16(lane_base + kColD + c0, v);
-                tc::wait_ld();
-                float bb[16];
+        for (int ch = ch_lo; ch < ch_hi; ++ch) {
+            const uint32_t c0 = (uint32_t)(ch * 16);
+            uint32_t v[16], hi[16], lo[16];
+            tc::tmem_ld16(lane_base + kColD + c0, v);
+            tc::wait_ld();
+            float bb[16];
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(sBias + c0 + j);
-                    bb[j] = b4.x; bb[j + 1] = b4.y; bb[j + 2] = b4.z; bb[j + 3] = b4.w;
-                }
-                uint32_t bits = 0;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float x = __uint_as_float(v[j]) + bb[j];
-                    if (SAVE && x > 0.f) bits |= 1u << j;
-                    tc::tf32_split(fmaxf(x, 0.f), hi[j], lo[j]);
-                }
-                if (ch < 4) rb0 |= (uint64_t)bits << (ch * 16); else rb1 |= (uint64_t)bits << ((ch - 4) * 16);
-                tc::tmem_st16(lane_base + kColA1Hi + c0, hi);
-                tc::tmem_st16(lane_base + kColA1Lo + c0, lo);
+            for (int j = 0; j < 16; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(sBias + c0 + j);
+                bb[j] = b4.x; bb[j + 1] = b4.y; bb[j + 2] = b4.z; bb[j + 3] = b4.w;
             }
-            if (SAVE && valid) store_relu_bits(tw.relu_bits, 0, n, gi, rb0, rb1);
-            tc::wait_st();
-            tc::fence_before_sync();
-            bar_sync(kBarM, 128);
-            G4D_CYC(4);   // epilogue 0
+            uint32_t bits = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float x = __uint_as_float(v[j]) + bb[j];
+                if (SAVE && x > 0.f) bits |= 1u << j;
+                tc::tf32_split(fmaxf(x, 0.f), hi[j], lo[j]);
+            }
+            if (SAVE) { const int k = ch - ch_lo; if (k < 2) rb[0] |= bits << (k * 16); else rb[1] |= bits << ((k - 2) * 16); }
+            tc::tmem_st16(lane_base + kColA1Hi + c0, hi);
+            tc::tmem_st16(lane_base + kColA1Lo + c0, lo);
+        }
+        if (SAVE && valid) store_relu_half(tw.relu_bits, 0, n, gi, is_m ? 2 : 0, rb[0], rb[1]);
+        tc::wait_st();
+        tc::fence_before_sync();
+        bar_sync(kBarE, 256);
+        G4D_CYC(4);   // epilogue 0
 
-            float dl[11];
+        float dl[11];
 #pragma unroll
-            for (int j = 0; j < 11; ++j) dl[j] = 0.f;
-            float dsh[48];
+        for (int j = 0; j < 11; ++j) dl[j] = 0.f;
+        float dsh[48];
 #pragma unroll
-            for (int j = 0; j < 48; ++j) dsh[j] = 0.f;
+        for (int j = 0; j < 48; ++j) dsh[j] = 0.f;
 
 #pragma unroll 1
-            for (int h = 0; h < G4D_NUM_HEADS; ++h) {
-                if (!(d.head_mask & (1 << h))) continue;
-                const float* b1 = sBias + 128 + h * 128;
-                const float* b2 = sBias + 128 + G4D_NUM_HEADS * 128 + b2off_of(d.head_mask, h);
-                int nh = -1;   // next head whose W1 goes into the buffer once this head has released it
-                {
-                    const int later = d.head_mask >> (h + 1);
-                    if (later) nh = h + 1 + (__ffs(later) - 1);
-                    else if (tile + gridDim.x < ntiles) nh = __ffs(d.head_mask) - 1;
-                }
-                // ---- layer 1: D = a1 * W1^T
+        for (int h = 0; h < G4D_NUM_HEADS; ++h) {
+            if (!(d.head_mask & (1 << h))) continue;
+            const float* b1 = sBias + 128 + h * 128;
+            const float* b2 = sBias + 128 + G4D_NUM_HEADS * 128 + b2off_of(d.head_mask, h);
+            int nh = -1;   // next head whose W1 goes into the buffer once this head has released it
+            {
+                const int later = d.head_mask >> (h + 1);
+                if (later) nh = h + 1 + (__ffs(later) - 1);
+                else if (has_next) nh = __ffs(d.head_mask) - 1;
+            }
+            // ---- layer 1: D = a1 * W1^T
+            if (is_m) {
                 mbar_wait(bar_w1, ph_w1); ph_w1 ^= 1u;
                 G4D_CYC(5);   // wait W1
                 if (issuer) {
                     tc::fence_after_sync();
                     tc::gemm_3xtf32<128>(tbase + kColD, tbase + kColA1Hi, tbase + kColA1Lo, sW1, sW1 + 65536u, 128, 128, 0, false);
-                    tc::umma_commit(bar_mma);
+                    tc::umma_commit(bar_l1);
                 }
-                mbar_wait(bar_mma, ph_mma); ph_mma ^= 1u;
-                tc::fence_after_sync();
-                G4D_CYC(6);   // layer-1 MMA
-                if (issuer && nh >= 0) {   // W1 buffer is free: stream the next W1
-                    mbar_expect_tx(bar_w1, 2u * 65536);
-                    tma_bulk_g2s(smem + Ls.w1, tw.w1[nh], 65536, bar_w1);
-                    tma_bulk_g2s(smem + Ls.w1 + 65536, tw.w1[nh] + 16384, 65536, bar_w1);
-                }
-                if (h < 4) {
-                    // ---- small head: layer 2 (k <= 4 outputs) fused into the epilogue in exact fp32 -- cheaper than two
-                    //      tensor-core round trips for a 128 x 4 x 128 GEMM
-                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float4* w2 = sW2s + h * 128;
-                    rb0 = rb1 = 0ull;
+            }
+            mbar_wait(bar_l1, ph_l1); ph_l1 ^= 1u;
+            tc::fence_after_sync();
+            G4D_CYC(6);   // layer-1 MMA
+            if (issuer && nh >= 0) {   // W1 buffer is free: stream the next W1
+                mbar_expect_tx(bar_w1, 2u * 65536);
+                tma_bulk_g2s(smem + Ls.w1, tw.w1[nh], 65536, bar_w1);
+                tma_bulk_g2s(smem + Ls.w1 + 65536, tw.w1[nh] + 16384, 65536, bar_w1);
+            }
+            rb[0] = rb[1] = rb[2] = rb[3] = 0u;
+            if (h < 4) {
+                // ---- small head: layer 2 (k <= 4 outputs) fused into the epilogue in exact fp32 -- cheaper than two
+                //      tensor-core round trips for a 128 x 4 x 128 GEMM.  Each group sums its own hidden units.
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4* w2 = sW2s + h * 128;
 #pragma unroll 1
-                    for (int ch = 0; ch < 8; ++ch) {
-                        uint32_t v[16];
-                        tc::tmem_ld16(lane_base + kColD + ch * 16, v);
+                for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                    uint32_t v[16];
+                    tc::tmem_ld16(lane_base + kColD + ch * 16, v);
+                    tc::wait_ld();
+                    float bb[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(b1 + ch * 16 + j);
+                        bb[j] = b4.x; bb[j + 1] = b4.y; bb[j + 2] = b4.z; bb[j + 3] = b4.w;
+                    }
+                    uint32_t bits = 0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float x = __uint_as_float(v[j]) + bb[j];
+                        if (SAVE && x > 0.f) bits |= 1u << j;
+                        const float a2 = fmaxf(x, 0.f);
+                        const float4 w = w2[ch * 16 + j];
+                        acc.x = fmaf(a2, w.x, acc.x); acc.y = fmaf(a2, w.y, acc.y);
+                        acc.z = fmaf(a2, w.z, acc.z); acc.w = fmaf(a2, w.w, acc.w);
+                    }
+                    if (SAVE) { const int k = ch - ch_lo; if (k < 2) rb[0] |= bits << (k * 16); else rb[1] |= bits << ((k - 2) * 16); }
+                }
+                if (SAVE && valid) store_relu_half(tw.relu_bits, 1 + h, n, gi, is_m ? 2 : 0, rb[0], rb[1]);
+                float4* slot = sAcc + (hseq & 1) * 128 + row;
+                if (!is_m) *slot = acc;
+                tc::fence_before_sync();
+                bar_sync(kBarE, 256);   // partial sums visible; D may be overwritten by the next layer-1 GEMM
+                if (is_m) {
+                    // fixed summation order: (G's hidden units 0..63) + (M's hidden units 64..127)
+                    const float4 ga = *slot;
+                    acc = make_float4(ga.x + acc.x, ga.y + acc.y, ga.z + acc.z, ga.w + acc.w);
+                    if (h == 0) { dl[0] = acc.x + b2[0]; dl[1] = acc.y + b2[1]; dl[2] = acc.z + b2[2]; }
+                    else if (h == 1) { dl[3] = acc.x + b2[0]; dl[4] = acc.y + b2[1]; dl[5] = acc.z + b2[2]; }
+                    else if (h == 2) { dl[6] = acc.x + b2[0]; dl[7] = acc.y + b2[1]; dl[8] = acc.z + b2[2]; dl[9] = acc.w + b2[3]; }
+                    else { dl[10] = acc.x + b2[0]; }
+                }
+                ++hseq;
+                G4D_CYC(8);   // small-head epilogue + fp32 layer 2
+            } else {
+#pragma unroll 1
+                for (int hh = 0; hh < 2; ++hh) {
+                    // hidden half hh: a2 = relu(D[:, 64hh : 64hh+64] + b1) -> X (hi | lo)
+#pragma unroll 1
+                    for (int ch = hc_lo; ch < hc_hi; ++ch) {
+                        const uint32_t cl = (uint32_t)(ch * 16);
+                        const uint32_t cg = (uint32_t)(hh * 64) + cl;
+                        uint32_t v[16], hi[16], lo[16];
+                        tc::tmem_ld16(lane_base + kColD + cg, v);
                         tc::wait_ld();
                         float bb[16];
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(b1 + ch * 16 + j);
+                            const float4 b4 = *reinterpret_cast<const float4*>(b1 + cg + j);
                             bb[j] = b4.x; bb[j + 1] = b4.y; bb[j + 2] = b4.z; bb[j + 3] = b4.w;
                         }
                         uint32_t bits = 0;
@@ -362,64 +452,33 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                         for (int j = 0; j < 16; ++j) {
                             const float x = __uint_as_float(v[j]) + bb[j];
                             if (SAVE && x > 0.f) bits |= 1u << j;
-                            const float a2 = fmaxf(x, 0.f);
-                            const float4 w = w2[ch * 16 + j];
-                            acc.x = fmaf(a2, w.x, acc.x); acc.y = fmaf(a2, w.y, acc.y);
-                            acc.z = fmaf(a2, w.z, acc.z); acc.w = fmaf(a2, w.w, acc.w);
+                            tc::tf32_split(fmaxf(x, 0.f), hi[j], lo[j]);
                         }
-                        if (ch < 4) rb0 |= (uint64_t)bits << (ch * 16); else rb1 |= (uint64_t)bits << ((ch - 4) * 16);
+                        if (SAVE) { if (hh == 0) rb[0] |= bits << ((ch - hc_lo) * 16); else rb[1] |= bits << ((ch - hc_lo) * 16); }
+                        tc::tmem_st16(lane_base + kColX + cl, hi);
+                        tc::tmem_st16(lane_base + kColXLo + cl, lo);
                     }
-                    if (SAVE && valid) store_relu_bits(tw.relu_bits, 1 + h, n, gi, rb0, rb1);
-                    if (h == 0) { dl[0] = acc.x + b2[0]; dl[1] = acc.y + b2[1]; dl[2] = acc.z + b2[2]; }
-                    else if (h == 1) { dl[3] = acc.x + b2[0]; dl[4] = acc.y + b2[1]; dl[5] = acc.z + b2[2]; }
-                    else if (h == 2) { dl[6] = acc.x + b2[0]; dl[7] = acc.y + b2[1]; dl[8] = acc.z + b2[2]; dl[9] = acc.w + b2[3]; }
-                    else { dl[10] = acc.x + b2[0]; }
-                    G4D_CYC(8);   // small-head epilogue + fp32 layer 2
-                } else {
-                    rb0 = rb1 = 0ull;
-#pragma unroll 1
-                    for (int hh = 0; hh < 2; ++hh) {
-                        // hidden half hh: a2 = relu(D[:, 64hh : 64hh+64] + b1) -> X (hi | lo)
-#pragma unroll 1
-                        for (int ch = 0; ch < 4; ++ch) {
-                            const uint32_t cl = (uint32_t)(ch * 16);
-                            const uint32_t cg = (uint32_t)(hh * 64) + cl;
-                            uint32_t v[16], hi[16], lo[16];
-                            tc::tmem_ld16(lane_base + kColD + cg, v);
-                            tc::wait_ld();
-                            float bb[16];
-#pragma unroll
-                            for (int j = 0; j < 16; j += 4) {
-                                const float4 b4 = *reinterpret_cast<const float4*>(b1 + cg + j);
-                                bb[j] = b4.x; bb[j + 1] = b4.y; bb[j + 2] = b4.z; bb[j + 3] = b4.w;
-                            }
-                            uint32_t bits = 0;
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const float x = __uint_as_float(v[j]) + bb[j];
-                                if (SAVE && x > 0.f) bits |= 1u << j;
-                                tc::tf32_split(fmaxf(x, 0.f), hi[j], lo[j]);
-                            }
-                            if (hh == 0) rb0 |= (uint64_t)bits << (ch * 16); else rb1 |= (uint64_t)bits << (ch * 16);
-                            tc::tmem_st16(lane_base + kColX + cl, hi);
-                            tc::tmem_st16(lane_base + kColXLo + cl, lo);
-                        }
-                        if (SAVE && hh == 1 && valid) store_relu_bits(tw.relu_bits, 1 + h, n, gi, rb0, rb1);
-                        tc::wait_st();
-                        tc::fence_before_sync();
-                        bar_sync(kBarM, 128);
-                        G4D_CYC(8);   // hidden-half epilogue
-                        // ---- layer 2 partial: D2 (+)= a2_half * W2[:, 64hh : 64hh+64]^T   (D2 = D columns [0, 48))
-                        if (issuer) {
-                            tc::fence_after_sync();
-                            tc::gemm_3xtf32<64>(tbase + kColD, tbase + kColX, tbase + kColXLo, sW2, sW2 + 48u * 128 * 4, 48, 128,
-                                                (uint32_t)(hh * 16), hh == 1);
-                            tc::umma_commit(bar_mma);
-                        }
-                        mbar_wait(bar_mma, ph_mma); ph_mma ^= 1u;
+                    tc::wait_st();
+                    tc::fence_before_sync();
+                    bar_sync(kBarE, 256);
+                    G4D_CYC(8);   // hidden-half epilogue
+                    // ---- layer 2 partial: D2 (+)= a2_half * W2[:, 64hh : 64hh+64]^T   (D2 = D columns [0, 48))
+                    if (issuer) {
                         tc::fence_after_sync();
-                        G4D_CYC(9);   // layer-2 partial MMA
+                        tc::gemm_3xtf32<64>(tbase + kColD, tbase + kColX, tbase + kColXLo, sW2, sW2 + 48u * 128 * 4, 48, 128,
+                                            (uint32_t)(hh * 16), hh == 1);
+                        tc::umma_commit(bar_l2);
                     }
+                    mbar_wait(bar_l2, ph_l2); ph_l2 ^= 1u;
+                    tc::fence_after_sync();
+                    G4D_CYC(9);   // layer-2 partial MMA
+                }
+                // sign bits of the SH head: word w of the 128-bit row = hidden units [32w, 32w+32); G owns words 0 and 2
+                if (SAVE && valid) {
+                    uint32_t* dst = tw.relu_bits + ((size_t)(1 + h) * (size_t)n + (size_t)gi) * 4 + (is_m ? 1 : 0);
+                    dst[0] = rb[0]; dst[2] = rb[1];
+                }
+                if (is_m) {
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch) {
                         uint32_t v[16];
@@ -428,12 +487,14 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
 #pragma unroll
                         for (int j = 0; j < 16; ++j) dsh[ch * 16 + j] = __uint_as_float(v[j]) + b2[ch * 16 + j];
                     }
+                    tc::fence_before_sync();
+                    bar_sync(kBarM, 128);   // D may be overwritten by the next layer-1 / layer-0 GEMM
                 }
-                tc::fence_before_sync();
-                bar_sync(kBarM, 128);   // D may be overwritten by the next layer-1 GEMM
-                G4D_CYC(10);  // head output / hand-over
             }
-            bar_arrive(kBarXFree, 256);   // every MMA reading X has completed: G may store the next tile's features
+            G4D_CYC(10);  // head output / hand-over
+        }
+        if (is_m) {
+            if (has_next) bar_arrive(kBarXFree, 256);   // every MMA reading X has completed: G may store the next tile's features
             p.x += dl[0]; p.y += dl[1]; p.z += dl[2];
             // ---- hand the deformed position and the SH deltas to the G thread of this lane (A1 is dead now)
             {
@@ -467,50 +528,14 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                 }
             }
             G4D_CYC(11);  // scratch hand-off + geometry tail
-        }
-        if (!first) { bar_sync(kBarScratchFree, 256); }   // pair the G group's last arrive
-        if (tw.dbg && issuer) {
-            for (int i = 0; i < 12; ++i) tw.dbg[blockIdx.x * 12 + i] = cyc[i];
-        }
-#undef G4D_CYC
-    } else {
-        // =========================================== G group ===========================================
-        float feat[F];
-        int64_t tile = blockIdx.x;
-        auto sample_tile = [&](int64_t tl) {
-            const int64_t gi = tl * 128 + row;
-            float pcs[3] = {0.f, 0.f, 0.f};
-            if (gi < n) {
-                pcs[0] = (io.xyz[3 * gi] - amax[0]) * ascale[0] - 1.0f;
-                pcs[1] = (io.xyz[3 * gi + 1] - amax[1]) * ascale[1] - 1.0f;
-                pcs[2] = (io.xyz[3 * gi + 2] - amax[2]) * ascale[2] - 1.0f;
-            }
-            sample_features_regs<C, L>(&sd, pcs, feat);
-        };
-        if (tile < ntiles) sample_tile(tile);
-        bool first = true;
-        for (; tile < ntiles; tile += gridDim.x, first = false) {
-            const int64_t gi = tile * 128 + row;
-            const bool valid = gi < n;
-            if (!first) { bar_sync(kBarXFree, 256); tc::fence_after_sync(); }
-#pragma unroll
-            for (int c0 = 0; c0 < F; c0 += 8) {
-                uint32_t hi[8], lo[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) tc::tf32_split(feat[c0 + j], hi[j], lo[j]);
-                tc::tmem_st8(lane_base + kColX + c0, hi);
-                tc::tmem_st8(lane_base + kColXLo + c0, lo);
-            }
-            tc::wait_st();
-            tc::fence_before_sync();
-            bar_arrive(kBarFeat, 256);
-            if (tile + gridDim.x < ntiles) sample_tile(tile + gridDim.x);   // overlaps with the tensor-core work on `tile`
-            // ---- SH colour of my Gaussian once the M group has published p and the SH deltas
+        } else {
+            // ---- G tail: next tile's features, then the SH colour of my Gaussian once M has published p and the SH deltas
+            if (has_next) stage_features(tile + gridDim.x);
             bar_sync(kBarScratch, 256);
             tc::fence_after_sync();
             uint32_t s8[8];
             tc::tmem_ld8(lane_base + kColScratch, s8);
-            float dsh[48];
+            float gsh[48];
             if (hsh) {
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
@@ -518,34 +543,66 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                     tc::tmem_ld16(lane_base + kColScratch + 8 + ch * 16, v);
                     tc::wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) dsh[ch * 16 + j] = __uint_as_float(v[j]);
+                    for (int j = 0; j < 16; ++j) gsh[ch * 16 + j] = __uint_as_float(v[j]);
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < 48; ++j) dsh[j] = 0.f;
+                for (int j = 0; j < 48; ++j) gsh[j] = 0.f;
             }
             tc::wait_ld();
             tc::fence_before_sync();
             bar_arrive(kBarScratchFree, 256);
             if (valid) {
-                const Vec3 p{__uint_as_float(s8[0]), __uint_as_float(s8[1]), __uint_as_float(s8[2])};
+                const Vec3 pg{__uint_as_float(s8[0]), __uint_as_float(s8[1]), __uint_as_float(s8[2])};
                 if (MODE == 0) {
                     if (io.out_shs && hsh) {
 #pragma unroll
                         for (int j = 0; j < 48; j += 4) {
                             const float4 b = *reinterpret_cast<const float4*>(io.shs + gi * 48 + j);
-                            *reinterpret_cast<float4*>(io.out_shs + gi * 48 + j) = make_float4(b.x + dsh[j], b.y + dsh[j + 1], b.z + dsh[j + 2], b.w + dsh[j + 3]);
+                            *reinterpret_cast<float4*>(io.out_shs + gi * 48 + j) = make_float4(b.x + gsh[j], b.y + gsh[j + 1], b.z + gsh[j + 2], b.w + gsh[j + 3]);
                         }
                     }
                 } else {
-                    fused_finish_colour(cam, io, gi, p, hsh, dsh);
+                    fused_finish_colour(cam, io, gi, pg, hsh, gsh);
                 }
             }
         }
     }
+    if (is_m && !first) { bar_sync(kBarScratchFree, 256); }   // pair the G group's last arrive
+    if (tw.dbg && issuer) {
+        for (int i = 0; i < 12; ++i) tw.dbg[blockIdx.x * 12 + i] = cyc[i];
+    }
+#undef G4D_CYC
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tbase, tc::kTmemCols);
+}
+
+// ---- HexPlane gather at full occupancy: C/4 threads per Gaussian, one channel vector each -> feat [N][F] fp32 -----------
+template <int C4>
+__global__ void __launch_bounds__(256) deform_features_kernel(DeformDesc d, int64_t n, const float* __restrict__ xyz, float* __restrict__ feat) {
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t g = t / C4;
+    const int v = (int)(t % C4);
+    if (g >= n) return;
+    float pcs[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float amax = __ldg(d.aabb + a), ascale = 2.0f / (__ldg(d.aabb + 3 + a) - amax);
+        pcs[a] = (xyz[3 * g + a] - amax) * ascale - 1.0f;
+    }
+    for (int l = 0; l < d.levels; ++l)
+        *reinterpret_cast<float4*>(feat + g * d.F + l * d.C + 4 * v) = sample_vector(&d, l, v, C4, pcs[0], pcs[1], pcs[2]);
+}
+
+cudaError_t launch_deform_features(const DeformDesc& d, int64_t n, const float* xyz, float* feat, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const int C4 = d.C / 4;
+    const unsigned grid = (unsigned)((n * C4 + 255) / 256);
+    if (C4 == 4) deform_features_kernel<4><<<grid, 256, 0, st>>>(d, n, xyz, feat);
+    else if (C4 == 8) deform_features_kernel<8><<<grid, 256, 0, st>>>(d, n, xyz, feat);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
 }
 
 bool tc_deform_supported(const DeformDesc& d) {
@@ -575,6 +632,11 @@ static cudaError_t launch_deform_tc_t(const DeformDesc& d, const TcWeights& tw, 
 cudaError_t launch_deform_tc(const DeformDesc& d, const TcWeights& tw, int mode, const CameraDev* cam, float time,
                              bool use_cam_time, int64_t n, const DeformIO& io, int sm_count, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
+    if (!tw.feat) return cudaErrorInvalidValue;
+    {
+        cudaError_t e = launch_deform_features(d, n, io.xyz, tw.feat, st);
+        if (e != cudaSuccess) return e;
+    }
     const int max_kp = (d.head_mask & G4D_HEAD_SHS) ? 48 : 16;
     const TcSmem Ls = tc_smem_layout(d.F, max_kp);
     const size_t bytes = Ls.total + 1024;

@@ -53,6 +53,7 @@ struct TcWeights {
     const float* w2[G4D_NUM_HEADS];    // packed (hi | lo), [kp16][128]
     int kp16[G4D_NUM_HEADS];
     long long* dbg;                    // optional [grid][12] per-phase cycle counters (debug)
+    float* feat;                       // [N][F] fp32 staging of the HexPlane features (deform_features_kernel)
     uint32_t* relu_bits;               // optional [6][N][4]: ReLU sign bits saved for the backward (G4D_RELU_BITS_WORDS)
 };
 
