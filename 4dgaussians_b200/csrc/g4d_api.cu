@@ -129,12 +129,13 @@ int ensure_geom(G4DContext* c, int64_t n) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
     const size_t o0 = take(N * 16), o1 = take(N * 16), o2 = take(N * 8), o3 = take(N * 4), o4 = take(N * 8), o5 = take(N * 4),
-                 o6 = take(N * 4), o7 = take(N);
+                 o6 = take(N * 4), o7 = take(N), o8 = take(N * 4), o9 = take(N * 16);
     G4D_CUDA(c->geom.ensure(off));
     char* base = c->geom.as<char>();
     c->g.rec0 = (float4*)(base + o0); c->g.rec1 = (float4*)(base + o1); c->g.rec2 = (float2*)(base + o2);
     c->g.radii = (int32_t*)(base + o3); c->g.rect = (uint2*)(base + o4); c->g.tiles_touched = (uint32_t*)(base + o5);
     c->g.offsets = (uint32_t*)(base + o6); c->g.clamped = (uint8_t*)(base + o7);
+    c->g.perm = (uint32_t*)(base + o8); c->g.dkeys = (uint32_t*)(base + o9);
     return G4D_OK;
 }
 
@@ -342,12 +343,13 @@ int bin_and_blend(G4DContext* c, const G4DCamera* cam, int64_t n, float* out_col
     // no-sync needs a capacity learnt from an earlier (synchronous) forward on this context
     const bool nosync = !ws->sync_mode && !(cam->debug & G4D_CAM_DEBUG) && c->capacity > 0 && c->R > 0 && n > 0;
     if (n > 0) {
-        const size_t tb = scan_temp_bytes(n);
+        const size_t tb = depth_order_temp_bytes(n);
         G4D_CUDA(ws->temp.ensure(tb));
         {
             StageTimer tm(c, G4D_STAGE_SCAN, st);
             if (ws->tight_cull) G4D_CUDA(launch_cull_count(n, c->g, st));
-            G4D_CUDA(launch_scan(c->g.tiles_touched, c->g.offsets, n, ws->temp.p, tb, st));
+            // Gaussians in depth order first: the 64-bit (tile | depth) sort then only has to sort on the tile bits
+            G4D_CUDA(launch_depth_order(n, c->g, ws->temp.p, tb, st));
         }
         if (!nosync) {
             G4D_CUDA(cudaMemcpyAsync(ws->h_pinned, c->g.offsets + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -370,7 +372,7 @@ int bin_and_blend(G4DContext* c, const G4DCamera* cam, int64_t n, float* out_col
             const size_t sb = sort_temp_bytes(R);
             G4D_CUDA(ws->temp.ensure(sb));
             StageTimer tm(c, G4D_STAGE_SORT, st);
-            G4D_CUDA(launch_sort(c->b, R, 32 + tile_bits, ws->temp.p, sb, st));
+            G4D_CUDA(launch_sort(c->b, R, 32, 32 + tile_bits, ws->temp.p, sb, st));
         }
         {
             StageTimer tm(c, G4D_STAGE_RANGES, st);
@@ -393,7 +395,7 @@ int bin_and_blend(G4DContext* c, const G4DCamera* cam, int64_t n, float* out_col
         G4D_CUDA(ws->temp.ensure(sb));
         {
             StageTimer tm(c, G4D_STAGE_SORT, st);
-            G4D_CUDA(launch_sort(c->b, cap, 32 + tile_bits + 1, ws->temp.p, sb, st));
+            G4D_CUDA(launch_sort(c->b, cap, 32, 32 + tile_bits + 1, ws->temp.p, sb, st));
         }
         StageTimer tm(c, G4D_STAGE_RANGES, st);
         G4D_CUDA(launch_tile_ranges(c->b, cap, num_tiles, st));

@@ -16,7 +16,9 @@ struct GeomBuffers {
     int32_t* radii;
     uint2* rect;         // x = minx | miny<<16, y = maxx | maxy<<16   (tile units)
     uint32_t* tiles_touched;
-    uint32_t* offsets;   // inclusive scan of tiles_touched
+    uint32_t* offsets;   // inclusive scan of tiles_touched IN DEPTH ORDER: offsets[k] belongs to Gaussian perm[k]
+    uint32_t* perm;      // Gaussian indices sorted by (depth bits, index); invisible ones last
+    uint32_t* dkeys;     // [4][N] scratch of the depth sort: keys in / keys out / iota / (unused)
     uint8_t* clamped;    // bit ch set when the forward clamped colour channel ch at 0
 };
 
@@ -92,12 +94,15 @@ cudaError_t launch_deform(const DeformDesc& d, int mode, const CameraDev* cam, f
                           int32_t* out_radii, int sm_count, cudaStream_t st, const TcWeights* tw = nullptr);
 
 size_t scan_temp_bytes(int64_t n);
+// depth order of the visible Gaussians + inclusive scan of tiles_touched in that order (g.perm, g.offsets)
+size_t depth_order_temp_bytes(int64_t n);
+cudaError_t launch_depth_order(int64_t n, GeomBuffers g, void* temp, size_t temp_bytes, cudaStream_t st);
 size_t sort_temp_bytes(int64_t r);
 cudaError_t launch_scan(const uint32_t* in, uint32_t* out, int64_t n, void* temp, size_t temp_bytes, cudaStream_t st);
 cudaError_t launch_cull_count(int64_t n, GeomBuffers g, cudaStream_t st);
 cudaError_t launch_emit_keys(const CameraDev* cam, int64_t n, GeomBuffers g, BinBuffers b, int64_t capacity, int tight,
                              cudaStream_t st);
-cudaError_t launch_sort(BinBuffers b, int64_t r, int end_bit, void* temp, size_t temp_bytes, cudaStream_t st);
+cudaError_t launch_sort(BinBuffers b, int64_t r, int begin_bit, int end_bit, void* temp, size_t temp_bytes, cudaStream_t st);
 cudaError_t launch_tile_ranges(BinBuffers b, int64_t r, int num_tiles, cudaStream_t st);
 cudaError_t launch_blend_forward(const CameraDev* cam, int grid_x, int grid_y, GeomBuffers g, BinBuffers b, ImageBuffers im,
                                  float* out_color, float* out_depth, cudaStream_t st);

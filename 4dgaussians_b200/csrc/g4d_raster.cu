@@ -24,6 +24,41 @@ cudaError_t launch_scan(const uint32_t* in, uint32_t* out, int64_t n, void* temp
     return cub::DeviceScan::InclusiveSum(temp, temp_bytes, in, out, (int)n, st);
 }
 
+// ---- depth order -------------------------------------------------------------------------------------------------
+// The reference sorts R (tile | depth) 64-bit keys on 32 + log2(tiles) bits (A.2).  A stable sort of the N Gaussians by
+// depth bits followed by key emission IN THAT ORDER and a stable sort of the R keys on the tile bits alone gives the
+// identical sequence (ties: depth-equal entries keep Gaussian-index order in both) with 2 instead of 6 passes over R.
+struct PermutedCount {
+    const uint32_t* tt; const uint32_t* perm;
+    __host__ __device__ uint32_t operator()(int k) const { return tt[perm[k]]; }
+};
+__global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, GeomBuffers g) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g.dkeys[i] = g.tiles_touched[i] ? __float_as_uint(g.rec2[i].y) : 0xFFFFFFFFu;   // depth > 0.2: sign bit clear, order-preserving
+    g.dkeys[2 * n + i] = (uint32_t)i;
+}
+size_t depth_order_temp_bytes(int64_t n) {
+    size_t a = 0, b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)n);
+    cub::CountingInputIterator<int> cnt(0);
+    cub::TransformInputIterator<uint32_t, PermutedCount, cub::CountingInputIterator<int>> it(cnt, PermutedCount{nullptr, nullptr});
+    cub::DeviceScan::InclusiveSum(nullptr, b, it, (uint32_t*)nullptr, (int)n);
+    return a > b ? a : b;
+}
+cudaError_t launch_depth_order(int64_t n, GeomBuffers g, void* temp, size_t temp_bytes, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    depth_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, g);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, g.dkeys, g.dkeys + n, g.dkeys + 2 * n, g.perm, (int)n, 0, 32, st);
+    if (e != cudaSuccess) return e;
+    cub::CountingInputIterator<int> cnt(0);
+    cub::TransformInputIterator<uint32_t, PermutedCount, cub::CountingInputIterator<int>> it(cnt, PermutedCount{g.tiles_touched, g.perm});
+    return cub::DeviceScan::InclusiveSum(temp, temp_bytes, it, g.offsets, (int)n, st);
+}
+
 // ---- exact-image tile culling (G4D_OPT_TIGHT_CULL) -------------------------------------------------------------
 // A (Gaussian, tile) pair can be dropped without changing a single pixel when even the best-placed point of the
 // tile's pixel rectangle has alpha = opacity * exp(-q/2) < 1/255 (the blend stage skips such contributions, A.3).
@@ -50,18 +85,47 @@ G4D_D bool tile_contributes(float4 r0, float4 r1, int tx, int ty) {
 }
 
 // tight mode: tiles_touched := number of tiles of the rect that can contribute (same predicate as emit_keys_kernel,
-// same translation unit, hence bit-identical decisions)
+// same translation unit, hence bit-identical decisions).
+// Warp-cooperative: a warp owns 32 consecutive Gaussians; for each visible one (broadcast by shuffle) the 32 lanes test
+// 32 tiles of its rect at a time -- a thread-per-Gaussian loop serialises on the largest rect of the warp.
+struct TileJob { float4 r0, r1; int minx, miny, w, ntiles; };
+G4D_D TileJob bcast_job(const float4& r0, const float4& r1, uint2 rc, int src) {
+    TileJob j;
+    j.r0.x = __shfl_sync(0xffffffffu, r0.x, src); j.r0.y = __shfl_sync(0xffffffffu, r0.y, src);
+    j.r0.z = __shfl_sync(0xffffffffu, r0.z, src); j.r0.w = __shfl_sync(0xffffffffu, r0.w, src);
+    j.r1.x = __shfl_sync(0xffffffffu, r1.x, src); j.r1.y = __shfl_sync(0xffffffffu, r1.y, src);
+    j.r1.z = 0.f; j.r1.w = 0.f;
+    const uint32_t rx = __shfl_sync(0xffffffffu, rc.x, src), ry = __shfl_sync(0xffffffffu, rc.y, src);
+    j.minx = rx & 0xFFFF; j.miny = rx >> 16;
+    const int maxx = ry & 0xFFFF, maxy = ry >> 16;
+    j.w = maxx - j.minx;
+    j.ntiles = j.w * (maxy - j.miny);
+    return j;
+}
+
 __global__ void __launch_bounds__(256) cull_count_kernel(int64_t n, GeomBuffers g) {
     const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gi >= n) return;
-    if (g.tiles_touched[gi] == 0) return;
-    const uint2 rc = g.rect[gi];
-    const int minx = rc.x & 0xFFFF, miny = rc.x >> 16, maxx = rc.y & 0xFFFF, maxy = rc.y >> 16;
-    const float4 r0 = g.rec0[gi], r1 = g.rec1[gi];
-    uint32_t cnt = 0;
-    for (int y = miny; y < maxy; ++y)
-        for (int x = minx; x < maxx; ++x) cnt += tile_contributes(r0, r1, x, y) ? 1u : 0u;
-    g.tiles_touched[gi] = cnt;
+    const int lane = threadIdx.x & 31;
+    const bool vis = gi < n && g.tiles_touched[gi] != 0;
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+    uint2 rc = make_uint2(0u, 0u);
+    if (vis) { r0 = g.rec0[gi]; r1 = g.rec1[gi]; rc = g.rect[gi]; }
+    uint32_t todo = __ballot_sync(0xffffffffu, vis);
+    uint32_t mine = 0;
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const TileJob j = bcast_job(r0, r1, rc, src);
+        uint32_t cnt = 0;
+        for (int base = 0; base < j.ntiles; base += 32) {
+            const int t = base + lane;
+            const int ty = t / j.w, tx = t - ty * j.w;
+            const bool c = t < j.ntiles && tile_contributes(j.r0, j.r1, j.minx + tx, j.miny + ty);
+            cnt += __popc(__ballot_sync(0xffffffffu, c));
+        }
+        if (lane == src) mine = cnt;
+    }
+    if (vis) g.tiles_touched[gi] = mine;
 }
 
 cudaError_t launch_cull_count(int64_t n, GeomBuffers g, cudaStream_t st) {
@@ -70,28 +134,48 @@ cudaError_t launch_cull_count(int64_t n, GeomBuffers g, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-// A.2: one (tile | depth bits) key and the Gaussian index per touched tile, at consecutive slots from offsets[i-1]
+// A.2: one (tile | depth bits) key and the Gaussian index per touched tile, at consecutive slots from offsets[i-1],
+// tiles in row-major order of the rect (warp-cooperative like cull_count_kernel)
 __global__ void __launch_bounds__(256) emit_keys_kernel(const CameraDev* __restrict__ cam, int64_t n, GeomBuffers g,
                                                         BinBuffers b, int64_t capacity, int tight) {
-    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gi >= n) return;
-    if (g.tiles_touched[gi] == 0) return;
-    int64_t off = gi == 0 ? 0 : (int64_t)g.offsets[gi - 1];
-    const uint2 rc = g.rect[gi];
-    const int minx = rc.x & 0xFFFF, miny = rc.x >> 16, maxx = rc.y & 0xFFFF, maxy = rc.y >> 16;
-    const uint32_t dbits = __float_as_uint(g.rec2[gi].y);
-    const int gx = cam->grid_x;
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // position in depth order
+    const int lane = threadIdx.x & 31;
+    const uint32_t gi = k < n ? g.perm[k] : 0u;
+    const bool vis = k < n && g.tiles_touched[gi] != 0;
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-    if (tight) { r0 = g.rec0[gi]; r1 = g.rec1[gi]; }
-    for (int y = miny; y < maxy; ++y)
-        for (int x = minx; x < maxx; ++x) {
-            if (tight && !tile_contributes(r0, r1, x, y)) continue;
-            if (off < capacity) {
-                b.keys_unsorted[off] = ((uint64_t)(uint32_t)(y * gx + x) << 32) | dbits;
-                b.ids_unsorted[off] = (uint32_t)gi;
+    uint2 rc = make_uint2(0u, 0u);
+    uint32_t dbits = 0, off0 = 0;
+    if (vis) {
+        rc = g.rect[gi];
+        dbits = __float_as_uint(g.rec2[gi].y);
+        off0 = k == 0 ? 0u : g.offsets[k - 1];
+        if (tight) { r0 = g.rec0[gi]; r1 = g.rec1[gi]; }
+    }
+    const int gx = cam->grid_x;
+    uint32_t todo = __ballot_sync(0xffffffffu, vis);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const TileJob j = bcast_job(r0, r1, rc, src);
+        const uint32_t db = __shfl_sync(0xffffffffu, dbits, src);
+        int64_t off = (int64_t)__shfl_sync(0xffffffffu, off0, src);
+        const uint32_t id = __shfl_sync(0xffffffffu, gi, src);
+        for (int base = 0; base < j.ntiles; base += 32) {
+            const int t = base + lane;
+            const int ty = t / j.w, tx = t - ty * j.w;
+            const int x = j.minx + tx, y = j.miny + ty;
+            const bool c = t < j.ntiles && (!tight || tile_contributes(j.r0, j.r1, x, y));
+            const uint32_t m = __ballot_sync(0xffffffffu, c);
+            if (c) {
+                const int64_t slot = off + __popc(m & ((1u << lane) - 1u));
+                if (slot < capacity) {
+                    b.keys_unsorted[slot] = ((uint64_t)(uint32_t)(y * gx + x) << 32) | db;
+                    b.ids_unsorted[slot] = id;
+                }
             }
-            ++off;
+            off += __popc(m);
         }
+    }
 }
 
 cudaError_t launch_emit_keys(const CameraDev* cam, int64_t n, GeomBuffers g, BinBuffers b, int64_t capacity, int tight,
@@ -101,10 +185,10 @@ cudaError_t launch_emit_keys(const CameraDev* cam, int64_t n, GeomBuffers g, Bin
     return cudaGetLastError();
 }
 
-cudaError_t launch_sort(BinBuffers b, int64_t r, int end_bit, void* temp, size_t temp_bytes, cudaStream_t st) {
+cudaError_t launch_sort(BinBuffers b, int64_t r, int begin_bit, int end_bit, void* temp, size_t temp_bytes, cudaStream_t st) {
     if (r == 0) return cudaSuccess;
     return cub::DeviceRadixSort::SortPairs(temp, temp_bytes, b.keys_unsorted, b.keys_sorted, b.ids_unsorted, b.ids_sorted,
-                                           (int)r, 0, end_bit, st);
+                                           (int)r, begin_bit, end_bit, st);
 }
 
 __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint64_t* __restrict__ keys, int64_t r, uint2* ranges,

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--backward", type=int, default=1)
     ap.add_argument("--stage-times", type=int, default=0)
     ap.add_argument("--tc-debug", type=int, default=0)
+    ap.add_argument("--tight-cull", type=int, default=0)
     a = ap.parse_args()
     g4d = importlib.import_module("4dgaussians_b200")
     synth = importlib.import_module("4dgaussians_b200.synth")
@@ -43,6 +44,8 @@ def main():
         ws.set_option(g4d._lib.OPT_STAGE_TIMING, 1)
     if a.tc_debug:
         ws.set_option(g4d._lib.OPT_TC_DEBUG, 1)
+    if a.tight_cull:
+        ws.set_option(g4d._lib.OPT_TIGHT_CULL, 1)
     for i in range(a.iters):
         cam = cams[i % len(cams)]
         if a.backward:
