@@ -156,7 +156,7 @@ int ensure_image(G4DContext* c, int H, int W) {
 int ensure_bin(G4DContext* c, int64_t r) {
     const size_t R = (size_t)(r > 0 ? r : 1);
     if ((int64_t)R <= c->capacity && c->bin.p) return G4D_OK;
-    const size_t cap = R + R / 4 + 1024;
+    const size_t cap = R + R / 2 + 1024;   // generous head-room: a regrow is a cudaFree + cudaMalloc (device sync)
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
     const size_t o0 = take(cap * 8), o1 = take(cap * 8), o2 = take(cap * 4), o3 = take(cap * 4);

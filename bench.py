@@ -226,11 +226,11 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(tight_ms, op=dist.ReduceOp.MAX)
     tight_value = world * K / (float(tight_ms.item()) / 1e3)
-    train_tight = run_train_steps(g4d, synth, lib, w, scene, mod, dev, dist, world, rank, max(3, min(K, 10)), 3, flush)
+    train_tight = run_train_steps(g4d, synth, lib, w, scene, mod, dev, dist, world, rank, max(3, min(K, 10)), 5, flush)
     ws.set_option(lib.OPT_TIGHT_CULL, 0)
 
     # ------------------------------------------------------------------ training step (B=2 views, fwd+bwd, all-reduce, Adam)
-    train = run_train_steps(g4d, synth, lib, w, scene, mod, dev, dist, world, rank, max(3, min(K, 10)), 3, flush)
+    train = run_train_steps(g4d, synth, lib, w, scene, mod, dev, dist, world, rank, max(3, min(K, 10)), 5, flush)
     clocks = sampler.stop() if rank == 0 else None     # sampled from the start of the timed region to the end of the train steps
 
     if rank == 0:
@@ -244,6 +244,15 @@ def run_ours(args):
         dom_bytes = {"geom": ab["geom"], "blend": ab["blend"], "sort": ab["binning"]}[dom]
         dom_ms = fwd_stages[dom]
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        traffic, traffic_src = None, None
+        try:     # dram bytes per launch of the dominant kernel from the committed ncu --set full capture of this workload
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1c_traffic.json")))
+            bpl = tj["bytes_per_launch"]
+            keys = {"geom": ["deform_tc_kernel<1, 16, 2, 1>", "deform_features_kernel<4>"], "blend": ["blend_forward_kernel"], "sort": []}[dom]
+            if keys and all(k_ in bpl for k_ in keys):
+                traffic, traffic_src = float(sum(bpl[k_] for k_ in keys)), tj["source"]
+        except Exception:
+            pass
         ms_per_step = total_ms / K
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
@@ -265,7 +274,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": {"geom": "deform_tc_kernel<1,16,2> (fused deform+activate+project, tcgen05)",
                                                     "blend": "blend_forward_kernel", "sort": "cub::DeviceRadixSort"}[dom],
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes": dom_bytes, "kernel_ms": dom_ms},
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes": dom_bytes, "kernel_ms": dom_ms},
             "roofline_path": {"what": "whole fused forward, B_fwd of SURVEY 8d", "algorithmic_bytes": ab["total"],
                               "achieved": ab["total"] / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                               "frac": ab["total"] / (ms_per_step * 1e-3) / 1e9 / peak},
@@ -320,7 +329,8 @@ def run_train_steps(g4d, synth, lib, w, scene, mod, dev, dist, world, rank, step
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ctx = lib.Workspace.get(dev.index)._free_contexts
     st = ctx[-1].stage_times() if ctx else {}
-    return {"ms_per_step": float(ms.item()), "views_per_step_per_gpu": B, "global_batch": B * world,
+    return {"ms_per_step": float(ms.item()), "step_ms": [round(x.elapsed_time(y), 3) for x, y in evs],
+            "views_per_step_per_gpu": B, "global_batch": B * world,
             "includes": "2x fused fwd+bwd, L1 loss, one flat-bucket all-reduce (%d floats), fused Adam" % bucket.numel,
             "last_view_stage_ms": st}
 
