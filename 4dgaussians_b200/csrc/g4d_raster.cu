@@ -1,6 +1,8 @@
 // g4d_raster.cu -- tile binning (scan, key emission, radix sort, tile ranges) and the per-tile front-to-back
 // alpha compositing forward / back-to-front backward.   SURVEY.md Appendix A.2-A.4.
 // Reference stage replaced: the CUDA rasterizer behind /root/reference/gaussian_renderer/__init__.py:120-128.
+#include <cstdlib>
+
 #include <cub/cub.cuh>
 
 #include "g4d_internal.h"
@@ -289,42 +291,56 @@ G4D_D float warp_sum(float v) {
     return v;
 }
 
-__global__ void __launch_bounds__(kTilePixels)
+// PPT pixels per thread (256 / PPT threads per tile): the per-Gaussian warp reduction -- half of the instruction count with
+// one pixel per thread -- is shared by PPT x 32 pixels, and the staged record is read once per thread instead of per pixel.
+template <int PPT>
+__global__ void __launch_bounds__(kTilePixels / PPT)
 blend_backward_kernel(const CameraDev* __restrict__ cam, GeomBuffers g, const uint32_t* __restrict__ ids,
                       const uint2* __restrict__ ranges, const float* __restrict__ final_T,
                       const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dcolor,
                       float* __restrict__ g_mean2D, float* __restrict__ g_conic, float* __restrict__ g_opacity,
                       float* __restrict__ g_rgb) {
+    constexpr int NT = kTilePixels / PPT;
     __shared__ float4 s0[kTilePixels];
     __shared__ float4 s1[kTilePixels];
     __shared__ float s2[kTilePixels];
     __shared__ uint32_t sid[kTilePixels];
     const int H = cam->H, W = cam->W;
     const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-    const int lx = threadIdx.x & (kTile - 1), ly = threadIdx.x >> 4;
-    const int px = blockIdx.x * kTile + lx, py = blockIdx.y * kTile + ly;
-    const bool inside = px < W && py < H;
-    const float pxf = (float)px, pyf = (float)py;
     const uint2 range = ranges[tile];
     const int total = (int)(range.y - range.x);
     const int rounds = (total + kTilePixels - 1) / kTilePixels;
-    const size_t pix = (size_t)py * W + px, hw = (size_t)H * W;
-    const float Tfin = inside ? final_T[pix] : 0.f;
-    float T = Tfin;
-    const int last = inside ? (int)n_contrib[pix] : 0;
-    float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
-    if (inside) { dp0 = dL_dcolor[pix]; dp1 = dL_dcolor[hw + pix]; dp2 = dL_dcolor[2 * hw + pix]; }
-    const float bgdot = cam->bg[0] * dp0 + cam->bg[1] * dp1 + cam->bg[2] * dp2;
+    const size_t hw = (size_t)H * W;
+    // pixel k of this thread: index threadIdx.x + k * NT inside the 16 x 16 tile (consecutive threads -> consecutive pixels)
+    float pxf[PPT], pyf[PPT], Tfin[PPT], T[PPT], dp0[PPT], dp1[PPT], dp2[PPT], bgdot[PPT];
+    float ac0[PPT], ac1[PPT], ac2[PPT], lc0[PPT], lc1[PPT], lc2[PPT], last_alpha[PPT];
+    int last[PPT];
+    int my_last = 0;
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        const int p = threadIdx.x + k * NT;
+        const int px = blockIdx.x * kTile + (p & (kTile - 1)), py = blockIdx.y * kTile + (p >> 4);
+        const bool inside = px < W && py < H;
+        const size_t pix = (size_t)py * W + px;
+        pxf[k] = (float)px; pyf[k] = (float)py;
+        Tfin[k] = inside ? final_T[pix] : 0.f;
+        T[k] = Tfin[k];
+        last[k] = inside ? (int)n_contrib[pix] : 0;
+        dp0[k] = dp1[k] = dp2[k] = 0.f;
+        if (inside) { dp0[k] = dL_dcolor[pix]; dp1[k] = dL_dcolor[hw + pix]; dp2[k] = dL_dcolor[2 * hw + pix]; }
+        bgdot[k] = cam->bg[0] * dp0[k] + cam->bg[1] * dp1[k] + cam->bg[2] * dp2[k];
+        ac0[k] = ac1[k] = ac2[k] = lc0[k] = lc1[k] = lc2[k] = last_alpha[k] = 0.f;
+        my_last = max(my_last, last[k]);
+    }
     const float ddx = 0.5f * (float)W, ddy = 0.5f * (float)H;
-    float ac0 = 0.f, ac1 = 0.f, ac2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
     // block-wide maximum of n_contrib: entries beyond it contribute to no pixel of the tile
-    const int max_last = __reduce_max_sync(0xffffffffu, last);
-    __shared__ int s_max[kTilePixels / 32];
+    const int max_last = __reduce_max_sync(0xffffffffu, my_last);
+    __shared__ int s_max[NT / 32];
     if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = max_last;
     __syncthreads();
     int tile_last = 0;
 #pragma unroll
-    for (int w = 0; w < kTilePixels / 32; ++w) tile_last = max(tile_last, s_max[w]);
+    for (int w = 0; w < NT / 32; ++w) tile_last = max(tile_last, s_max[w]);
     const int lane = threadIdx.x & 31;
     // warp-level reduction plan: after the butterfly lane l holds value (l >> 2) of {mean2D.xy, conic.xyz, rgb}; lanes
     // 0,4,..,28 add one value each, lane 1 adds the opacity gradient -- one predicated RED instruction per Gaussian
@@ -339,51 +355,64 @@ blend_backward_kernel(const CameraDev* __restrict__ cam, GeomBuffers g, const ui
         const int hi = total - i * kTilePixels;           // exclusive upper position of this batch
         if (hi - kTilePixels >= tile_last) continue;      // whole batch behind every pixel's last contributor
         __syncthreads();
-        const int pos = hi - 1 - (int)threadIdx.x;         // thread t stages list position hi-1-t
-        if (pos >= 0) {
-            const uint32_t id = ids[range.x + pos];
-            sid[threadIdx.x] = id;
-            s0[threadIdx.x] = g.rec0[id];
-            s1[threadIdx.x] = g.rec1[id];
-            s2[threadIdx.x] = g.rec2[id].x;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const int slot = threadIdx.x + k * NT;
+            const int pos = hi - 1 - slot;                // slot s stages list position hi-1-s
+            if (pos >= 0) {
+                const uint32_t id = ids[range.x + pos];
+                sid[slot] = id;
+                s0[slot] = g.rec0[id];
+                s1[slot] = g.rec1[id];
+                s2[slot] = g.rec2[id].x;
+            }
         }
         __syncthreads();
         const int cnt = min(kTilePixels, hi);
         for (int j = 0; j < cnt; ++j) {
             const int lpos = hi - 1 - j;                  // position in the tile list (0-based)
             if (lpos >= tile_last) continue;              // uniform across the block
-            bool valid = inside && lpos < last;
             const float4 a = s0[j];
             const float4 b = s1[j];
-            const float dx = a.x - pxf, dy = a.y - pyf;
-            const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-            const float G = __expf(power);
-            const float alpha = fminf(kAlphaMax, b.y * G);
-            valid = valid && power <= 0.f && alpha >= kAlphaMin;
-            if (!__any_sync(0xffffffffu, valid)) continue;
+            float Gk[PPT], alphak[PPT], dxk[PPT], dyk[PPT];
+            bool validk[PPT];
+            bool any_valid = false;
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {
+                dxk[k] = a.x - pxf[k]; dyk[k] = a.y - pyf[k];
+                const float power = -0.5f * (a.z * dxk[k] * dxk[k] + b.x * dyk[k] * dyk[k]) - a.w * dxk[k] * dyk[k];
+                Gk[k] = __expf(power);
+                alphak[k] = fminf(kAlphaMax, b.y * Gk[k]);
+                validk[k] = lpos < last[k] && power <= 0.f && alphak[k] >= kAlphaMin;
+                any_valid = any_valid || validk[k];
+            }
+            if (!__any_sync(0xffffffffu, any_valid)) continue;
             float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // mean2D.xy, conic.xyz, rgb
             float v_op = 0.f;
-            if (valid) {
+            const float c0 = b.z, c1 = b.w, c2 = s2[j];
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {
+                if (!validk[k]) continue;
+                const float alpha = alphak[k], G = Gk[k], dx = dxk[k], dy = dyk[k];
                 const float ra = 1.f / (1.f - alpha);
-                T = T * ra;
-                const float w = alpha * T;
-                const float c0 = b.z, c1 = b.w, c2 = s2[j];
-                ac0 = last_alpha * lc0 + (1.f - last_alpha) * ac0; lc0 = c0;
-                ac1 = last_alpha * lc1 + (1.f - last_alpha) * ac1; lc1 = c1;
-                ac2 = last_alpha * lc2 + (1.f - last_alpha) * ac2; lc2 = c2;
-                float dL_dalpha = (c0 - ac0) * dp0 + (c1 - ac1) * dp1 + (c2 - ac2) * dp2;
-                v[5] = w * dp0; v[6] = w * dp1; v[7] = w * dp2;
-                dL_dalpha *= T;
-                last_alpha = alpha;
-                dL_dalpha += (-Tfin * ra) * bgdot;
+                T[k] = T[k] * ra;
+                const float w = alpha * T[k];
+                ac0[k] = last_alpha[k] * lc0[k] + (1.f - last_alpha[k]) * ac0[k]; lc0[k] = c0;
+                ac1[k] = last_alpha[k] * lc1[k] + (1.f - last_alpha[k]) * ac1[k]; lc1[k] = c1;
+                ac2[k] = last_alpha[k] * lc2[k] + (1.f - last_alpha[k]) * ac2[k]; lc2[k] = c2;
+                float dL_dalpha = (c0 - ac0[k]) * dp0[k] + (c1 - ac1[k]) * dp1[k] + (c2 - ac2[k]) * dp2[k];
+                v[5] += w * dp0[k]; v[6] += w * dp1[k]; v[7] += w * dp2[k];
+                dL_dalpha *= T[k];
+                last_alpha[k] = alpha;
+                dL_dalpha += (-Tfin[k] * ra) * bgdot[k];
                 const float dL_dG = b.y * dL_dalpha;
                 const float gdx = G * dx, gdy = G * dy;
-                v[0] = dL_dG * (-gdx * a.z - gdy * a.w) * ddx;
-                v[1] = dL_dG * (-gdy * b.x - gdx * a.w) * ddy;
-                v[2] = -0.5f * gdx * dx * dL_dG;
-                v[3] = -gdx * dy * dL_dG;
-                v[4] = -0.5f * gdy * dy * dL_dG;
-                v_op = G * dL_dalpha;
+                v[0] += dL_dG * (-gdx * a.z - gdy * a.w) * ddx;
+                v[1] += dL_dG * (-gdy * b.x - gdx * a.w) * ddy;
+                v[2] += -0.5f * gdx * dx * dL_dG;
+                v[3] += -gdx * dy * dL_dG;
+                v[4] += -0.5f * gdy * dy * dL_dG;
+                v_op += G * dL_dalpha;
             }
             // transposing butterfly: 8 values x 32 lanes -> value (lane >> 2) summed over the warp in 9 shuffles
             float u[4];
@@ -414,9 +443,16 @@ cudaError_t launch_blend_backward(const CameraDev* cam, int grid_x, int grid_y, 
                                   const float* dL_dcolor, float* g_mean2D, float* g_conic, float* g_opacity, float* g_rgb,
                                   cudaStream_t st) {
     if (grid_x * grid_y == 0) return cudaSuccess;
-    blend_backward_kernel<<<dim3(grid_x, grid_y), kTilePixels, 0, st>>>(cam, g, b.ids_sorted, b.ranges, im.final_T,
-                                                                        im.n_contrib, dL_dcolor, g_mean2D, g_conic,
-                                                                        g_opacity, g_rgb);
+    // pixels per thread: 2 measured best at C3 (tools/profile_step.py; G4D_BLEND_BWD_PPT overrides for experiments)
+    static int ppt = []() { const char* e = getenv("G4D_BLEND_BWD_PPT"); const int v = e ? atoi(e) : 2; return (v == 1 || v == 4) ? v : 2; }();
+#define G4D_LAUNCH_BB(P)                                                                                               \
+    blend_backward_kernel<P><<<dim3(grid_x, grid_y), kTilePixels / P, 0, st>>>(cam, g, b.ids_sorted, b.ranges, im.final_T, \
+                                                                                im.n_contrib, dL_dcolor, g_mean2D, g_conic, \
+                                                                                g_opacity, g_rgb)
+    if (ppt == 1) G4D_LAUNCH_BB(1);
+    else if (ppt == 4) G4D_LAUNCH_BB(4);
+    else G4D_LAUNCH_BB(2);
+#undef G4D_LAUNCH_BB
     return cudaGetLastError();
 }
 
