@@ -212,72 +212,105 @@ cudaError_t launch_tile_ranges(BinBuffers b, int64_t r, int num_tiles, cudaStrea
 
 // ------------------------------------------------------------------------------------------------------
 // A.3 blend forward: one 16x16 CTA per tile, instances staged through shared memory in batches of 256.
-__global__ void __launch_bounds__(kTilePixels)
+template <int PPT>
+__global__ void __launch_bounds__(kTilePixels / PPT)
 blend_forward_kernel(const CameraDev* __restrict__ cam, GeomBuffers g, const uint32_t* __restrict__ ids,
                      const uint2* __restrict__ ranges, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
                      float* __restrict__ out_color, float* __restrict__ out_depth) {
+    constexpr int NT = kTilePixels / PPT;
     __shared__ float4 s0[kTilePixels];
     __shared__ float4 s1[kTilePixels];
     __shared__ float2 s2[kTilePixels];
     const int H = cam->H, W = cam->W;
     const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-    const int lx = threadIdx.x & (kTile - 1), ly = threadIdx.x >> 4;
-    const int px = blockIdx.x * kTile + lx, py = blockIdx.y * kTile + ly;
-    const bool inside = px < W && py < H;
-    const float pxf = (float)px, pyf = (float)py;
     const uint2 range = ranges[tile];
     const int rounds = (int)((range.y - range.x + kTilePixels - 1) / kTilePixels);
     int todo = (int)(range.y - range.x);
-    bool done = !inside;
-    float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
-    uint32_t contributor = 0, last_contributor = 0;
+    // pixel k of this thread: index threadIdx.x + k * NT inside the 16 x 16 tile
+    float pxf[PPT], pyf[PPT], T[PPT], C0[PPT], C1[PPT], C2[PPT], D[PPT];
+    uint32_t last_contributor[PPT];
+    bool done[PPT], inside[PPT];
+    bool all_done = true;
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        const int p = threadIdx.x + k * NT;
+        const int px = blockIdx.x * kTile + (p & (kTile - 1)), py = blockIdx.y * kTile + (p >> 4);
+        inside[k] = px < W && py < H;
+        pxf[k] = (float)px; pyf[k] = (float)py;
+        T[k] = 1.f; C0[k] = C1[k] = C2[k] = D[k] = 0.f;
+        last_contributor[k] = 0;
+        done[k] = !inside[k];
+        all_done = all_done && done[k];
+    }
+    uint32_t contributor = 0;
     for (int i = 0; i < rounds; ++i, todo -= kTilePixels) {
-        if (__syncthreads_count(done) == kTilePixels) break;
-        const int progress = i * kTilePixels + threadIdx.x;
-        if (range.x + progress < range.y) {
-            const uint32_t id = ids[range.x + progress];
-            s0[threadIdx.x] = g.rec0[id];
-            s1[threadIdx.x] = g.rec1[id];
-            s2[threadIdx.x] = g.rec2[id];
+        if (__syncthreads_count(all_done) == NT) break;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const int slot = threadIdx.x + k * NT;
+            const int progress = i * kTilePixels + slot;
+            if (range.x + progress < range.y) {
+                const uint32_t id = ids[range.x + progress];
+                s0[slot] = g.rec0[id];
+                s1[slot] = g.rec1[id];
+                s2[slot] = g.rec2[id];
+            }
         }
         __syncthreads();
         const int cnt = min(kTilePixels, todo);
-        for (int j = 0; !done && j < cnt; ++j) {
+        for (int j = 0; !all_done && j < cnt; ++j) {
             contributor++;
             const float4 a = s0[j];
             const float4 b = s1[j];
-            const float dx = a.x - pxf, dy = a.y - pyf;
-            const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-            if (power > 0.f) continue;
-            const float alpha = fminf(kAlphaMax, b.y * __expf(power));
-            if (alpha < kAlphaMin) continue;
-            const float test_T = T * (1.f - alpha);
-            if (test_T < kTransmittanceStop) { done = true; continue; }
-            const float w = alpha * T;
             const float2 c = s2[j];
-            C0 = fmaf(b.z, w, C0); C1 = fmaf(b.w, w, C1); C2 = fmaf(c.x, w, C2);
-            D = fmaf(c.y, w, D);
-            T = test_T;
-            last_contributor = contributor;
+            all_done = true;
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {
+                if (!done[k]) {
+                    const float dx = a.x - pxf[k], dy = a.y - pyf[k];
+                    const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+                    const float alpha = fminf(kAlphaMax, b.y * __expf(power));
+                    if (power <= 0.f && alpha >= kAlphaMin) {
+                        const float test_T = T[k] * (1.f - alpha);
+                        if (test_T < kTransmittanceStop) done[k] = true;
+                        else {
+                            const float w = alpha * T[k];
+                            C0[k] = fmaf(b.z, w, C0[k]); C1[k] = fmaf(b.w, w, C1[k]); C2[k] = fmaf(c.x, w, C2[k]);
+                            D[k] = fmaf(c.y, w, D[k]);
+                            T[k] = test_T;
+                            last_contributor[k] = contributor;
+                        }
+                    }
+                }
+                all_done = all_done && done[k];
+            }
         }
     }
-    if (inside) {
-        const size_t pix = (size_t)py * W + px;
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        if (!inside[k]) continue;
+        const size_t pix = (size_t)pyf[k] * W + (size_t)pxf[k];
         const size_t hw = (size_t)H * W;
-        final_T[pix] = T;
-        n_contrib[pix] = last_contributor;
-        out_color[pix] = fmaf(T, cam->bg[0], C0);
-        out_color[hw + pix] = fmaf(T, cam->bg[1], C1);
-        out_color[2 * hw + pix] = fmaf(T, cam->bg[2], C2);
-        out_depth[pix] = D;
+        final_T[pix] = T[k];
+        n_contrib[pix] = last_contributor[k];
+        out_color[pix] = fmaf(T[k], cam->bg[0], C0[k]);
+        out_color[hw + pix] = fmaf(T[k], cam->bg[1], C1[k]);
+        out_color[2 * hw + pix] = fmaf(T[k], cam->bg[2], C2[k]);
+        out_depth[pix] = D[k];
     }
 }
 
 cudaError_t launch_blend_forward(const CameraDev* cam, int grid_x, int grid_y, GeomBuffers g, BinBuffers b, ImageBuffers im,
                                  float* out_color, float* out_depth, cudaStream_t st) {
     if (grid_x * grid_y == 0) return cudaSuccess;
-    blend_forward_kernel<<<dim3(grid_x, grid_y), kTilePixels, 0, st>>>(cam, g, b.ids_sorted, b.ranges, im.final_T,
-                                                                       im.n_contrib, out_color, out_depth);
+    static int ppt = []() { const char* e = getenv("G4D_BLEND_FWD_PPT"); const int v = e ? atoi(e) : 2; return (v == 1 || v == 4) ? v : 2; }();
+#define G4D_LAUNCH_BF(P)                                                                                                  \
+    blend_forward_kernel<P><<<dim3(grid_x, grid_y), kTilePixels / P, 0, st>>>(cam, g, b.ids_sorted, b.ranges, im.final_T, \
+                                                                               im.n_contrib, out_color, out_depth)
+    if (ppt == 1) G4D_LAUNCH_BF(1);
+    else if (ppt == 4) G4D_LAUNCH_BF(4);
+    else G4D_LAUNCH_BF(2);
+#undef G4D_LAUNCH_BF
     return cudaGetLastError();
 }
 

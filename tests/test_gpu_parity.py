@@ -467,7 +467,7 @@ def test_no_sync_mode_matches_sync_mode_and_reports_overflow():
         ws2_ctx_cam_far = synth.make_camera(0.0, 320, 240, radius=60.0)
         ws._free_contexts.clear()                 # fresh context => fresh capacity
         render(ws2_ctx_cam_far); render(ws2_ctx_cam_far)
-        render(synth.make_camera(0.0, 320, 240, radius=2.0))
+        render(synth.make_camera(0.0, 640, 480, radius=1.6))     # several times the instances of the far views
         with pytest.raises(g4d._lib.G4DError, match="overflow"):
             render(ws2_ctx_cam_far)
     finally:
