@@ -57,6 +57,7 @@ struct G4DWorkspace {
     int tight_cull = 0;
     int stage_timing = 0;
     int tensor_cores = 1;
+    int warp_cull = 1;
     DevBuf tc_packed;
     TcWeights tcw{};
     DevBuf tc_bwd_packed, tc_feat;
@@ -403,7 +404,7 @@ int bin_and_blend(G4DContext* c, const G4DCamera* cam, int64_t n, float* out_col
     if ((rc = debug_sync(cam, st, "binning")) != G4D_OK) return rc;
     {
         StageTimer tm(c, G4D_STAGE_BLEND, st);
-        G4D_CUDA(launch_blend_forward(dcam, c->grid_x, c->grid_y, c->g, c->b, c->im, out_color, out_depth, st));
+        G4D_CUDA(launch_blend_forward(dcam, c->grid_x, c->grid_y, c->g, c->b, c->im, out_color, out_depth, ws->warp_cull, st));
     }
     if ((rc = debug_sync(cam, st, "blend_forward")) != G4D_OK) return rc;
     c->n = n;
@@ -428,7 +429,7 @@ int raster_backward_stages(G4DContext* c, const G4DCamera* cam, int64_t n, const
     {
         StageTimer tm(c, G4D_STAGE_BLEND_BWD, st);
         G4D_CUDA(launch_blend_backward(dcam, c->grid_x, c->grid_y, c->g, c->b, c->im, dL_dcolor, g_mean2D, g_conic, g_opacities,
-                                       g_rgb, st));
+                                       g_rgb, c->ws->warp_cull, st));
     }
     int rc;
     if ((rc = debug_sync(cam, st, "blend_backward")) != G4D_OK) return rc;
@@ -500,6 +501,7 @@ int g4d_workspace_set_option(G4DWorkspace* ws, int option, int64_t value) {
         case G4D_OPT_TIGHT_CULL: ws->tight_cull = value ? 1 : 0; return G4D_OK;
         case G4D_OPT_STAGE_TIMING: ws->stage_timing = value ? 1 : 0; return G4D_OK;
         case G4D_OPT_TENSOR_CORES: ws->tensor_cores = value ? 1 : 0; return G4D_OK;
+        case G4D_OPT_WARP_CULL: ws->warp_cull = value ? 1 : 0; return G4D_OK;
         case G4D_OPT_TC_DEBUG: ws->tc_debug = value ? 1 : 0; return G4D_OK;
         default: return fail(G4D_ERR_ARG, "unknown option");
     }

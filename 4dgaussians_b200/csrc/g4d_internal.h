@@ -105,10 +105,10 @@ cudaError_t launch_emit_keys(const CameraDev* cam, int64_t n, GeomBuffers g, Bin
 cudaError_t launch_sort(BinBuffers b, int64_t r, int begin_bit, int end_bit, void* temp, size_t temp_bytes, cudaStream_t st);
 cudaError_t launch_tile_ranges(BinBuffers b, int64_t r, int num_tiles, cudaStream_t st);
 cudaError_t launch_blend_forward(const CameraDev* cam, int grid_x, int grid_y, GeomBuffers g, BinBuffers b, ImageBuffers im,
-                                 float* out_color, float* out_depth, cudaStream_t st);
+                                 float* out_color, float* out_depth, int warp_cull, cudaStream_t st);
 cudaError_t launch_blend_backward(const CameraDev* cam, int grid_x, int grid_y, GeomBuffers g, BinBuffers b, ImageBuffers im,
                                   const float* dL_dcolor, float* g_mean2D, float* g_conic, float* g_opacity, float* g_rgb,
-                                  cudaStream_t st);
+                                  int warp_cull, cudaStream_t st);
 // per-Gaussian backward; g_shs may alias separate dc/rest sinks through (g_sh_dc, g_sh_rest) when g_shs == NULL
 cudaError_t launch_preprocess_backward(const CameraDev* cam, int64_t n, const RasterInputs& in, GeomBuffers g,
                                        const float* g_mean2D, const float* g_conic, const float* g_rgb, float* g_means3D,

@@ -72,6 +72,20 @@ G4D_D float edge_min(float a, float b, float c, float fixed, float lo, float hi)
     t = fminf(fmaxf(t, lo), hi);
     return a * fixed * fixed + 2.f * b * fixed * t + c * t * t;
 }
+// can the Gaussian reach alpha >= 1/255 anywhere in the pixel rectangle [x0, x1] x [y0, y1] (inclusive pixel centres)?
+G4D_D bool rect_contributes(float4 r0, float4 r1, float x0, float x1, float y0, float y1) {
+    const float A = r0.z, B = r0.w, C = r1.x, op = r1.y;
+    const float dx0 = r0.x - x1, dx1 = r0.x - x0;
+    const float dy0 = r0.y - y1, dy1 = r0.y - y0;
+    float qmin;
+    if (dx0 <= 0.f && dx1 >= 0.f && dy0 <= 0.f && dy1 >= 0.f) qmin = 0.f;
+    else {
+        qmin = fminf(fminf(edge_min(A, B, C, dx0, dy0, dy1), edge_min(A, B, C, dx1, dy0, dy1)),
+                     fminf(edge_min(C, B, A, dy0, dx0, dx1), edge_min(C, B, A, dy1, dx0, dx1)));
+        qmin = fmaxf(qmin, 0.f);
+    }
+    return op * __expf(-0.5f * qmin) * 1.0001f >= kAlphaMin;
+}
 G4D_D bool tile_contributes(float4 r0, float4 r1, int tx, int ty) {
     const float A = r0.z, B = r0.w, C = r1.x, op = r1.y;
     const float dx0 = r0.x - (float)(tx * kTile + kTile - 1), dx1 = r0.x - (float)(tx * kTile);
@@ -216,7 +230,7 @@ template <int PPT>
 __global__ void __launch_bounds__(kTilePixels / PPT)
 blend_forward_kernel(const CameraDev* __restrict__ cam, GeomBuffers g, const uint32_t* __restrict__ ids,
                      const uint2* __restrict__ ranges, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
-                     float* __restrict__ out_color, float* __restrict__ out_depth) {
+                     float* __restrict__ out_color, float* __restrict__ out_depth, int warp_cull) {
     constexpr int NT = kTilePixels / PPT;
     __shared__ float4 s0[kTilePixels];
     __shared__ float4 s1[kTilePixels];
@@ -226,15 +240,15 @@ blend_forward_kernel(const CameraDev* __restrict__ cam, GeomBuffers g, const uin
     const uint2 range = ranges[tile];
     const int rounds = (int)((range.y - range.x + kTilePixels - 1) / kTilePixels);
     int todo = (int)(range.y - range.x);
-    // pixel k of this thread: index threadIdx.x + k * NT inside the 16 x 16 tile
+    // a warp owns a compact 16 x (2 PPT) pixel strip of the tile: lane l, pixel k -> (l & 15, 2 PPT warp + (l >> 4) + 2 k)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float pxf[PPT], pyf[PPT], T[PPT], C0[PPT], C1[PPT], C2[PPT], D[PPT];
     uint32_t last_contributor[PPT];
     bool done[PPT], inside[PPT];
     bool all_done = true;
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
-        const int p = threadIdx.x + k * NT;
-        const int px = blockIdx.x * kTile + (p & (kTile - 1)), py = blockIdx.y * kTile + (p >> 4);
+        const int px = blockIdx.x * kTile + (lane & 15), py = blockIdx.y * kTile + 2 * PPT * warp + (lane >> 4) + 2 * k;
         inside[k] = px < W && py < H;
         pxf[k] = (float)px; pyf[k] = (float)py;
         T[k] = 1.f; C0[k] = C1[k] = C2[k] = D[k] = 0.f;
@@ -242,7 +256,9 @@ blend_forward_kernel(const CameraDev* __restrict__ cam, GeomBuffers g, const uin
         done[k] = !inside[k];
         all_done = all_done && done[k];
     }
-    uint32_t contributor = 0;
+    // strip rectangle for the per-warp exact cull (same predicate as G4D_OPT_TIGHT_CULL, on 16 x 2 PPT pixels)
+    const float sx0 = (float)(blockIdx.x * kTile), sx1 = sx0 + (float)(kTile - 1);
+    const float sy0 = (float)(blockIdx.y * kTile + 2 * PPT * warp), sy1 = sy0 + (float)(2 * PPT - 1);
     for (int i = 0; i < rounds; ++i, todo -= kTilePixels) {
         if (__syncthreads_count(all_done) == NT) break;
 #pragma unroll
@@ -258,32 +274,44 @@ blend_forward_kernel(const CameraDev* __restrict__ cam, GeomBuffers g, const uin
         }
         __syncthreads();
         const int cnt = min(kTilePixels, todo);
-        for (int j = 0; !all_done && j < cnt; ++j) {
-            contributor++;
-            const float4 a = s0[j];
-            const float4 b = s1[j];
-            const float2 c = s2[j];
-            all_done = true;
+        for (int base = 0; base < cnt; base += 32) {
+            if (__all_sync(0xffffffffu, all_done)) break;
+            // lane l tests instance base + l against the warp's strip: instances that cannot reach alpha >= 1/255 on any
+            // of its pixels are skipped by the whole warp (they would be skipped pixel by pixel anyway)
+            const int jt = base + lane;
+            bool hit = jt < cnt;
+            if (hit && warp_cull) hit = rect_contributes(s0[jt], s1[jt], sx0, sx1, sy0, sy1);
+            uint32_t mask = __ballot_sync(0xffffffffu, hit);
+            while (mask) {
+                const int j = base + __ffs(mask) - 1;
+                mask &= mask - 1;
+                const uint32_t contributor = (uint32_t)(i * kTilePixels + j + 1);
+                const float4 a = s0[j];
+                const float4 b = s1[j];
+                const float2 c = s2[j];
 #pragma unroll
-            for (int k = 0; k < PPT; ++k) {
-                if (!done[k]) {
-                    const float dx = a.x - pxf[k], dy = a.y - pyf[k];
-                    const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-                    const float alpha = fminf(kAlphaMax, b.y * __expf(power));
-                    if (power <= 0.f && alpha >= kAlphaMin) {
-                        const float test_T = T[k] * (1.f - alpha);
-                        if (test_T < kTransmittanceStop) done[k] = true;
-                        else {
-                            const float w = alpha * T[k];
-                            C0[k] = fmaf(b.z, w, C0[k]); C1[k] = fmaf(b.w, w, C1[k]); C2[k] = fmaf(c.x, w, C2[k]);
-                            D[k] = fmaf(c.y, w, D[k]);
-                            T[k] = test_T;
-                            last_contributor[k] = contributor;
+                for (int k = 0; k < PPT; ++k) {
+                    if (!done[k]) {
+                        const float dx = a.x - pxf[k], dy = a.y - pyf[k];
+                        const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+                        const float alpha = fminf(kAlphaMax, b.y * __expf(power));
+                        if (power <= 0.f && alpha >= kAlphaMin) {
+                            const float test_T = T[k] * (1.f - alpha);
+                            if (test_T < kTransmittanceStop) done[k] = true;
+                            else {
+                                const float w = alpha * T[k];
+                                C0[k] = fmaf(b.z, w, C0[k]); C1[k] = fmaf(b.w, w, C1[k]); C2[k] = fmaf(c.x, w, C2[k]);
+                                D[k] = fmaf(c.y, w, D[k]);
+                                T[k] = test_T;
+                                last_contributor[k] = contributor;
+                            }
                         }
                     }
                 }
-                all_done = all_done && done[k];
             }
+            all_done = true;
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) all_done = all_done && done[k];
         }
     }
 #pragma unroll
@@ -301,12 +329,12 @@ blend_forward_kernel(const CameraDev* __restrict__ cam, GeomBuffers g, const uin
 }
 
 cudaError_t launch_blend_forward(const CameraDev* cam, int grid_x, int grid_y, GeomBuffers g, BinBuffers b, ImageBuffers im,
-                                 float* out_color, float* out_depth, cudaStream_t st) {
+                                 float* out_color, float* out_depth, int warp_cull, cudaStream_t st) {
     if (grid_x * grid_y == 0) return cudaSuccess;
     static int ppt = []() { const char* e = getenv("G4D_BLEND_FWD_PPT"); const int v = e ? atoi(e) : 2; return (v == 1 || v == 4) ? v : 2; }();
 #define G4D_LAUNCH_BF(P)                                                                                                  \
     blend_forward_kernel<P><<<dim3(grid_x, grid_y), kTilePixels / P, 0, st>>>(cam, g, b.ids_sorted, b.ranges, im.final_T, \
-                                                                               im.n_contrib, out_color, out_depth)
+                                                                               im.n_contrib, out_color, out_depth, warp_cull)
     if (ppt == 1) G4D_LAUNCH_BF(1);
     else if (ppt == 4) G4D_LAUNCH_BF(4);
     else G4D_LAUNCH_BF(2);
@@ -332,7 +360,7 @@ blend_backward_kernel(const CameraDev* __restrict__ cam, GeomBuffers g, const ui
                       const uint2* __restrict__ ranges, const float* __restrict__ final_T,
                       const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dcolor,
                       float* __restrict__ g_mean2D, float* __restrict__ g_conic, float* __restrict__ g_opacity,
-                      float* __restrict__ g_rgb) {
+                      float* __restrict__ g_rgb, int warp_cull) {
     constexpr int NT = kTilePixels / PPT;
     __shared__ float4 s0[kTilePixels];
     __shared__ float4 s1[kTilePixels];
@@ -344,15 +372,17 @@ blend_backward_kernel(const CameraDev* __restrict__ cam, GeomBuffers g, const ui
     const int total = (int)(range.y - range.x);
     const int rounds = (total + kTilePixels - 1) / kTilePixels;
     const size_t hw = (size_t)H * W;
-    // pixel k of this thread: index threadIdx.x + k * NT inside the 16 x 16 tile (consecutive threads -> consecutive pixels)
+    // a warp owns a compact 16 x (2 PPT) pixel strip of the tile: lane l, pixel k -> (l & 15, 2 PPT warp + (l >> 4) + 2 k)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float sx0 = (float)(blockIdx.x * kTile), sx1 = sx0 + (float)(kTile - 1);
+    const float sy0 = (float)(blockIdx.y * kTile + 2 * PPT * warp), sy1 = sy0 + (float)(2 * PPT - 1);
     float pxf[PPT], pyf[PPT], Tfin[PPT], T[PPT], dp0[PPT], dp1[PPT], dp2[PPT], bgdot[PPT];
     float ac0[PPT], ac1[PPT], ac2[PPT], lc0[PPT], lc1[PPT], lc2[PPT], last_alpha[PPT];
     int last[PPT];
     int my_last = 0;
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
-        const int p = threadIdx.x + k * NT;
-        const int px = blockIdx.x * kTile + (p & (kTile - 1)), py = blockIdx.y * kTile + (p >> 4);
+        const int px = blockIdx.x * kTile + (lane & 15), py = blockIdx.y * kTile + 2 * PPT * warp + (lane >> 4) + 2 * k;
         const bool inside = px < W && py < H;
         const size_t pix = (size_t)py * W + px;
         pxf[k] = (float)px; pyf[k] = (float)py;
@@ -374,7 +404,6 @@ blend_backward_kernel(const CameraDev* __restrict__ cam, GeomBuffers g, const ui
     int tile_last = 0;
 #pragma unroll
     for (int w = 0; w < NT / 32; ++w) tile_last = max(tile_last, s_max[w]);
-    const int lane = threadIdx.x & 31;
     // warp-level reduction plan: after the butterfly lane l holds value (l >> 2) of {mean2D.xy, conic.xyz, rgb}; lanes
     // 0,4,..,28 add one value each, lane 1 adds the opacity gradient -- one predicated RED instruction per Gaussian
     const bool hi16 = lane & 16, hi8 = lane & 8, hi4 = lane & 4;
@@ -402,9 +431,17 @@ blend_backward_kernel(const CameraDev* __restrict__ cam, GeomBuffers g, const ui
         }
         __syncthreads();
         const int cnt = min(kTilePixels, hi);
-        for (int j = 0; j < cnt; ++j) {
+        for (int base = 0; base < cnt; base += 32) {
+          // lane l tests instance base + l: behind every pixel of this warp's strip, or unable to reach alpha >= 1/255
+          // anywhere on the strip (same predicate as the exact tile cull) -> skipped by the whole warp
+          const int jt = base + lane;
+          bool hit = jt < cnt && (hi - 1 - jt) < max_last;
+          if (hit && warp_cull) hit = rect_contributes(s0[jt], s1[jt], sx0, sx1, sy0, sy1);
+          uint32_t mask = __ballot_sync(0xffffffffu, hit);
+          while (mask) {
+            const int j = base + __ffs(mask) - 1;
+            mask &= mask - 1;
             const int lpos = hi - 1 - j;                  // position in the tile list (0-based)
-            if (lpos >= tile_last) continue;              // uniform across the block
             const float4 a = s0[j];
             const float4 b = s1[j];
             float Gk[PPT], alphak[PPT], dxk[PPT], dyk[PPT];
@@ -468,20 +505,21 @@ blend_backward_kernel(const CameraDev* __restrict__ cam, GeomBuffers g, const ui
                 const uint32_t id = sid[j];
                 atomicAdd(red_base + red_stride * id, lane == 1 ? v_op : x);
             }
+          }
         }
     }
 }
 
 cudaError_t launch_blend_backward(const CameraDev* cam, int grid_x, int grid_y, GeomBuffers g, BinBuffers b, ImageBuffers im,
                                   const float* dL_dcolor, float* g_mean2D, float* g_conic, float* g_opacity, float* g_rgb,
-                                  cudaStream_t st) {
+                                  int warp_cull, cudaStream_t st) {
     if (grid_x * grid_y == 0) return cudaSuccess;
     // pixels per thread: 2 measured best at C3 (tools/profile_step.py; G4D_BLEND_BWD_PPT overrides for experiments)
     static int ppt = []() { const char* e = getenv("G4D_BLEND_BWD_PPT"); const int v = e ? atoi(e) : 2; return (v == 1 || v == 4) ? v : 2; }();
 #define G4D_LAUNCH_BB(P)                                                                                               \
     blend_backward_kernel<P><<<dim3(grid_x, grid_y), kTilePixels / P, 0, st>>>(cam, g, b.ids_sorted, b.ranges, im.final_T, \
                                                                                 im.n_contrib, dL_dcolor, g_mean2D, g_conic, \
-                                                                                g_opacity, g_rgb)
+                                                                                g_opacity, g_rgb, warp_cull)
     if (ppt == 1) G4D_LAUNCH_BB(1);
     else if (ppt == 4) G4D_LAUNCH_BB(4);
     else G4D_LAUNCH_BB(2);

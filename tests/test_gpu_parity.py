@@ -443,6 +443,33 @@ def test_tight_cull_gives_bit_identical_images_with_fewer_instances():
         assert float((x - y).abs().max()) <= 1e-4 * max(1e-3, float(x.abs().max()))
 
 
+def test_warp_strip_cull_changes_no_pixel_and_no_gradient():
+    """G4D_OPT_WARP_CULL (default on): the blend kernels skip, warp by warp, instances that cannot reach alpha >= 1/255 on
+    the warp's 16 x 4 pixel strip.  Forward outputs must be BIT-identical to testing every pixel; gradients equal up to the
+    order of the floating-point atomics."""
+    ins = [t.float().cuda() for t in raster_inputs(20_000, 4, scale_mean=0.03)]
+    cam = synth.make_camera(35.0, 333, 250, radius=2.4)
+    ws = g4d._lib.Workspace.get(0)
+    outs = []
+    try:
+        for flag in (1, 0):
+            ws.set_option(g4d._lib.OPT_WARP_CULL, flag)
+            leaves = [x.clone().requires_grad_(True) for x in ins]
+            m2d = torch.zeros(ins[0].shape[0], 3, device="cuda", requires_grad=True)
+            color, radii, depth = g4d.GaussianRasterizer(_settings(cam, (0.2, 0.1, 0.3)))(means3D=leaves[0], means2D=m2d, shs=leaves[4], colors_precomp=None,
+                                                             opacities=leaves[3], scales=leaves[1], rotations=leaves[2],
+                                                             cov3D_precomp=None)
+            g = torch.Generator(device="cuda").manual_seed(1)
+            (color * torch.rand(color.shape, device="cuda", generator=g)).sum().backward()
+            outs.append((color.detach().clone(), depth.detach().clone(), radii.clone(), [x.grad.clone() for x in leaves], m2d.grad.clone()))
+    finally:
+        ws.set_option(g4d._lib.OPT_WARP_CULL, 1)
+    (c1, d1, r1, g1, m1), (c0, d0, r0, g0, m0) = outs
+    assert torch.equal(c1, c0) and torch.equal(d1, d0) and torch.equal(r1, r0)
+    for a, b in zip(g1 + [m1], g0 + [m0]):
+        assert float((a - b).abs().max()) <= 1e-5 * max(1.0, float(b.abs().max()))
+
+
 def test_no_sync_mode_matches_sync_mode_and_reports_overflow():
     """G4D_OPT_SYNC_MODE=0: capacity-bounded binning without the host round trip gives bit-identical images; a forward
     that outgrows the capacity is reported by the next call on the context."""
