@@ -36,7 +36,7 @@ struct DevBuf {
     size_t cap = 0;
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
-        size_t want = bytes + bytes / 4 + 256;
+        size_t want = bytes + bytes / 2 + 256;
         if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) { p = nullptr; cap = 0; return e; }
@@ -157,7 +157,7 @@ int ensure_image(G4DContext* c, int H, int W) {
 int ensure_bin(G4DContext* c, int64_t r) {
     const size_t R = (size_t)(r > 0 ? r : 1);
     if ((int64_t)R <= c->capacity && c->bin.p) return G4D_OK;
-    const size_t cap = R + R / 2 + 1024;   // generous head-room: a regrow is a cudaFree + cudaMalloc (device sync)
+    const size_t cap = 2 * R + 1024;   // generous head-room: a regrow is a cudaFree + cudaMalloc (device sync, up to 100+ ms)
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
     const size_t o0 = take(cap * 8), o1 = take(cap * 8), o2 = take(cap * 4), o3 = take(cap * 4);
@@ -370,7 +370,7 @@ int bin_and_blend(G4DContext* c, const G4DCamera* cam, int64_t n, float* out_col
                 StageTimer tm(c, G4D_STAGE_EMIT, st);
                 G4D_CUDA(launch_emit_keys(dcam, n, c->g, c->b, c->capacity, ws->tight_cull, st));
             }
-            const size_t sb = sort_temp_bytes(R);
+            const size_t sb = sort_temp_bytes(c->capacity);   // sized for the capacity, not R: no regrow while R wanders
             G4D_CUDA(ws->temp.ensure(sb));
             StageTimer tm(c, G4D_STAGE_SORT, st);
             G4D_CUDA(launch_sort(c->b, R, 32, 32 + tile_bits, ws->temp.p, sb, st));
