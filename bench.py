@@ -115,6 +115,10 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         self.reasons.add(name)
 
+    def mark(self):
+        """start of the timed region: earlier samples (NVML warm-up, GPU idle) are dropped"""
+        self.sm, self.mx, self.reasons = [], [], set()
+
     def stop(self):
         self._stop = True
         if self.proc is not None:
@@ -165,8 +169,10 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (the version banner goes to stdout)
+        # keep stdout to the one JSON line: NCCL prints its version banner to stdout at levels VERSION and WARN
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     g4d, synth, w, scene, mod = build_scene(dev)
     lib = g4d._lib
@@ -193,13 +199,16 @@ def run_ours(args):
     # ------------------------------------------------------------------ resident arm (`value`)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     stage_acc, Rs, vis = {}, [], []
+    sampler = ClockSampler(local)
+    if rank == 0 and not os.environ.get("G4D_BENCH_NO_SAMPLER"):
+        sampler.start()          # NVML initialisation / first queries happen during the warm-up, not in the timed region
+    import gc
     with torch.no_grad():
         for i in range(Wm):
             g4d.render(my_cams[i], pc, Pipe, bg)
         barrier()
-        sampler = ClockSampler(local)
-        if rank == 0 and not os.environ.get("G4D_BENCH_NO_SAMPLER"):
-            sampler.start()
+        gc.collect(); gc.disable()     # a host hiccup shows up 1:1 in a ~1 ms step that synchronises on R once per frame
+        sampler.mark()
         t_wall0 = time.perf_counter()
         for i in range(K):
             flush.fill_(i & 0xFF)
@@ -208,6 +217,7 @@ def run_ours(args):
             ev[i][1].record()
         barrier()
         t_wall = time.perf_counter() - t_wall0
+        gc.enable()
         # per-stage device times and instance counts: separate, untimed pass (the queries synchronise)
         for i in range(min(K, 8)):
             g4d.render(my_cams[Wm + i], pc, Pipe, bg)
