@@ -82,7 +82,7 @@ struct G4DWorkspace {
 
 struct G4DContext {
     G4DWorkspace* ws = nullptr;
-    DevBuf cam, geom, bin, img, fused, gscratch, gdeform, trow, relu;
+    DevBuf cam, geom, bin, img, fused, gscratch, gdeform, trow, relu, feat;
     bool relu_saved = false;
     int64_t n = 0;
     int H = 0, W = 0, grid_x = 0, grid_y = 0;
@@ -232,13 +232,13 @@ int refresh_tc_bwd(G4DWorkspace* ws, const G4DDeformParams* p, cudaStream_t st) 
 // backward of the deformation network: tensor-core path when the configuration allows, FFMA path otherwise
 int deform_backward_dispatch(G4DWorkspace* ws, const DeformDesc& d, const G4DDeformParams* prm, const G4DDeformGrads* grads,
                              float time, int64_t n, const float* xyz, const float* const go[G4D_NUM_HEADS],
-                             float* const gi[G4D_NUM_HEADS], const uint32_t* relu_bits, cudaStream_t st) {
+                             float* const gi[G4D_NUM_HEADS], const uint32_t* relu_bits, const float* saved_feat, cudaStream_t st) {
     int rc;
     if (ws->tensor_cores && tc_deform_supported(d)) {
         if ((rc = refresh_tc_bwd(ws, prm, st)) != G4D_OK) return rc;
         if (ws->tc_debug) G4D_CUDA(ws->tc_dbg.ensure((size_t)ws->sm_count * 12 * 8));
         G4D_CUDA(ws->scratch.ensure(tc_deform_backward_scratch_bytes(d, n)));
-        G4D_CUDA(launch_deform_backward_tc(d, *prm, *grads, ws->tcbw, time, n, xyz, go, gi, relu_bits, ws->tc_debug ? ws->tc_dbg.as<long long>() : nullptr,
+        G4D_CUDA(launch_deform_backward_tc(d, *prm, *grads, ws->tcbw, time, n, xyz, go, gi, relu_bits, saved_feat, ws->tc_debug ? ws->tc_dbg.as<long long>() : nullptr,
                                            ws->scratch.as<uint8_t>(), ws->sm_count, st));
         return G4D_OK;
     }
@@ -488,7 +488,7 @@ void g4d_context_destroy(G4DContext* c) {
     if (c->ev_created) for (int i = 0; i < 2 * G4D_STAGE_COUNT; ++i) cudaEventDestroy(c->ev[i]);
     if (c->ev_r) cudaEventDestroy(c->ev_r);
     if (c->h_r) cudaFreeHost(c->h_r);
-    c->cam.release(); c->geom.release(); c->bin.release(); c->img.release(); c->fused.release(); c->gscratch.release(); c->gdeform.release(); c->relu.release();
+    c->cam.release(); c->geom.release(); c->bin.release(); c->img.release(); c->fused.release(); c->gscratch.release(); c->gdeform.release(); c->relu.release(); c->feat.release();
     c->trow.release();
     delete c;
 }
@@ -704,7 +704,7 @@ int g4d_deform_backward(G4DWorkspace* ws, const G4DDeformParams* prm, G4DDeformG
     const DeformDesc d = make_desc(ws, prm, trow);
     const float* go[G4D_NUM_HEADS] = {g_out_xyz, g_out_scaling, g_out_rotation, g_out_opacity, g_out_shs};
     float* gi[G4D_NUM_HEADS] = {g_in_xyz, g_in_scaling, g_in_rotation, g_in_opacity, g_in_shs};
-    return deform_backward_dispatch(ws, d, prm, grads, time, n, xyz, go, gi, relu_bits, st);
+    return deform_backward_dispatch(ws, d, prm, grads, time, n, xyz, go, gi, relu_bits, nullptr, st);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -750,6 +750,10 @@ int g4d_render_forward(G4DContext* c, const G4DCamera* cam, const G4DDeformParam
         c->relu_saved = use_tc && !(cam->debug & G4D_CAM_NO_GRAD);
         if (c->relu_saved) G4D_CUDA(c->relu.ensure(G4D_RELU_BITS_WORDS(n) * 4));
         if ((rc = attach_relu_bits(ws, use_tc, c->relu_saved, c->relu_saved ? c->relu.as<uint32_t>() : nullptr, n, st)) != G4D_OK) return rc;
+        if (c->relu_saved) {   // a backward will follow: keep the staged HexPlane features with the context (it re-uses them)
+            G4D_CUDA(c->feat.ensure((size_t)(n > 0 ? n : 1) * (size_t)d.F * 4 + 256));
+            ws->tcw.feat = c->feat.as<float>();
+        }
         G4D_CUDA(launch_deform(d, 1, dcam, cam->time, false, n, g->xyz, g->scaling, g->rotation, g->opacity, shs, dc,
                                g->features_rest, nullptr, nullptr, nullptr, nullptr, nullptr, c->g, c->fo, out_radii,
                                ws->sm_count, st, use_tc ? &ws->tcw : nullptr));
@@ -820,7 +824,8 @@ int g4d_render_backward(G4DContext* c, const G4DCamera* cam, const G4DDeformPara
     float* gi[G4D_NUM_HEADS] = {gg->xyz, gg->scaling, gg->rotation, gg->opacity, nullptr};
     {
         StageTimer tm(c, G4D_STAGE_DEFORM_BWD, st);
-        if ((rc = deform_backward_dispatch(ws, d, prm, pgrads, cam->time, n, g->xyz, go, gi, c->relu_saved ? c->relu.as<uint32_t>() : nullptr, st)) != G4D_OK) return rc;
+        if ((rc = deform_backward_dispatch(ws, d, prm, pgrads, cam->time, n, g->xyz, go, gi, c->relu_saved ? c->relu.as<uint32_t>() : nullptr,
+                                           c->relu_saved ? c->feat.as<float>() : nullptr, st)) != G4D_OK) return rc;
     }
     return debug_sync(cam, st, "deform_backward");
 }

@@ -13,52 +13,66 @@ preprocess_backward_kernel(const CameraDev* __restrict__ camp, int64_t n, Raster
                            const float* __restrict__ g_rgb, float* __restrict__ g_means3D, float* __restrict__ g_means2D_out,
                            float* __restrict__ g_scales, float* __restrict__ g_rotations, float* __restrict__ g_shs,
                            float* __restrict__ g_sh_dc, float* __restrict__ g_sh_rest) {
+    // SH coefficients travel through shared memory: a warp reads / writes the 32 x 48 floats of its Gaussians as contiguous
+    // 128-byte lines instead of 48 scalar accesses per thread at a 192-byte stride
+    constexpr int kRow = 49;                       // padded row: lane i <-> row i is bank-conflict free (49 odd)
+    extern __shared__ float sh_smem[];             // [warps][2][32 * kRow]
     __shared__ CameraDev cam;
     for (int i = threadIdx.x; i < (int)(sizeof(CameraDev) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(&cam)[i] = reinterpret_cast<const uint32_t*>(camp)[i];
     __syncthreads();
-    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gi >= n) return;
-    float* gsh = g_shs ? g_shs + gi * 48 : nullptr;
-    float* gdc = g_sh_dc ? g_sh_dc + gi * 3 : nullptr;
-    float* grest = g_sh_rest ? g_sh_rest + gi * 45 : nullptr;
-    auto sh_store = [&](int k, int ch, float v) {
-        if (gsh) gsh[3 * k + ch] = v;
-        if (k == 0) { if (gdc) gdc[ch] = v; }
-        else if (grest) grest[3 * (k - 1) + ch] = v;
-    };
-    if (g_means2D_out) {
-        const bool vis = g.radii[gi] > 0;
-        g_means2D_out[3 * gi] = vis ? g_mean2D[2 * gi] : 0.f;
-        g_means2D_out[3 * gi + 1] = vis ? g_mean2D[2 * gi + 1] : 0.f;
-        g_means2D_out[3 * gi + 2] = 0.f;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* ld = sh_smem + (size_t)warp * 2 * 32 * kRow;
+    float* st = ld + 32 * kRow;
+    const int64_t g0 = (int64_t)blockIdx.x * blockDim.x + warp * 32;
+    const int cnt = (int)(n - g0 < 32 ? (n - g0 > 0 ? n - g0 : 0) : 32);
+    if (cnt == 0) return;                          // whole warp
+    const int64_t gi = g0 + lane;
+    const bool active = lane < cnt;
+    for (int idx = lane; idx < cnt * 48; idx += 32) {
+        const int i = idx / 48, e = idx - i * 48;
+        float v;
+        if (in.shs) v = __ldg(in.shs + g0 * 48 + idx);
+        else v = e < 3 ? __ldg(in.sh_dc + (g0 + i) * 3 + e) : __ldg(in.sh_rest + (g0 + i) * 45 + (e - 3));
+        ld[i * kRow + e] = v;
     }
-    if (!(g.radii[gi] > 0)) {
-        for (int k = 0; k < 3; ++k) { g_means3D[3 * gi + k] = 0.f; g_scales[3 * gi + k] = 0.f; }
-        for (int k = 0; k < 4; ++k) g_rotations[4 * gi + k] = 0.f;
-        for (int k = 0; k < kShCoeffs; ++k)
-            for (int ch = 0; ch < 3; ++ch) sh_store(k, ch, 0.f);
-        return;
+    __syncwarp();
+    auto sh_store = [&](int k, int ch, float v) { st[lane * kRow + 3 * k + ch] = v; };
+    if (active) {
+        if (g_means2D_out) {
+            const bool vis = g.radii[gi] > 0;
+            g_means2D_out[3 * gi] = vis ? g_mean2D[2 * gi] : 0.f;
+            g_means2D_out[3 * gi + 1] = vis ? g_mean2D[2 * gi + 1] : 0.f;
+            g_means2D_out[3 * gi + 2] = 0.f;
+        }
+        if (!(g.radii[gi] > 0)) {
+            for (int k = 0; k < 3; ++k) { g_means3D[3 * gi + k] = 0.f; g_scales[3 * gi + k] = 0.f; }
+            for (int k = 0; k < 4; ++k) g_rotations[4 * gi + k] = 0.f;
+            for (int k = 0; k < kShCoeffs; ++k)
+                for (int ch = 0; ch < 3; ++ch) sh_store(k, ch, 0.f);
+        } else {
+            const Vec3 p{in.means3D[3 * gi], in.means3D[3 * gi + 1], in.means3D[3 * gi + 2]};
+            const Vec3 sc{in.scales[3 * gi], in.scales[3 * gi + 1], in.scales[3 * gi + 2]};
+            const float4 q4 = *reinterpret_cast<const float4*>(in.rotations + 4 * gi);
+            const float gm2[2] = {g_mean2D[2 * gi], g_mean2D[2 * gi + 1]};
+            const float gc[3] = {g_conic[3 * gi], g_conic[3 * gi + 1], g_conic[3 * gi + 2]};
+            const float gr[3] = {g_rgb[3 * gi], g_rgb[3 * gi + 1], g_rgb[3 * gi + 2]};
+            GaussGrad gg;
+            const float* row = ld + lane * kRow;
+            gaussian_backward(cam, p, sc, Quat{q4.x, q4.y, q4.z, q4.w}, (uint32_t)g.clamped[gi], gm2, gc, gr,
+                              [&](int k, int ch) { return row[3 * k + ch]; }, sh_store, gg);
+            for (int k = 0; k < 3; ++k) { g_means3D[3 * gi + k] = gg.mean[k]; g_scales[3 * gi + k] = gg.scale[k]; }
+            for (int k = 0; k < 4; ++k) g_rotations[4 * gi + k] = gg.rot[k];
+        }
     }
-    const Vec3 p{in.means3D[3 * gi], in.means3D[3 * gi + 1], in.means3D[3 * gi + 2]};
-    const Vec3 sc{in.scales[3 * gi], in.scales[3 * gi + 1], in.scales[3 * gi + 2]};
-    const float4 q4 = *reinterpret_cast<const float4*>(in.rotations + 4 * gi);
-    const float gm2[2] = {g_mean2D[2 * gi], g_mean2D[2 * gi + 1]};
-    const float gc[3] = {g_conic[3 * gi], g_conic[3 * gi + 1], g_conic[3 * gi + 2]};
-    const float gr[3] = {g_rgb[3 * gi], g_rgb[3 * gi + 1], g_rgb[3 * gi + 2]};
-    GaussGrad gg;
-    if (in.shs) {
-        const float* sh = in.shs + gi * 48;
-        gaussian_backward(cam, p, sc, Quat{q4.x, q4.y, q4.z, q4.w}, (uint32_t)g.clamped[gi], gm2, gc, gr,
-                          [&](int k, int ch) { return __ldg(sh + 3 * k + ch); }, sh_store, gg);
-    } else {
-        const float* dc = in.sh_dc + gi * 3;
-        const float* rest = in.sh_rest + gi * 45;
-        gaussian_backward(cam, p, sc, Quat{q4.x, q4.y, q4.z, q4.w}, (uint32_t)g.clamped[gi], gm2, gc, gr,
-                          [&](int k, int ch) { return k == 0 ? __ldg(dc + ch) : __ldg(rest + 3 * (k - 1) + ch); }, sh_store, gg);
+    __syncwarp();
+    for (int idx = lane; idx < cnt * 48; idx += 32) {
+        const int i = idx / 48, e = idx - i * 48;
+        const float v = st[i * kRow + e];
+        if (g_shs) g_shs[g0 * 48 + idx] = v;
+        if (e < 3) { if (g_sh_dc) g_sh_dc[(g0 + i) * 3 + e] = v; }
+        else if (g_sh_rest) g_sh_rest[(g0 + i) * 45 + (e - 3)] = v;
     }
-    for (int k = 0; k < 3; ++k) { g_means3D[3 * gi + k] = gg.mean[k]; g_scales[3 * gi + k] = gg.scale[k]; }
-    for (int k = 0; k < 4; ++k) g_rotations[4 * gi + k] = gg.rot[k];
 }
 
 cudaError_t launch_preprocess_backward(const CameraDev* cam, int64_t n, const RasterInputs& in, GeomBuffers g,
@@ -66,9 +80,15 @@ cudaError_t launch_preprocess_backward(const CameraDev* cam, int64_t n, const Ra
                                        float* g_means2D_out, float* g_scales, float* g_rotations, float* g_shs,
                                        float* g_sh_dc, float* g_sh_rest, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    preprocess_backward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cam, n, in, g, g_mean2D, g_conic, g_rgb, g_means3D,
-                                                                            g_means2D_out, g_scales, g_rotations, g_shs,
-                                                                            g_sh_dc, g_sh_rest);
+    constexpr int kThreads = 128;
+    const size_t smem = (size_t)(kThreads / 32) * 2 * 32 * 49 * sizeof(float);   // 50 KB: SH staging (see the kernel)
+    {
+        cudaError_t e = cudaFuncSetAttribute(preprocess_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    preprocess_backward_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, smem, st>>>(cam, n, in, g, g_mean2D, g_conic, g_rgb,
+                                                                                                  g_means3D, g_means2D_out, g_scales,
+                                                                                                  g_rotations, g_shs, g_sh_dc, g_sh_rest);
     return cudaGetLastError();
 }
 

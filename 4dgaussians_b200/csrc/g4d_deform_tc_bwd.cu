@@ -728,7 +728,7 @@ __global__ void __launch_bounds__(256, 2) bwd_scatter_kernel(BwdScatterDesc sd, 
 // ======================================================================================================
 struct BwdBDesc {
     BwdImages img;
-    int head_mask, F, nchunks;
+    int head_mask, F, nheads, chunks_head, chunks_l0;
     int64_t ntiles;
     float* g_w0; float* g_b0;
     float* g_w1[G4D_NUM_HEADS]; float* g_b1[G4D_NUM_HEADS]; float* g_w2[G4D_NUM_HEADS];
@@ -739,10 +739,16 @@ __global__ void __launch_bounds__(128, 1) deform_tc_bwd_wgrad_kernel(BwdBDesc b)
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(8) uint64_t bar_ld, bar_mma;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int grp = blockIdx.x % 6, chunk = blockIdx.x / 6;
-    const bool layer0 = grp == 5;
-    const int h = grp;
-    if (!layer0 && !(b.head_mask & (1 << h))) return;
+    // CTAs [0, nheads * chunks_head) serve the active heads, the rest layer 0 (CTA counts proportional to the bytes per tile)
+    const bool layer0 = (int)blockIdx.x >= b.nheads * b.chunks_head;
+    const int chunk = layer0 ? (int)blockIdx.x - b.nheads * b.chunks_head : (int)blockIdx.x % b.chunks_head;
+    const int nch = layer0 ? b.chunks_l0 : b.chunks_head;
+    int h = 5;
+    if (!layer0) {
+        int m = b.head_mask;
+        for (int i = 0; i < (int)blockIdx.x / b.chunks_head; ++i) m &= m - 1;
+        h = __ffs(m) - 1;
+    }
     const int kp16 = (h == 4) ? 48 : 16;
     // smem: X (DZ_h or DH) | Y (A1 or FEAT) | A2_h | DOUT_h | ONES
     uint8_t* sX = smem;
@@ -761,7 +767,7 @@ __global__ void __launch_bounds__(128, 1) deform_tc_bwd_wgrad_kernel(BwdBDesc b)
     const uint32_t tbase = tmem_base_s;
     const uint32_t lane_base = tbase + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t colW = 0, colW2 = 128, colB = 192;   // accumulators: dW (128 or F cols) | dW2^T (kp16) | bias (16)
-    const int64_t per = (b.ntiles + b.nchunks - 1) / b.nchunks;
+    const int64_t per = (b.ntiles + nch - 1) / nch;
     const int64_t t0 = (int64_t)chunk * per, t1 = (t0 + per < b.ntiles) ? t0 + per : b.ntiles;
     const uint32_t y_bytes = layer0 ? b.img.feat_bytes : 2u * kImg128;
     const uint32_t do_bytes = 2u * 128 * kp16 * 2;
@@ -863,7 +869,8 @@ static cudaError_t launch_a(const BwdADesc& bd, float time, int64_t n, const flo
 cudaError_t launch_deform_backward_tc(const DeformDesc& d, const G4DDeformParams& prm, const G4DDeformGrads& grads,
                                       const TcBwdWeights& w, float time, int64_t n, const float* xyz,
                                       const float* const go[G4D_NUM_HEADS], float* const gi[G4D_NUM_HEADS],
-                                      const uint32_t* relu_bits, long long* dbg, uint8_t* scratch, int sm_count, cudaStream_t st) {
+                                      const uint32_t* relu_bits, const float* saved_feat, long long* dbg, uint8_t* scratch,
+                                      int sm_count, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     const int64_t ntiles = (n + 127) / 128;
     BwdADesc a{};
@@ -883,7 +890,7 @@ cudaError_t launch_deform_backward_tc(const DeformDesc& d, const G4DDeformParams
     }
     float* feat = reinterpret_cast<float*>(take((size_t)ntiles * 128 * d.F * 4));
     float* dfeat = reinterpret_cast<float*>(take((size_t)ntiles * 128 * d.F * 4));
-    a.feat = feat; a.dfeat = dfeat;
+    a.feat = saved_feat ? saved_feat : feat; a.dfeat = dfeat;   // saved_feat: the features the forward of this view staged
     size_t row_floats = 0;
     for (int l = 0; l < d.levels; ++l)
         for (int k = 0; k < 3; ++k) row_floats += (size_t)d.res[l][k] * d.C;
@@ -901,8 +908,8 @@ cudaError_t launch_deform_backward_tc(const DeformDesc& d, const G4DDeformParams
     cudaError_t e = cudaMemsetAsync(rows, 0, row_floats * 4, st);
     if (e != cudaSuccess) return e;
     const int C4 = d.C / 4;
-    // gather at full occupancy
-    {
+    // gather at full occupancy (skipped when the forward's feature staging buffer was kept for this backward)
+    if (!saved_feat) {
         const int64_t threads = n * C4;
         const unsigned grid = (unsigned)((threads + 255) / 256);
         if (C4 == 4) bwd_features_kernel<4><<<grid, 256, 0, st>>>(d, n, xyz, feat);
@@ -926,14 +933,25 @@ cudaError_t launch_deform_backward_tc(const DeformDesc& d, const G4DDeformParams
     // kernel B
     BwdBDesc b{};
     b.img = a.img; b.head_mask = d.head_mask; b.F = d.F; b.ntiles = ntiles;
-    b.nchunks = sm_count / 6 > 0 ? sm_count / 6 : 1;
-    if ((int64_t)b.nchunks > ntiles) b.nchunks = (int)ntiles;
+    {
+        int nheads = 0;
+        for (int h = 0; h < G4D_NUM_HEADS; ++h) nheads += (d.head_mask >> h) & 1;
+        // bytes per tile: a head streams DZ + A1 + A2 (+ DOUT), layer 0 streams DH + FEAT
+        const double wh = 3.0 * 64 + 16, w0 = 64 + (double)(2 * 128 * d.F * 2) / 1024.0, tot = nheads * wh + w0;
+        int ch = nheads ? (int)(sm_count * wh / tot) : 0;
+        if (ch < 1) ch = 1;
+        int c0 = sm_count - nheads * ch;
+        if (c0 < 1) c0 = 1;
+        if ((int64_t)ch > ntiles) ch = (int)ntiles;
+        if ((int64_t)c0 > ntiles) c0 = (int)ntiles;
+        b.nheads = nheads; b.chunks_head = ch; b.chunks_l0 = c0;
+    }
     b.g_w0 = grads.w0; b.g_b0 = grads.b0;
     for (int h = 0; h < G4D_NUM_HEADS; ++h) { b.g_w1[h] = grads.w1[h]; b.g_b1[h] = grads.b1[h]; b.g_w2[h] = grads.w2[h]; }
     const size_t smem_b = (size_t)6 * kImg128 + (size_t)2 * 128 * 48 * 2 + 128 * 16 * 2 + 1024;
     e = cudaFuncSetAttribute(deform_tc_bwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
     if (e != cudaSuccess) return e;
-    deform_tc_bwd_wgrad_kernel<<<6 * b.nchunks, 128, smem_b, st>>>(b);
+    deform_tc_bwd_wgrad_kernel<<<b.nheads * b.chunks_head + b.chunks_l0, 128, smem_b, st>>>(b);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     return launch_distribute_time_grad(d, sc.trow_grad, sc.g_planes, time, st);
 }

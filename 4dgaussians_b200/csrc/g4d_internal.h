@@ -74,7 +74,8 @@ size_t tc_deform_backward_scratch_bytes(const DeformDesc& d, int64_t n);
 cudaError_t launch_deform_backward_tc(const DeformDesc& d, const G4DDeformParams& prm, const G4DDeformGrads& grads,
                                       const TcBwdWeights& w, float time, int64_t n, const float* xyz,
                                       const float* const go[G4D_NUM_HEADS], float* const gi[G4D_NUM_HEADS],
-                                      const uint32_t* relu_bits, long long* dbg, uint8_t* scratch, int sm_count, cudaStream_t st);
+                                      const uint32_t* relu_bits, const float* saved_feat, long long* dbg, uint8_t* scratch,
+                                      int sm_count, cudaStream_t st);
 // collapsed time-row gradients -> the two time rows of each (axis, t) plane (g4d_backward.cu)
 cudaError_t launch_distribute_time_grad(const DeformDesc& d, float* const (*trow_grad)[3], float* const (*g_planes)[6], float time,
                                         cudaStream_t st);

@@ -237,6 +237,24 @@ class deform_network(nn.Module):
             off += n
         return out
 
+    # Opt-in (default off, autograd semantics untouched): when True and every parameter already owns a `.grad` with the
+    # parameter's own memory layout (e.g. views of a dp.FlatGradBucket), the backward kernels -- which ACCUMULATE with
+    # atomics anyway -- add straight into those tensors and autograd receives None for the parameters: no per-view
+    # zero-filled staging buffer and no 47 AccumulateGrad `add_` launches per view.
+    fused_grad_accumulation = False
+
+    def grad_sinks(self) -> Optional[List[torch.Tensor]]:
+        """the parameters' own .grad tensors when fused accumulation is possible, else None"""
+        if not self.fused_grad_accumulation:
+            return None
+        out = []
+        for p in self.flat_parameters():
+            g = p.grad
+            if g is None or g.dtype != torch.float32 or g.shape != p.shape or g.stride() != p.stride() or g.device != p.device:
+                return None
+            out.append(g)
+        return out
+
     def c_grads(self, grads: List[torch.Tensor]) -> _lib.DeformGrads:
         g = _lib.DeformGrads()
         L = len(self.deformation_net.grid.grids)
@@ -319,8 +337,13 @@ class _DeformFunction(torch.autograd.Function):
         prm = module.c_params(keep)
         hm = prm.head_mask
         flat = module.flat_parameters()
-        pgrads = module.alloc_grads()                      # one buffer, channel-last views for the planes
-        cg = module.c_grads(pgrads)
+        sinks = module.grad_sinks()
+        if sinks is not None:                              # opt-in fused accumulation into the parameters' own .grad
+            pgrads = [None] * len(sinks)
+            cg = module.c_grads(sinks)
+        else:
+            pgrads = module.alloc_grads()                  # one buffer, channel-last views for the planes
+            cg = module.c_grads(pgrads)
 
         def gin(g, shape_ok):
             if g is None or not shape_ok or g.numel() == 0:

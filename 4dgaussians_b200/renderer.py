@@ -79,8 +79,13 @@ class _FusedRender(torch.autograd.Function):
         prm = module.c_params(keep) if module is not None else None
         pgrads, cg = [], None
         if module is not None:
-            pgrads = module.alloc_grads()
-            cg = module.c_grads(pgrads)
+            sinks = module.grad_sinks()
+            if sinks is not None:          # opt-in fused accumulation: kernels add into the parameters' own .grad
+                cg = module.c_grads(sinks)
+                pgrads = [None] * len(sinks)
+            else:
+                pgrads = module.alloc_grads()
+                cg = module.c_grads(pgrads)
         g = _lib.Gaussians(n, x.data_ptr(), s.data_ptr(), r.data_ptr(), o.data_ptr(), dc.data_ptr(), rest.data_ptr())
         gx = torch.empty(n, 3, device=dev); gs = torch.empty(n, 3, device=dev); gr = torch.empty(n, 4, device=dev)
         go = torch.empty(n, 1, device=dev); gdc = torch.empty(n, 1, 3, device=dev); grest = torch.empty(n, 15, 3, device=dev)

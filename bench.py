@@ -345,6 +345,7 @@ def run_train_steps(g4d, synth, lib, w, scene, mod, dev, dist, world, rank, step
     pc = synth.SyntheticGaussianModel(scene, mod, device=dev, sh_degree=3, requires_grad=True)
     params = pc.gaussian_parameters() + [p for p in mod.flat_parameters()]
     bucket = dp.FlatGradBucket(params)
+    mod.fused_grad_accumulation = True      # backward kernels add straight into the bucket views (deformation.py)
     opt = torch.optim.Adam([{"params": params, "lr": 1e-4}], eps=1e-15, fused=True)
     B = 2
     cams = synth.orbit_cameras(64, w["width"], w["height"], radius=w["radius"], focal=w["focal"], timestamps=300)
@@ -378,7 +379,7 @@ def run_train_steps(g4d, synth, lib, w, scene, mod, dev, dist, world, rank, step
     st = ctx[-1].stage_times() if ctx else {}
     return {"ms_per_step": float(ms.item()), "step_ms": [round(x.elapsed_time(y), 3) for x, y in evs],
             "views_per_step_per_gpu": B, "global_batch": B * world,
-            "includes": "2x fused fwd+bwd, L1 loss, one flat-bucket all-reduce (%d floats), fused Adam" % bucket.numel,
+            "includes": "2x fused fwd+bwd (network gradients accumulated straight into the flat bucket), L1 loss, one flat-bucket all-reduce (%d floats), fused Adam" % bucket.numel,
             "last_view_stage_ms": st}
 
 

@@ -8,6 +8,8 @@ import math
 import os
 
 import numpy as np
+import importlib
+
 import pytest
 import torch
 
@@ -277,6 +279,28 @@ def test_fused_render_backward(ci, stage):
                 assert e <= 3 * GRAD_TOL, (k, e)
     else:
         assert all(p.grad is None for p in mod.parameters())
+
+
+def test_fused_grad_accumulation_matches_autograd_accumulation():
+    """deform_network.fused_grad_accumulation: two views accumulated by the kernels straight into FlatGradBucket views give
+    the same .grad as autograd's AccumulateGrad over per-view staging buffers."""
+    dp = importlib.import_module("4dgaussians_b200.dp")
+    c = FUSED_CASES[2]
+    res = []
+    for fused in (False, True):
+        scene, mod, pc, cam = _fused_setup(c)
+        params = pc.gaussian_parameters() + list(mod.flat_parameters())
+        bucket = dp.FlatGradBucket(params)
+        mod.fused_grad_accumulation = fused
+        bucket.zero_()
+        for th in (c["theta"], c["theta"] + 25.0):
+            cam_v = synth.make_camera(th, c["wh"][0], c["wh"][1], radius=c["radius"], time=c["t"])
+            out = g4d.render(cam_v, pc, _Pipe, torch.tensor(c["bg"], device="cuda"))
+            (out["render"] * 0.5).abs().mean().backward()
+        res.append(bucket.flat.clone())
+    a, b = res
+    assert float(b.abs().max()) > 0
+    assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
 
 
 def test_render_matches_unfused_dropin_composition():
