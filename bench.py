@@ -292,9 +292,9 @@ def run_ours(args):
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         traffic, traffic_src = None, None
         try:     # dram bytes per launch of the dominant kernel from the committed ncu --set full capture of this workload
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1c_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1e_traffic.json")))
             bpl = tj["bytes_per_launch"]
-            keys = {"geom": ["deform_tc_kernel<1, 16, 2, 1>", "deform_features_kernel<4>"], "blend": ["blend_forward_kernel"], "sort": []}[dom]
+            keys = {"geom": ["deform_tc_kernel<1, 16, 2, 1>", "deform_features_kernel<4>"], "blend": ["blend_forward_kernel<2>"], "sort": []}[dom]
             if keys and all(k_ in bpl for k_ in keys):
                 traffic, traffic_src = float(sum(bpl[k_] for k_ in keys)), tj["source"]
         except Exception:
