@@ -163,13 +163,20 @@ def hidden_args(net: str):
         # small shapes for fast tests (same code paths as dnerf / dynerf)
         "small64": dict(channels=16, resolution=[12, 10, 9, 7], multires=[1, 2], net_width=64, no_do=True, no_dshs=True),
         "small128": dict(channels=16, resolution=[9, 12, 10, 8], multires=[1, 2], net_width=128, no_do=False, no_dshs=False),
+        # head-mask / shape corner cases of the tensor-core kernels
+        "pos128": dict(channels=16, resolution=[9, 12, 10, 8], multires=[1, 2], net_width=128, no_do=True, no_dshs=True,
+                       no_ds=True, no_dr=True),                                                   # a single head
+        "shs128": dict(channels=16, resolution=[8, 8, 8, 6], multires=[1, 2], net_width=128, no_do=True, no_dshs=False,
+                       no_dx=True, no_ds=True, no_dr=True),                                       # only the 48-wide head
+        "c32w128": dict(channels=32, resolution=[10, 9, 8, 6], multires=[1, 2], net_width=128, no_do=False, no_dshs=True),
     }
     c = cfgs[net]
     return Namespace(net_width=c["net_width"], timebase_pe=4, defor_depth=1, posebase_pe=10, scale_rotation_pe=2, opacity_pe=2,
                      timenet_width=64, timenet_output=32, bounds=1.6, grid_pe=0,
                      kplanes_config={"grid_dimensions": 2, "input_coordinate_dim": 4, "output_coordinate_dim": c["channels"],
                                      "resolution": list(c["resolution"])},
-                     multires=list(c["multires"]), no_dx=False, no_grid=False, no_ds=False, no_dr=False, no_do=c["no_do"],
+                     multires=list(c["multires"]), no_dx=c.get("no_dx", False), no_grid=False, no_ds=c.get("no_ds", False),
+                     no_dr=c.get("no_dr", False), no_do=c["no_do"],
                      no_dshs=c["no_dshs"], empty_voxel=False, static_mlp=False, apply_rotation=False)
 
 

@@ -404,6 +404,33 @@ def test_tensor_core_mlp_matches_ffma_path(net, n):
         assert float((x - y).abs().max()) <= 5e-6, (nm, float((x - y).abs().max()))
 
 
+@pytest.mark.parametrize("net,n", [("pos128", 1), ("pos128", 129), ("shs128", 700), ("c32w128", 300), ("dynerf", 127), ("small128", 300)])
+def test_tensor_core_paths_corner_cases_vs_oracle(net, n):
+    """Head masks with one head / only the 48-wide head, the C=32 and L=3 template instances, tiles of 1, 127 and 129
+    Gaussians: forward AND backward of the tensor-core kernels against the CPU oracle."""
+    t = 0.43
+    mod = make_module(net, seed=8)
+    cfg, prm = oracle_params_from_module(mod)
+    ins, probes = _deform_inputs(n, 12)
+    dev_in = [x.clone().requires_grad_(True) for x in ins]
+    outs = mod(*dev_in, torch.tensor(t).repeat(n, 1).cuda())
+    cpu_in = [x.cpu().clone().requires_grad_(True) for x in ins]
+    w = dr.deform_forward(cfg, prm, *cpu_in, t)
+    for o, r, nm in zip(outs, w, ("pts", "scales", "rot", "opacity", "shs")):
+        assert float((o.detach().cpu() - r.detach()).abs().max()) <= 3e-5, (nm,)
+    sum((o * p.cuda()).sum() for o, p in zip(outs, probes)).backward()
+    sum((o * p).sum() for o, p in zip(w, probes)).backward()
+    for a, b, nm in zip(dev_in, cpu_in, ("xyz", "scales", "rot", "opacity", "shs")):
+        e, emax = rel_err_bulk(a.grad.cpu().numpy(), b.grad.numpy())
+        assert e <= GRAD_TOL and emax <= 5e-2, (nm, e, emax)
+    osd = dr.params_to_state_dict(prm)
+    for k, p in mod.named_parameters():
+        if k not in osd or not p.requires_grad or osd[k].grad is None:
+            continue
+        e = rel_err(p.grad.cpu().numpy(), osd[k].grad.numpy())
+        assert e <= 3 * GRAD_TOL, (k, e)
+
+
 @pytest.mark.parametrize("net,n", [("small128", 700), ("dynerf", 21000), ("hypernerf", 40000)])
 def test_tensor_core_backward_matches_ffma_path(net, n):
     """BF16x2 tcgen05 backward (dgrad + wgrad kernels) against the FP32 FFMA backward: same gradients for every input
