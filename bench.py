@@ -250,7 +250,31 @@ def run_ours(args):
     e2e_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev2)], device=dev, dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * K / (float(e2e_ms.item()) / 1e3)
+    e2e_serial = world * K / (float(e2e_ms.item()) / 1e3)
+    # the same K steps as a user would pipeline them: the image of frame i travels to (double-buffered) pinned host memory
+    # on a copy stream while frame i+1 renders.  ONE event pair around the K steps; the L2 flushes are inside the bracket.
+    pinned2 = [pinned, torch.empty(3, H, Wd, dtype=torch.float32).pin_memory()]
+    copy_stream = torch.cuda.Stream(device=dev)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        barrier()
+        p0.record()
+        for i in range(K):
+            flush.fill_(i & 0xFF)
+            out = g4d.render(my_cams[Wm + i], pc, Pipe, bg)
+            ready = torch.cuda.Event()
+            ready.record()
+            copy_stream.wait_event(ready)
+            with torch.cuda.stream(copy_stream):
+                pinned2[i & 1].copy_(out["render"], non_blocking=True)
+            out["render"].record_stream(copy_stream)
+        torch.cuda.current_stream(dev).wait_stream(copy_stream)
+        p1.record()
+        barrier()
+    e2e_pipe_ms = torch.tensor([p0.elapsed_time(p1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(e2e_pipe_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * K / (float(e2e_pipe_ms.item()) / 1e3)
     cam_bytes = 4 * (16 + 16 + 3 + 3 + 4) + 16
 
     # ------------------------------------------------------------------ opt-in exact-image tile culling (same pixels, fewer bins)
@@ -312,7 +336,12 @@ def run_ours(args):
                        "binning": "capacity-bounded, no host sync (overflow-checked)" if args.no_host_sync else "host sync on R",
                        "mlp": "tcgen05 3xTF32 forward (fp32-accurate), BF16x2 tcgen05 backward",
                        "parallelism": "scene replicated, views sharded (dp%d)" % world},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cam_bytes, "d2h_bytes_per_step": 3 * H * Wd * 4},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cam_bytes, "d2h_bytes_per_step": 3 * H * Wd * 4,
+                    "how": "public render() per frame, camera from host memory, image to double-buffered pinned host memory on a "
+                           "copy stream (frame i copies while frame i+1 renders); one event pair around the K steps, the "
+                           "512 MiB L2 flush of every step INSIDE the bracket",
+                    "serial_value": e2e_serial,
+                    "serial_how": "same steps, copy on the render stream, per-step event pairs (flush outside): no overlap"},
             "gpu_launches": 8 * K,
             "gpu_launches_note": "own kernels per step: pack_camera, collapse_time_rows, deform_features, deform_tc_kernel(fused), "
                                  "depth_keys, emit_keys, tile_ranges, blend_forward; plus CUB scan/sort library launches",
