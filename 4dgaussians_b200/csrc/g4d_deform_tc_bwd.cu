@@ -48,7 +48,8 @@ __device__ __forceinline__ void gemm_bf16x2_ts(uint32_t d_tmem, uint32_t a_hi, u
     }
 }
 
-// D[128 x N] (+)= A^T B with both operands MN-major images (rows = K = Gaussian, cols = M resp. N), K = 128
+// D[128 x N] (+)= A^T B with both operands MN-major images (rows = K = Gaussian, cols = M resp. N), K rows
+template <int K>
 __device__ __forceinline__ void gemm_bf16x2_ss_mn(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t a_ncols, uint32_t b_hi,
                                                   uint32_t b_lo, uint32_t b_ncols, uint32_t N, bool accumulate, bool b_single) {
     const uint32_t idesc = tc::make_idesc_bf16(128, N, true, true);
@@ -62,7 +63,7 @@ __device__ __forceinline__ void gemm_bf16x2_ss_mn(uint32_t d_tmem, uint32_t a_hi
         const uint64_t ad = (p == 0) ? ad_lo : ad_hi;
         const uint64_t bd = (p == 1) ? bd_lo : bd_hi;
 #pragma unroll
-        for (int ks = 0; ks < 128; ks += 16)
+        for (int ks = 0; ks < K; ks += 16)
             tc::umma_bf16_ss(d_tmem, ad + (uint64_t)((ks >> 4) * a_step), bd + (uint64_t)((ks >> 4) * b_step), idesc,
                              accumulate || p > 0 || ks > 0);
     }
@@ -86,13 +87,15 @@ struct Split16 {
     uint32_t hi[8], lo[8];
 };
 __device__ __forceinline__ void split16(const float (&x)[16], Split16& o) {
+    // two elements per cvt: cvt.rn.bf16x2.f32 d, a, b packs a into the upper and b into the lower half (lower = even k)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        uint16_t h0, l0, h1, l1;
-        tc::bf16_split(x[2 * j], h0, l0);
-        tc::bf16_split(x[2 * j + 1], h1, l1);
-        o.hi[j] = pack2(h0, h1);
-        o.lo[j] = pack2(l0, l1);
+        uint32_t hi, lo;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x[2 * j + 1]), "f"(x[2 * j]));
+        const float he = __uint_as_float(hi << 16), ho = __uint_as_float(hi & 0xffff0000u);
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x[2 * j + 1] - ho), "f"(x[2 * j] - he));
+        o.hi[j] = hi;
+        o.lo[j] = lo;
     }
 }
 // write 16 columns [c0, c0+16) of row g of a (hi | lo) image with `ncols` columns (lo part at +part_bytes)
@@ -737,7 +740,7 @@ struct BwdBDesc {
 __global__ void __launch_bounds__(128, 1) deform_tc_bwd_wgrad_kernel(BwdBDesc b) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(8) uint64_t bar_ld, bar_mma;
+    __shared__ __align__(8) uint64_t bar_ld[2], bar_mma[2], bar_done;
     const int tid = threadIdx.x, warp = tid >> 5;
     // CTAs [0, nheads * chunks_head) serve the active heads, the rest layer 0 (CTA counts proportional to the bytes per tile)
     const bool layer0 = (int)blockIdx.x >= b.nheads * b.chunks_head;
@@ -750,16 +753,19 @@ __global__ void __launch_bounds__(128, 1) deform_tc_bwd_wgrad_kernel(BwdBDesc b)
         h = __ffs(m) - 1;
     }
     const int kp16 = (h == 4) ? 48 : 16;
-    // smem: X (DZ_h or DH) | Y (A1 or FEAT) | A2_h | DOUT_h | ONES
-    uint8_t* sX = smem;
-    uint8_t* sY = smem + 2 * kImg128;
-    uint8_t* sA2 = smem + 4 * kImg128;
-    uint8_t* sDO = smem + 6 * kImg128;
-    uint8_t* sOnes = sDO + 2u * 128 * 48 * 2;
-    // ones image [128 g][16]: bf16 1.0 = 0x3F80
-    for (int i = tid; i < 128 * 16; i += 128) reinterpret_cast<uint16_t*>(sOnes)[i] = 0x3F80;
+    // Two pipeline stages of HALF a tile each (64 Gaussians = the K extent of one MMA chain): the images are row-group major,
+    // so rows [64 hf, 64 hf + 64) of a part are one contiguous half of its bytes.  While the tensor core chews on one stage the
+    // TMA fills the other.  Per stage: X (DZ_h or DH) | Y (A1 or FEAT) | A2_h | DOUT_h, each as (hi half | lo half).
+    constexpr uint32_t kHalf128 = kImg128 / 2;                       // 16 KB: 64 rows x 128 cols bf16
+    constexpr uint32_t kStage = 3u * 2u * kHalf128 + 2u * 64 * 48 * 2;   // 108 KB
+    uint8_t* sOnes = smem + 2 * kStage;
+    // ones image [64 g][16]: bf16 1.0 = 0x3F80
+    for (int i = tid; i < 64 * 16; i += 128) reinterpret_cast<uint16_t*>(sOnes)[i] = 0x3F80;
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, tc::kTmemCols);
-    if (tid == 0) { mbar_init(&bar_ld, 1); mbar_init(&bar_mma, 1); fence_barrier_init(); }
+    if (tid == 0) {
+        mbar_init(&bar_ld[0], 1); mbar_init(&bar_ld[1], 1); mbar_init(&bar_mma[0], 1); mbar_init(&bar_mma[1], 1); mbar_init(&bar_done, 1);
+        fence_barrier_init();
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc::fence_before_sync();
     __syncthreads();
@@ -769,37 +775,60 @@ __global__ void __launch_bounds__(128, 1) deform_tc_bwd_wgrad_kernel(BwdBDesc b)
     const uint32_t colW = 0, colW2 = 128, colB = 192;   // accumulators: dW (128 or F cols) | dW2^T (kp16) | bias (16)
     const int64_t per = (b.ntiles + nch - 1) / nch;
     const int64_t t0 = (int64_t)chunk * per, t1 = (t0 + per < b.ntiles) ? t0 + per : b.ntiles;
-    const uint32_t y_bytes = layer0 ? b.img.feat_bytes : 2u * kImg128;
-    const uint32_t do_bytes = 2u * 128 * kp16 * 2;
-    uint32_t phase = 0;
+    const uint32_t yp = layer0 ? 128u * b.F * 2u : kImg128;            // bytes of one part (hi or lo) of Y
+    const uint32_t dp = 128u * kp16 * 2u;                              // ... of DOUT
+    const int64_t nwork = t1 > t0 ? 2 * (t1 - t0) : 0;
     bool started = false;
-    for (int64_t t = t0; t < t1; ++t) {
-        if (tid == 0) {
-            const uint32_t bytes = 2u * kImg128 + y_bytes + (layer0 ? 0u : 2u * kImg128 + do_bytes);
-            mbar_expect_tx(&bar_ld, bytes);
-            tma_bulk_g2s(sX, (layer0 ? b.img.dh : b.img.dz[h]) + (size_t)t * 2 * kImg128, 2u * kImg128, &bar_ld);
-            tma_bulk_g2s(sY, layer0 ? b.img.feat + (size_t)t * b.img.feat_bytes : b.img.a1 + (size_t)t * 2 * kImg128, y_bytes, &bar_ld);
+    if (tid == 0 && nwork > 0) {
+        auto load = [&](int64_t w) {
+            const int st = (int)(w & 1), hf = (int)(w & 1);             // work item w = 2 (t - t0) + hf uses stage w & 1
+            const int64_t t = t0 + (w >> 1);
+            uint8_t* base = smem + st * kStage;
+            uint8_t *dX = base, *dY = base + 2 * kHalf128, *dA2 = base + 4 * kHalf128, *dDO = base + 6 * kHalf128;
+            const uint8_t* srcX = (layer0 ? b.img.dh : b.img.dz[h]) + (size_t)t * 2 * kImg128;
+            const uint8_t* srcY = layer0 ? b.img.feat + (size_t)t * b.img.feat_bytes : b.img.a1 + (size_t)t * 2 * kImg128;
+            const uint32_t bytes = 2u * kHalf128 + yp + (layer0 ? 0u : 2u * kHalf128 + dp);
+            mbar_expect_tx(&bar_ld[st], bytes);
+            tma_bulk_g2s(dX, srcX + hf * kHalf128, kHalf128, &bar_ld[st]);
+            tma_bulk_g2s(dX + kHalf128, srcX + kImg128 + hf * kHalf128, kHalf128, &bar_ld[st]);
+            tma_bulk_g2s(dY, srcY + hf * (yp / 2), yp / 2, &bar_ld[st]);
+            tma_bulk_g2s(dY + yp / 2, srcY + yp + hf * (yp / 2), yp / 2, &bar_ld[st]);
             if (!layer0) {
-                tma_bulk_g2s(sA2, b.img.a2[h] + (size_t)t * 2 * kImg128, 2u * kImg128, &bar_ld);
-                tma_bulk_g2s(sDO, b.img.dout[h] + (size_t)t * do_bytes, do_bytes, &bar_ld);
+                const uint8_t* srcA = b.img.a2[h] + (size_t)t * 2 * kImg128;
+                const uint8_t* srcD = b.img.dout[h] + (size_t)t * 2 * dp;
+                tma_bulk_g2s(dA2, srcA + hf * kHalf128, kHalf128, &bar_ld[st]);
+                tma_bulk_g2s(dA2 + kHalf128, srcA + kImg128 + hf * kHalf128, kHalf128, &bar_ld[st]);
+                tma_bulk_g2s(dDO, srcD + hf * (dp / 2), dp / 2, &bar_ld[st]);
+                tma_bulk_g2s(dDO + dp / 2, srcD + dp + hf * (dp / 2), dp / 2, &bar_ld[st]);
             }
-            mbar_wait(&bar_ld, phase);
+        };
+        uint32_t ph_ld[2] = {0u, 0u}, ph_mma[2] = {0u, 0u};
+        load(0);
+        for (int64_t w = 0; w < nwork; ++w) {
+            const int st = (int)(w & 1);
+            if (w + 1 < nwork) {
+                const int ns = st ^ 1;
+                if (w >= 1) { mbar_wait(&bar_mma[ns], ph_mma[ns]); ph_mma[ns] ^= 1u; }   // MMAs of work item w-1 have released stage ns
+                load(w + 1);
+            }
+            mbar_wait(&bar_ld[st], ph_ld[st]); ph_ld[st] ^= 1u;
             tc::fence_after_sync();
-            const uint32_t x = tc::smem_addr(sX), y = tc::smem_addr(sY), ones = tc::smem_addr(sOnes);
+            const uint32_t base = tc::smem_addr(smem + st * kStage), ones = tc::smem_addr(sOnes);
+            const uint32_t x = base, y = base + 2 * kHalf128, a2 = base + 4 * kHalf128, dd = base + 6 * kHalf128;
             if (layer0) {
-                gemm_bf16x2_ss_mn(tbase + colW, x, x + kImg128, 128, y, y + 128u * b.F * 2, (uint32_t)b.F, (uint32_t)b.F, started, false);
+                gemm_bf16x2_ss_mn<64>(tbase + colW, x, x + kHalf128, 128, y, y + yp / 2, (uint32_t)b.F, (uint32_t)b.F, started, false);
             } else {
-                gemm_bf16x2_ss_mn(tbase + colW, x, x + kImg128, 128, y, y + kImg128, 128, 128, started, false);
-                const uint32_t a2 = tc::smem_addr(sA2), dd = tc::smem_addr(sDO);
-                gemm_bf16x2_ss_mn(tbase + colW2, a2, a2 + kImg128, 128, dd, dd + 128u * kp16 * 2, (uint32_t)kp16, (uint32_t)kp16, started, false);
+                gemm_bf16x2_ss_mn<64>(tbase + colW, x, x + kHalf128, 128, y, y + kHalf128, 128, 128, started, false);
+                gemm_bf16x2_ss_mn<64>(tbase + colW2, a2, a2 + kHalf128, 128, dd, dd + dp / 2, (uint32_t)kp16, (uint32_t)kp16, started, false);
             }
-            gemm_bf16x2_ss_mn(tbase + colB, x, x + kImg128, 128, ones, ones, 16, 16, started, true);
-            tc::umma_commit(&bar_mma);
-            mbar_wait(&bar_mma, phase);     // operands are single-buffered: wait before the next tile overwrites them
-            phase ^= 1u;
+            gemm_bf16x2_ss_mn<64>(tbase + colB, x, x + kHalf128, 128, ones, ones, 16, 16, started, true);
+            tc::umma_commit(&bar_mma[st]);
             started = true;
         }
+        tc::umma_commit(&bar_done);        // covers every MMA issued above
+        mbar_wait(&bar_done, 0);
     }
+    started = nwork > 0;
     __syncthreads();
     tc::fence_after_sync();
     if (started || true) {
@@ -948,7 +977,7 @@ cudaError_t launch_deform_backward_tc(const DeformDesc& d, const G4DDeformParams
     }
     b.g_w0 = grads.w0; b.g_b0 = grads.b0;
     for (int h = 0; h < G4D_NUM_HEADS; ++h) { b.g_w1[h] = grads.w1[h]; b.g_b1[h] = grads.b1[h]; b.g_w2[h] = grads.w2[h]; }
-    const size_t smem_b = (size_t)6 * kImg128 + (size_t)2 * 128 * 48 * 2 + 128 * 16 * 2 + 1024;
+    const size_t smem_b = (size_t)2 * (3 * kImg128 + 2 * 64 * 48 * 2) + 64 * 16 * 2 + 1024;   // two half-tile stages + ones
     e = cudaFuncSetAttribute(deform_tc_bwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
     if (e != cudaSuccess) return e;
     deform_tc_bwd_wgrad_kernel<<<b.nheads * b.chunks_head + b.chunks_l0, 128, smem_b, st>>>(b);
