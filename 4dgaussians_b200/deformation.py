@@ -247,15 +247,29 @@ class deform_network(nn.Module):
         """the parameters' own .grad tensors when fused accumulation is possible, else None"""
         if not self.fused_grad_accumulation:
             return None
+        flat = self.flat_parameters()
+        cache = getattr(self, "_sink_cache", None)
+        if cache is not None and len(cache[0]) == len(flat) and all(p.grad is g for p, g in zip(flat, cache[0])):
+            return cache[0]                       # same .grad objects as last time: already validated
         out = []
-        for p in self.flat_parameters():
+        for p in flat:
             g = p.grad
             if g is None or g.dtype != torch.float32 or g.shape != p.shape or g.stride() != p.stride() or g.device != p.device:
                 return None
             out.append(g)
+        self._sink_cache = [out, None]
         return out
 
     def c_grads(self, grads: List[torch.Tensor]) -> _lib.DeformGrads:
+        cache = getattr(self, "_sink_cache", None)
+        if cache is not None and grads is cache[0] and cache[1] is not None:
+            return cache[1]
+        g = self._build_c_grads(grads)
+        if cache is not None and grads is cache[0]:
+            cache[1] = g
+        return g
+
+    def _build_c_grads(self, grads: List[torch.Tensor]) -> _lib.DeformGrads:
         g = _lib.DeformGrads()
         L = len(self.deformation_net.grid.grids)
         i = 0
