@@ -206,8 +206,8 @@ def run_ours(args):
     with torch.no_grad():
         for i in range(Wm):
             g4d.render(my_cams[i], pc, Pipe, bg)
-        barrier()
         gc.collect(); gc.disable()     # a host hiccup shows up 1:1 in a ~1 ms step that synchronises on R once per frame
+        barrier()                      # nothing slow between here and the first timed step: an idle GPU drops its clocks
         sampler.mark()
         t_wall0 = time.perf_counter()
         for i in range(K):
