@@ -464,7 +464,7 @@ blend_backward_kernel(const CameraDev* __restrict__ cam, GeomBuffers g, const ui
             for (int k = 0; k < PPT; ++k) {
                 if (!validk[k]) continue;
                 const float alpha = alphak[k], G = Gk[k], dx = dxk[k], dy = dyk[k];
-                const float ra = 1.f / (1.f - alpha);
+                const float ra = __fdividef(1.f, 1.f - alpha);   // alpha <= 0.99: well inside the fast-division range
                 T[k] = T[k] * ra;
                 const float w = alpha * T[k];
                 ac0[k] = last_alpha[k] * lc0[k] + (1.f - last_alpha[k]) * ac0[k]; lc0[k] = c0;
