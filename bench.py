@@ -207,7 +207,13 @@ def run_ours(args):
         for i in range(Wm):
             g4d.render(my_cams[i], pc, Pipe, bg)
         gc.collect(); gc.disable()     # a host hiccup shows up 1:1 in a ~1 ms step that synchronises on R once per frame
-        barrier()                      # nothing slow between here and the first timed step: an idle GPU drops its clocks
+        barrier()
+        # Ranks leave the collective barrier at different times and an idle B200 drops its clocks within milliseconds (measured:
+        # the 2nd step after an idle gap stalls 5-40 ms).  Two more untimed warm-up renders, then the synchronize that
+        # brackets the timed region -- after it the GPU is idle for microseconds only.
+        for i in range(2):
+            g4d.render(my_cams[i], pc, Pipe, bg)
+        torch.cuda.synchronize(dev)
         sampler.mark()
         t_wall0 = time.perf_counter()
         for i in range(K):
