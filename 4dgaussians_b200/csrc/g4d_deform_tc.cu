@@ -8,8 +8,10 @@
 //     (hi | lo TF32 parts) and streamed head by head with TMA bulk copies + mbarriers;
 //   * fp32 accuracy through 3xTF32 (lo*hi + hi*lo + hi*hi, fp32 accumulate in TMEM): measured error below a plain
 //     fp32 SGEMM's, which the 1e-4 image tolerance needs -- single-pass TF32 is 1000x worse;
-//   * epilogues (bias, ReLU, hi/lo split) are tcgen05.ld -> registers -> tcgen05.st, one thread per TMEM lane,
-//     two warps per lane quadrant splitting the columns;
+//   * epilogues (bias, ReLU, sign bits for the backward, hi/lo split) are tcgen05.ld -> registers -> tcgen05.st, one
+//     thread per TMEM lane, two warps per lane quadrant splitting the hidden columns;
+//   * the HexPlane gather runs BEFORE this kernel at full occupancy (deform_features_kernel, feat [N][F] stays in L2):
+//     inside a 1-CTA/SM persistent kernel four gather warps were latency-bound and slowed the epilogue warps;
 //   * the tile's 128 result rows stay in registers of their owner threads, which finish the Gaussian
 //     (activations, EWA projection, SH colour) exactly like the SIMT path (geom_finish.cuh).
 //
@@ -95,12 +97,14 @@ cudaError_t launch_tc_pack_weights(const G4DDeformParams& prm, float* blob, TcWe
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------------------
-// Warp roles (256 threads):
-//   M = warps 0-3 (thread m <-> TMEM lane m <-> Gaussian m of the tile): MMA issue (thread 0), epilogues, head outputs,
-//       activations + projection of the Gaussian, TMA weight streaming.
-//   G = warps 4-7 (thread 128+m <-> the same lane / Gaussian): HexPlane gathers of the NEXT tile (held in registers while
-//       the tensor cores chew on the current one), and the SH colour of the current tile.
-// Hand-offs use named barriers (ids 1-4, 256 threads) + tcgen05 fences; the M group syncs internally on id 5.
+// Thread groups (256 threads; thread 128+m and thread m both own TMEM lane m = Gaussian m of the tile):
+//   M = warps 4-7: MMA issue + TMA weight streaming (thread 128), hidden columns [64,128) of every epilogue, head outputs,
+//       activations + projection of the Gaussian.  (The hardware scheduler favours the higher warp ids of a sub-partition.)
+//   G = warps 0-3: stages the next tile's features into TMEM, hidden columns [0,64) of every epilogue (its partial layer-2
+//       sums of the small heads go to M through shared memory), and the SH colour of the current tile.
+// Hand-offs use named barriers (ids 1-4 and 6, 256 threads) + tcgen05 fences; the M group syncs internally on id 5.
+// Each MMA kind has its own mbarrier (layer 0 / layer 1 / layer-2 partials) so that a thread that only waits for some of
+// them can never fall a full phase behind.
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 

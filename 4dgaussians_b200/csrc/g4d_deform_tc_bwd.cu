@@ -3,13 +3,17 @@
 //  A  "dgrad":  tile of 128 Gaussians per pass (TMEM lanes).  Recomputes the forward activations with BF16x2 tcgen05
 //               MMAs (hi + lo parts, 3 products, fp32 accumulate: ~16 mantissa bits, measured gradient error 1.5e-5),
 //               forms dz per head in the epilogue (layer 2 is tiny: its dgrad is done in fp32 by the epilogue threads),
-//               accumulates d(a1) over the heads IN TMEM with one MMA chain per head, then d(feat) = dh W0 and hands it
-//               to the gather warps, which scatter into the HexPlane planes (vector RED) and produce d(xyz).
+//               accumulates d(a1) over the heads IN TMEM with one MMA chain per head, then d(feat) = dh W0 -> [N][F] fp32.
+//               Both 128-thread groups own half of the hidden columns of every epilogue.  The ReLU signs come from the
+//               bits the forward saved (G4D_RELU_BITS_WORDS), so this is the gradient of the forward that ran.
 //               Everything the weight gradients need is written ONCE as ready-to-use MMA operand images
 //               (8x8 bf16 core-matrix layout, tc_umma.cuh) so that kernel B is pure TMA + MMA.
+//               HexPlane gather (bwd_features_kernel, skipped when the forward's staging buffer was kept) and scatter
+//               (bwd_scatter_kernel: plane REDs, d(xyz), residual paths) run around it at full occupancy.
 //  B  "wgrad":  dW1_h = DZ_h^T A1, dW2_h^T = A2_h^T DOUT_h, db1_h = DZ_h^T 1, dW0 = DH^T FEAT, db0 = DH^T 1 as split-K
 //               tcgen05 GEMMs over the Gaussian index (both operands MN-major straight from the images), accumulators
-//               persistent in TMEM across the CTA's tiles, one atomic flush per CTA.
+//               persistent in TMEM across the CTA's tiles, one atomic flush per CTA; two half-tile smem stages pipeline
+//               the TMA loads against the MMAs.
 //
 // Replaces the autograd backward of scene/deformation.py:67-148 + scene/hexplane.py:73-106 (loss.backward(), train.py:219).
 // Compiled with the default FMA contraction (no index-producing math here).
