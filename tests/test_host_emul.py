@@ -67,3 +67,27 @@ def test_gaussian_backward_vs_oracle():
         err = (np.abs(got - ref) / denom).max()
         assert err < 5e-3, (nm, err)
         assert np.abs(ref).max() > 0
+
+
+def test_depth_ordered_emission_plus_tile_sort_equals_the_reference_key_sort():
+    """DESIGN §4 binning: stable-sorting the Gaussians by depth bits, emitting their (tile | depth) keys in that order and
+    stable-sorting the keys on the TILE bits only must reproduce, entry for entry, the reference's stable sort of the keys
+    emitted in Gaussian-index order on (tile, depth) -- including ties (equal depth bits keep Gaussian-index order)."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    n, tiles = 4000, 37
+    depth = rng.integers(0x3E4CCCCD, 0x3E4CCCCD + 60, size=n, dtype=np.uint64)          # few distinct values: many ties
+    touched = rng.integers(0, 6, size=n)
+    rects = [np.sort(rng.choice(tiles, size=k, replace=False)) for k in touched]         # tiles of Gaussian i, emission order
+    # reference: emit in index order, stable sort on the full 64-bit key
+    keys = np.concatenate([(t.astype(np.uint64) << np.uint64(32)) | depth[i] for i, t in enumerate(rects)])
+    ids = np.concatenate([np.full(len(t), i, dtype=np.uint32) for i, t in enumerate(rects)])
+    o = np.argsort(keys, kind="stable")
+    ref_keys, ref_ids = keys[o], ids[o]
+    # g4d: depth order first (invisible Gaussians last), emit in that order, stable sort on the tile bits alone
+    dkey = np.where(touched > 0, depth, np.uint64(0xFFFFFFFF))
+    perm = np.argsort(dkey, kind="stable")
+    keys2 = np.concatenate([(rects[i].astype(np.uint64) << np.uint64(32)) | depth[i] for i in perm])
+    ids2 = np.concatenate([np.full(len(rects[i]), i, dtype=np.uint32) for i in perm])
+    o2 = np.argsort(keys2 >> np.uint64(32), kind="stable")
+    assert np.array_equal(keys2[o2], ref_keys) and np.array_equal(ids2[o2], ref_ids)
