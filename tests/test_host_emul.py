@@ -91,3 +91,48 @@ def test_depth_ordered_emission_plus_tile_sort_equals_the_reference_key_sort():
     ids2 = np.concatenate([np.full(len(rects[i]), i, dtype=np.uint32) for i in perm])
     o2 = np.argsort(keys2 >> np.uint64(32), kind="stable")
     assert np.array_equal(keys2[o2], ref_keys) and np.array_equal(ids2[o2], ref_ids)
+
+
+def test_strip_cull_predicate_is_conservative():
+    """The exact-cull predicate of the blend kernels / G4D_OPT_TIGHT_CULL (g4d_raster.cu rect_contributes), restated in
+    float32 numpy: whenever it says 'cannot contribute', NO pixel centre of the rectangle reaches alpha >= 1/255."""
+    import numpy as np
+    f = np.float32
+    rng = np.random.default_rng(11)
+
+    def edge_min(a, b, c, fixed, lo, hi):
+        t = f(-b * fixed / c)
+        t = min(max(t, lo), hi)
+        return f(a * fixed * fixed + f(2) * b * fixed * t + c * t * t)
+
+    def rect_contributes(mx, my, A, B, C, op, x0, x1, y0, y1):
+        dx0, dx1, dy0, dy1 = f(mx - x1), f(mx - x0), f(my - y1), f(my - y0)
+        if dx0 <= 0 and dx1 >= 0 and dy0 <= 0 and dy1 >= 0:
+            q = f(0)
+        else:
+            q = min(edge_min(A, B, C, dx0, dy0, dy1), edge_min(A, B, C, dx1, dy0, dy1),
+                    edge_min(C, B, A, dy0, dx0, dx1), edge_min(C, B, A, dy1, dx0, dx1))
+            q = max(q, f(0))
+        return op * f(np.exp(f(-0.5) * q)) * f(1.0001) >= f(1.0 / 255.0)
+
+    culled = kept = 0
+    for _ in range(3000):
+        # random positive-definite conic, mean near a 16 x 4 strip
+        s1, s2, th = rng.uniform(0.8, 12.0), rng.uniform(0.8, 12.0), rng.uniform(0, np.pi)
+        R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        con = np.linalg.inv(R @ np.diag([s1 * s1, s2 * s2]) @ R.T)
+        A, B, C = f(con[0, 0]), f(con[0, 1]), f(con[1, 1])
+        op = f(rng.uniform(0.02, 0.99))
+        mx, my = f(rng.uniform(-30, 46)), f(rng.uniform(-30, 34))
+        x0, x1, y0, y1 = f(0), f(15), f(0), f(3)
+        xs, ys = np.meshgrid(np.arange(16, dtype=np.float32), np.arange(4, dtype=np.float32))
+        dx, dy = mx - xs, my - ys
+        power = f(-0.5) * (A * dx * dx + C * dy * dy) - B * dx * dy
+        alpha = np.minimum(f(0.99), op * np.exp(power))
+        reach = bool(((power <= 0) & (alpha >= f(1.0 / 255.0))).any())
+        if rect_contributes(mx, my, A, B, C, op, x0, x1, y0, y1):
+            kept += 1
+        else:
+            culled += 1
+            assert not reach, (mx, my, A, B, C, op)
+    assert culled > 300 and kept > 300      # the sample exercises both outcomes
