@@ -50,6 +50,23 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def _tensor_roofline(n, geom_ms):
+    """The geometry kernel is bound by the tensor pipe + its epilogues, not by HBM: report it against the measured dense
+    BF16 peak too.  Algorithmic FLOPs = 2 * (F*Wd + h*Wd^2 + Wd*sum(k)) per Gaussian = 187.1 kFLOP (dynerf net)."""
+    try:
+        j = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak, src = float(j["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    except Exception:
+        peak, src = 2250.0, "fallback (nominal dense bf16 2.25 PFLOP/s)"
+    flops = 2.0 * (32 * 128 + 5 * 128 * 128 + 128 * (3 + 3 + 4 + 1 + 48)) * n
+    ach = flops / (geom_ms * 1e-3) / 1e12 if geom_ms > 0 else 0.0
+    return {"bound": "tensor", "kernel": "deform_features + deform_tc_kernel (stage `geom`)", "achieved": ach, "peak": peak,
+            "unit": "TFLOP/s", "frac": ach / peak if peak else None, "peak_source": src, "algorithmic_flops": flops,
+            "kernel_ms": geom_ms,
+            "note": "fp32-accurate 3xTF32: every algorithmic MAC is 3 tensor-core MACs at the TF32 rate (half of BF16), so "
+                    "the ceiling of this scheme is peak/6; ncu: tensor pipe active 36 % of the kernel (profiles/r1e_ncu_full_C3.md)"}
+
+
 class ClockSampler:
     """SM clock / throttle reasons DURING the timed region.  In-process NVML (three light queries every 200 ms from a thread;
     ctypes drops the GIL during the calls); falls back to a low-rate `nvidia-smi -lms` subprocess when pynvml is unusable."""
@@ -332,6 +349,7 @@ def run_ours(args):
             "roofline_path": {"what": "whole fused forward, B_fwd of SURVEY 8d", "algorithmic_bytes": ab["total"],
                               "achieved": ab["total"] / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                               "frac": ab["total"] / (ms_per_step * 1e-3) / 1e9 / peak},
+            "roofline_tensor": _tensor_roofline(w["n"], fwd_stages.get("geom", 0.0)),
             "stage_ms": stages, "train_step": train, "wall_s_timed_region": t_wall,
             "step_ms": [round(x, 3) for x in step_ms],
             "exact_tile_cull": {"what": "opt-in G4D_OPT_TIGHT_CULL: (Gaussian, tile) pairs whose best-case alpha over the tile is "
