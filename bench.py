@@ -4,20 +4,26 @@
 
     python bench.py --gpus N --steps K --warmup W            # our arm (CUDA path through the public API)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU implementation of the path
+    python bench.py --workload C1|C2|C3|C4                   # other BASELINE.json configs (default C3, the metric's)
 
-A "step" is one pass of the hot path over one synthetic view: the fused deform + rasterize FORWARD of workload C3
-(`configs[3]`, the configuration the metric is quoted on; 300k Gaussians fit one GPU).  Views / timestamps are sharded
-over ranks with no data-path collective (weak scaling); the per-step NCCL gradient all-reduce only exists
-in the training step, reported in `train_step` (B=2 views fwd+bwd + flat-bucket all-reduce + fused Adam).
+A "step" is one pass of the hot path over one BATCH of synthetic views: `--views-per-step` (default 32) fused
+deform + rasterize FORWARDS of the workload, back to back -- so that `--steps 20` times >= 0.5 s of device work instead of
+20 ms.  Views / timestamps are sharded over ranks with no data-path collective (weak scaling); the per-step
+NCCL gradient all-reduce only exists in the training step, reported in `train_step` (B=2 views fwd+bwd + fused
+L1 loss + flat-bucket all-reduce + Adam).
 
-Timing: CUDA events around every step on the launching stream, W warm-up steps, an L2 flush (write of a 512 MiB buffer)
-between timed steps outside the event pairs, barrier + synchronize on both sides of the timed region, MAX over ranks.
+Timing: one CUDA-event pair per step on the launching stream, W warm-up steps (same code path and the same output
+bindings as the timed steps), an L2 flush (512 MiB write) between steps outside the event pairs -- inside a step every
+view moves ~0.3 GB (instance lists + images), more than the 126 MB L2, so consecutive views evict one another --
+barrier + synchronize on both sides of the timed region, MAX over ranks.
 `value` = inputs resident in HBM; `e2e` = the same steps through the public `render()` with the camera arriving from host
-memory and the rendered image copied to pinned host memory every step (reference render.py:59-60 semantics).
+memory and every rendered image copied to pinned host memory (double-buffered, on a copy stream, inside the step's event
+pair: reference render.py:59-60 semantics).
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import importlib
 import json
 import math
@@ -34,37 +40,79 @@ if ROOT not in sys.path:
 import numpy as np
 import torch
 
-METRIC = "render FPS @300k gauss 1352x1014 (fused deform+rasterize forward); train-step ms in `train_step`"
 UNIT = "frames/s"
-WORKLOAD = "C3"
+NETS = {   # C (channels), L (levels), Wd, heads (k outputs) per reference config
+    "dnerf": dict(C=32, L=2, Wd=64, heads=(3, 3, 4)),
+    "hypernerf": dict(C=16, L=3, Wd=128, heads=(3, 3, 4)),
+    "dynerf": dict(C=16, L=2, Wd=128, heads=(3, 3, 4, 1, 48)),
+}
+WORKLOAD_TEXT = {
+    "C1": "C1: D-NeRF bouncingballs shape, 70k Gaussians, 800x800, dnerf net (C=32,L=2,T=75,Wd=64,3 heads)",
+    "C2": "C2: HyperNeRF vrig-broom shape, 200k Gaussians, 536x960, hypernerf net (C=16,L=3,T=100,Wd=128,3 heads)",
+    "C3": "C3: 300k Gaussians, 1352x1014, dynerf net (C=16,L=2,T=150,Wd=128,5 heads), sh_degree 3, 300 timestamps, "
+          "views sharded over ranks",
+    "C4": "C4: stress, 2M Gaussians, 64 cams 1920x1080, dynerf net, views sharded over ranks",
+}
 
 
-def _peaks():
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.isfile(p):
-        try:
-            j = json.load(open(p))
-            return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        except Exception:
-            pass
+def metric_name(wl):
+    w = importlib.import_module("4dgaussians_b200.synth").WORKLOADS[wl]
+    return "render FPS @%dk gauss %dx%d (fused deform+rasterize forward); train-step ms in `train_step`" % (
+        w["n"] // 1000, w["width"], w["height"])
+
+
+def _peaks_json():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def _hbm_peak():
+    j = _peaks_json()
+    if "hbm_gbs" in j:
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def _tensor_roofline(n, geom_ms):
+def mlp_flops_per_gaussian(net):
+    c = NETS[net]
+    F, Wd, h = c["C"] * c["L"], c["Wd"], len(c["heads"])
+    return 2.0 * (F * Wd + h * Wd * Wd + Wd * sum(c["heads"]))
+
+
+def _tensor_roofline(net, n, geom_ms):
     """The geometry kernel is bound by the tensor pipe + its epilogues, not by HBM: report it against the measured dense
-    BF16 peak too.  Algorithmic FLOPs = 2 * (F*Wd + h*Wd^2 + Wd*sum(k)) per Gaussian = 187.1 kFLOP (dynerf net)."""
-    try:
-        j = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    BF16 peak too.  Algorithmic FLOPs = 2 * (F*Wd + h*Wd^2 + Wd*sum(k)) per Gaussian."""
+    j = _peaks_json()
+    if "bf16_tflops_sustained" in j:
         peak, src = float(j["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
-    except Exception:
+    else:
         peak, src = 2250.0, "fallback (nominal dense bf16 2.25 PFLOP/s)"
-    flops = 2.0 * (32 * 128 + 5 * 128 * 128 + 128 * (3 + 3 + 4 + 1 + 48)) * n
+    flops = mlp_flops_per_gaussian(net) * n
     ach = flops / (geom_ms * 1e-3) / 1e12 if geom_ms > 0 else 0.0
     return {"bound": "tensor", "kernel": "deform_features + deform_tc_kernel (stage `geom`)", "achieved": ach, "peak": peak,
             "unit": "TFLOP/s", "frac": ach / peak if peak else None, "peak_source": src, "algorithmic_flops": flops,
             "kernel_ms": geom_ms,
             "note": "fp32-accurate 3xTF32: every algorithmic MAC is 3 tensor-core MACs at the TF32 rate (half of BF16), so "
-                    "the ceiling of this scheme is peak/6; ncu: tensor pipe active 36 % of the kernel (profiles/r1e_ncu_full_C3.md)"}
+                    "the ceiling of this scheme is peak/6 (frac 0.167); net_width 64 (dnerf) runs the FP32 FFMA kernel"}
+
+
+def _blend_roofline(pairs, blend_ms, sm_count):
+    """Blend is FP32-ALU / MUFU bound: (pixel, instance) evaluations per second against the SM peaks.
+    pairs = sum over pixels of the index of the last instance the pixel had to look at (n_contrib) = the evaluations the
+    reference algorithm performs; 27 flop + 1 ex2 each (dx,dy; quadratic form; exp; alpha clamp/tests; T update; 4 FMA)."""
+    j = _peaks_json()
+    mhz = float(j.get("sm_max_mhz", 1965.0))
+    fp32 = sm_count * 128 * 2 * mhz * 1e6           # flop/s
+    mufu = sm_count * 16 * mhz * 1e6                # ex2/s
+    peak_pairs = min(fp32 / 27.0, mufu)
+    ach = pairs / (blend_ms * 1e-3) if blend_ms > 0 else 0.0
+    return {"bound": "fp32 alu / mufu", "kernel": "blend_forward_kernel", "achieved": ach / 1e9, "peak": peak_pairs / 1e9,
+            "unit": "G(pixel x instance)/s", "frac": ach / peak_pairs if peak_pairs else None, "pairs_per_view": pairs,
+            "kernel_ms": blend_ms, "fp32_bound_gpairs": fp32 / 27.0 / 1e9, "mufu_bound_gpairs": mufu / 1e9,
+            "note": "27 flop + 1 MUFU.EX2 per evaluated pair; peaks = %d SMs x 128 FP32 lanes x 2 / x 16 MUFU lanes at %.0f MHz"
+                    % (sm_count, mhz)}
 
 
 class ClockSampler:
@@ -148,10 +196,10 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
-def build_scene(device, seed=0):
+def build_scene(workload, seed=0):
     g4d = importlib.import_module("4dgaussians_b200")
     synth = importlib.import_module("4dgaussians_b200.synth")
-    w = synth.WORKLOADS[WORKLOAD]
+    w = synth.WORKLOADS[workload]
     scene = synth.make_scene(w["n"], seed=seed, scale_mean=w["scale_mean"])
     torch.manual_seed(seed)
     mod = g4d.deform_network(synth.hidden_args(w["net"]))
@@ -161,7 +209,7 @@ def build_scene(device, seed=0):
 
 
 def algorithmic_bytes(n, H, W, R, param_bytes):
-    """SURVEY §8d B_fwd per view and its per-stage split."""
+    """SURVEY 8d B_fwd per view and its per-stage split."""
     geom = n * 236 + n * 4 + param_bytes           # SoA read once + radii + planes/MLP read once
     binning = R * (8 + 4) * 2                      # one (key,id) record written then read
     blend = R * 44 + H * W * 16                    # per-instance fetch + colour/depth write
@@ -172,6 +220,13 @@ class Pipe:
     convert_SHs_python = False
     compute_cov3D_python = False
     debug = False
+
+
+def _max_over_ranks(dist, dev, x):
+    t = torch.tensor([x], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
 
 
 def run_ours(args):
@@ -191,21 +246,24 @@ def run_ours(args):
             os.environ.pop("NCCL_DEBUG")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
-    g4d, synth, w, scene, mod = build_scene(dev)
+    wl = args.workload
+    g4d, synth, w, scene, mod = build_scene(wl)
     lib = g4d._lib
     mod = mod.to(dev)
     pc = synth.SyntheticGaussianModel(scene, mod, device=dev, sh_degree=3, requires_grad=False)
-    K, Wm = args.steps, args.warmup
-    n_views = (K + Wm) * world
-    cams_all = synth.orbit_cameras(max(n_views, 8), w["width"], w["height"], radius=w["radius"], focal=w["focal"], timestamps=300)
-    my_cams = [cams_all[(i * world + rank) % len(cams_all)] for i in range(K + Wm)]
+    K, Wm, V = args.steps, args.warmup, args.views_per_step
+    ncams = 64 if wl == "C4" else 300
+    cams_all = synth.orbit_cameras(ncams, w["width"], w["height"], radius=w["radius"], focal=w["focal"], timestamps=300)
+
+    def cam_of(step, v):   # global view index -> this rank's camera (round robin over ranks)
+        return cams_all[((step * V + v) * world + rank) % len(cams_all)]
     bg = torch.tensor(w["bg"], dtype=torch.float32, device=dev)
     ws = lib.Workspace.get(local)
     ws.set_option(lib.OPT_STAGE_TIMING, 1)
-    ws.set_option(lib.OPT_SYNC_MODE, 0 if args.no_host_sync else 1)
+    ws.set_option(lib.OPT_SYNC_MODE, 1 if args.host_sync else 0)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     H, Wd = w["height"], w["width"]
-    rz = importlib.import_module("4dgaussians_b200.renderer")
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -214,36 +272,45 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     # ------------------------------------------------------------------ resident arm (`value`)
+    def resident_step(step):
+        out = None
+        for v in range(V):
+            out = g4d.render(cam_of(step, v), pc, Pipe, bg)      # same binding in warm-up and timed steps
+        return out
+
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    stage_acc, Rs, vis = {}, [], []
     sampler = ClockSampler(local)
     if rank == 0 and not os.environ.get("G4D_BENCH_NO_SAMPLER"):
         sampler.start()          # NVML initialisation / first queries happen during the warm-up, not in the timed region
-    import gc
     with torch.no_grad():
         for i in range(Wm):
-            g4d.render(my_cams[i], pc, Pipe, bg)
-        gc.collect(); gc.disable()     # a host hiccup shows up 1:1 in a ~1 ms step that synchronises on R once per frame
+            flush.fill_(i & 0xFF)
+            out = resident_step(i)
+        gc.collect(); gc.disable()     # a host hiccup shows up 1:1 in a ~1 ms view
         barrier()
-        # Ranks leave the collective barrier at different times and an idle B200 drops its clocks within milliseconds (measured:
-        # the 2nd step after an idle gap stalls 5-40 ms).  Two more untimed warm-up renders, then the synchronize that
-        # brackets the timed region -- after it the GPU is idle for microseconds only.
-        for i in range(2):
-            g4d.render(my_cams[i], pc, Pipe, bg)
+        # ranks leave the collective barrier at different times and an idle B200 drops its clocks within milliseconds:
+        # one more untimed step, then the synchronize that brackets the timed region
+        out = resident_step(Wm)
         torch.cuda.synchronize(dev)
         sampler.mark()
         t_wall0 = time.perf_counter()
         for i in range(K):
             flush.fill_(i & 0xFF)
             ev[i][0].record()
-            out = g4d.render(my_cams[Wm + i], pc, Pipe, bg)
+            out = resident_step(Wm + i)
             ev[i][1].record()
         barrier()
         t_wall = time.perf_counter() - t_wall0
         gc.enable()
-        # per-stage device times and instance counts: separate, untimed pass (the queries synchronise)
-        for i in range(min(K, 8)):
-            g4d.render(my_cams[Wm + i], pc, Pipe, bg)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = _max_over_ranks(dist, dev, sum(step_ms))
+    value = world * K * V / (total_ms / 1e3)
+
+    # ------------------------------------------------------------------ per-stage device times, R, blend work (untimed pass)
+    stage_acc, Rs, vis, pairs = {}, [], [], []
+    with torch.no_grad():
+        for i in range(min(V, 8)):
+            g4d.render(cam_of(Wm, i), pc, Pipe, bg)
             torch.cuda.synchronize(dev)
             fn_ctx = ws._free_contexts[-1] if ws._free_contexts else None
             if fn_ctx is not None:
@@ -251,117 +318,221 @@ def run_ours(args):
                     stage_acc[k_] = stage_acc.get(k_, 0.0) + v_
                 s_ = fn_ctx.stats()
                 Rs.append(int(s_.num_rendered)); vis.append(int(s_.num_visible))
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
-    value = world * K / (total_ms / 1e3)
+                if i < 2:
+                    pairs.append(float(fn_ctx.read("n_contrib").astype(np.float64).sum()))
 
     # ------------------------------------------------------------------ e2e arm: host camera in, image out to pinned host
-    pinned = torch.empty(3, H, Wd, dtype=torch.float32).pin_memory()
+    pinned = [torch.empty(3, H, Wd, dtype=torch.float32).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream(dev)
+    main_stream = torch.cuda.current_stream(dev)
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def e2e_step(step):
+        for v in range(V):
+            out = g4d.render(cam_of(step, v), pc, Pipe, bg)      # camera matrices are HOST tensors -> kernel params
+            img = out["render"]
+            rendered = torch.cuda.Event(); rendered.record(main_stream)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(rendered)
+                pinned[v & 1].copy_(img, non_blocking=True)      # (stream order: this buffer's previous copy has completed)
+                img.record_stream(copy_stream)
+                done[v & 1].record(copy_stream)
+        main_stream.wait_event(done[0]); main_stream.wait_event(done[1])   # the step ends when its last image is on the host
+
     with torch.no_grad():
+        e2e_step(0)
         barrier()
+        e2e_step(1)
+        torch.cuda.synchronize(dev)
         for i in range(K):
             flush.fill_(i & 0xFF)
             ev2[i][0].record()
-            out = g4d.render(my_cams[Wm + i], pc, Pipe, bg)          # camera matrices are HOST tensors -> kernel params
-            pinned.copy_(out["render"], non_blocking=True)
+            e2e_step(Wm + i)
             ev2[i][1].record()
         barrier()
-    e2e_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev2)], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * K / (float(e2e_ms.item()) / 1e3)
+    e2e_steps = [a.elapsed_time(b) for a, b in ev2]
+    e2e_ms = _max_over_ranks(dist, dev, sum(e2e_steps))
+    e2e_value = world * K * V / (e2e_ms / 1e3)
     cam_bytes = 4 * (16 + 16 + 3 + 3 + 4) + 16
 
-    # ------------------------------------------------------------------ opt-in exact-image tile culling (same pixels, fewer bins)
-    ws.set_option(lib.OPT_TIGHT_CULL, 1)
-    ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    with torch.no_grad():
-        for i in range(3):
-            g4d.render(my_cams[i], pc, Pipe, bg)
-        barrier()
-        for i in range(K):
-            flush.fill_(i & 0xFF)
-            ev3[i][0].record()
-            out = g4d.render(my_cams[Wm + i], pc, Pipe, bg)
-            ev3[i][1].record()
-        barrier()
-        fn_ctx = ws._free_contexts[-1] if ws._free_contexts else None
-        R_tight = int(fn_ctx.stats().num_rendered) if fn_ctx is not None else None
-    tight_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev3)], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(tight_ms, op=dist.ReduceOp.MAX)
-    tight_value = world * K / (float(tight_ms.item()) / 1e3)
-    train_tight = run_train_steps(g4d, synth, lib, w, scene, mod, dev, dist, world, rank, max(3, min(K, 10)), 5, flush)
-    ws.set_option(lib.OPT_TIGHT_CULL, 0)
+    # ------------------------------------------------------------------ frame 0 of this workload against the CPU oracle (untimed)
+    parity = None
+    if rank == 0 and not args.no_parity_check:
+        parity = parity_check(g4d, synth, wl, w, scene, mod, pc, cams_all[0], dev)
 
     # ------------------------------------------------------------------ training step (B=2 views, fwd+bwd, all-reduce, Adam)
-    train = run_train_steps(g4d, synth, lib, w, scene, mod, dev, dist, world, rank, max(3, min(K, 10)), 5, flush)
+    train = None
+    if not args.no_train:
+        train = run_train_steps(g4d, synth, lib, w, scene, mod, dev, dist, world, rank, max(3, min(K, 10)), 5, flush)
     clocks = sampler.stop() if rank == 0 else None     # sampled from the start of the timed region to the end of the train steps
 
+    eager = None
+    if rank == 0 and world == 1 and not args.no_eager_baseline:
+        eager = gpu_eager_baseline(g4d, synth, w, scene, mod, dev)
+
     if rank == 0:
-        peak, peak_src = _peaks()
+        peak, peak_src = _hbm_peak()
         R = float(np.mean(Rs)) if Rs else 0.0
         pbytes = sum(p.numel() * 4 for p in mod.flat_parameters())
         ab = algorithmic_bytes(w["n"], H, Wd, R, pbytes)
         stages = {k_: v_ / max(1, len(Rs)) for k_, v_ in stage_acc.items()}
         fwd_stages = {k_: stages.get(k_, 0.0) for k_ in ("prep", "geom", "scan", "emit", "sort", "ranges", "blend")}
-        dom = max(("geom", "blend", "sort"), key=lambda k_: fwd_stages.get(k_, 0.0))
-        dom_bytes = {"geom": ab["geom"], "blend": ab["blend"], "sort": ab["binning"]}[dom]
-        dom_ms = fwd_stages[dom]
+        bin_ms = sum(fwd_stages[k_] for k_ in ("scan", "emit", "sort", "ranges"))
+        dom = max(("geom", "blend", "binning"), key=lambda k_: bin_ms if k_ == "binning" else fwd_stages.get(k_, 0.0))
+        dom_bytes = ab[dom]
+        dom_ms = bin_ms if dom == "binning" else fwd_stages[dom]
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         traffic, traffic_src = None, None
         try:     # dram bytes per launch of the dominant kernel from the committed ncu --set full capture of this workload
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1e_traffic.json")))
-            bpl = tj["bytes_per_launch"]
-            keys = {"geom": ["deform_tc_kernel<1, 16, 2, 1>", "deform_features_kernel<4>"], "blend": ["blend_forward_kernel<2>"], "sort": []}[dom]
-            if keys and all(k_ in bpl for k_ in keys):
-                traffic, traffic_src = float(sum(bpl[k_] for k_ in keys)), tj["source"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tj.get("workload", "C3") == wl and dom in tj["per_stage"]:
+                traffic, traffic_src = float(tj["per_stage"][dom]), tj["source"]
         except Exception:
             pass
-        ms_per_step = total_ms / K
+        ms_per_view = total_ms / (K * V)
+        srt = sorted(step_ms)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": metric_name(wl), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C3: 300k Gaussians, 1352x1014, dynerf net (C=16,L=2,T=150,Wd=128,5 heads), sh_degree 3, "
-                                   "300 timestamps, views sharded over ranks", "n_gaussians": w["n"], "width": Wd, "height": H,
+            "config": {"workload": WORKLOAD_TEXT[wl], "views_per_step": V, "n_gaussians": w["n"], "width": Wd, "height": H,
                        "focal_px": w["focal"], "orbit_radius": w["radius"], "scale_mean": w["scale_mean"],
                        "tile_instances_R": R, "visible_gaussians": float(np.mean(vis)) if vis else None,
-                       "l2": "flushed between timed steps (512 MiB write, outside the event pairs)",
-                       "binning": "capacity-bounded, no host sync (overflow-checked)" if args.no_host_sync else "host sync on R",
-                       "mlp": "tcgen05 3xTF32 forward (fp32-accurate), BF16x2 tcgen05 backward",
+                       "l2": "flushed between timed steps (512 MiB write, outside the event pairs); inside a step each view "
+                             "moves ~%.2f GB > 126 MB L2" % (ab["total"] / 1e9),
+                       "binning": "host sync on R (exact sizing)" if args.host_sync else
+                                  "device-side R, capacity-bounded, no host sync (overflow-checked)",
+                       "mlp": "tcgen05 3xTF32 forward (fp32-accurate), BF16x2 tcgen05 backward" if NETS[w["net"]]["Wd"] == 128
+                              else "FP32 FFMA (net_width 64)",
                        "parallelism": "scene replicated, views sharded (dp%d)" % world},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cam_bytes, "d2h_bytes_per_step": 3 * H * Wd * 4,
-                    "how": "public render() per frame, camera from host memory, image copied to pinned host memory on the render "
-                           "stream inside every step's event pair"},
-            "gpu_launches": 8 * K,
-            "gpu_launches_note": "own kernels per step: pack_camera, collapse_time_rows, deform_features, deform_tc_kernel(fused), "
-                                 "depth_keys, emit_keys, tile_ranges, blend_forward; plus CUB scan/sort library launches",
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": {"geom": "deform_tc_kernel<1,16,2> (fused deform+activate+project, tcgen05)",
-                                                    "blend": "blend_forward_kernel", "sort": "cub::DeviceRadixSort"}[dom],
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes": dom_bytes, "kernel_ms": dom_ms},
-            "roofline_path": {"what": "whole fused forward, B_fwd of SURVEY 8d", "algorithmic_bytes": ab["total"],
-                              "achieved": ab["total"] / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                              "frac": ab["total"] / (ms_per_step * 1e-3) / 1e9 / peak},
-            "roofline_tensor": _tensor_roofline(w["n"], fwd_stages.get("geom", 0.0)),
-            "stage_ms": stages, "train_step": train, "wall_s_timed_region": t_wall,
+            "ms_per_view": ms_per_view,
+            "step_ms_stats": {"mean": float(np.mean(step_ms)), "median": float(np.median(step_ms)), "min": srt[0], "max": srt[-1]},
             "step_ms": [round(x, 3) for x in step_ms],
-            "exact_tile_cull": {"what": "opt-in G4D_OPT_TIGHT_CULL: (Gaussian, tile) pairs whose best-case alpha over the tile is "
-                                        "< 1/255 are not binned; pixels bit-identical (tests), bins no longer the reference's",
-                                "value": tight_value, "unit": UNIT, "tile_instances_R_last_view": R_tight,
-                                "train_step_ms": train_tight["ms_per_step"]},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cam_bytes * V, "d2h_bytes_per_step": 3 * H * Wd * 4 * V,
+                    "step_ms_median": float(np.median(e2e_steps)),
+                    "how": "public render() per view, camera from host memory, every image copied to pinned host memory "
+                           "(double-buffered, copy stream) inside the step's event pair; the step ends when its last image "
+                           "has landed"},
+            "gpu_launches": launches_per_view(w["net"]) * K * V,
+            "gpu_launches_note": "own kernels per view (fused forward): " + ", ".join(LAUNCH_LIST[0 if NETS[w["net"]]["Wd"] == 128 else 1]),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": {"geom": "deform_features + deform_tc_kernel (fused deform+activate+project, tcgen05)"
+                                                    if NETS[w["net"]]["Wd"] == 128 else "deform_kernel (FFMA)",
+                                                    "blend": "blend_forward_kernel", "binning": "bin_sort + bin_place"}[dom],
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes": dom_bytes,
+                         "kernel_ms": dom_ms},
+            "roofline_path": {"what": "whole fused forward, B_fwd of SURVEY 8d", "algorithmic_bytes": ab["total"],
+                              "achieved": ab["total"] / (ms_per_view * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": ab["total"] / (ms_per_view * 1e-3) / 1e9 / peak},
+            "roofline_tensor": _tensor_roofline(w["net"], w["n"], fwd_stages.get("geom", 0.0)),
+            "roofline_blend": _blend_roofline(float(np.mean(pairs)) if pairs else 0.0, fwd_stages.get("blend", 0.0), sm_count),
+            "stage_ms": stages, "binning_ms": bin_ms, "train_step": train, "wall_s_timed_region": t_wall,
+            "parity_check": parity, "gpu_eager_baseline": eager,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference_arm(steps=1, warmup=1, quiet=True)["cpu_baseline"]
+            line["cpu_baseline"] = cpu_reference_arm(wl, steps=2, warmup=1)["cpu_baseline"]
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+LAUNCH_LIST = (["pack_camera", "collapse_time_rows", "deform_features", "deform_tc_kernel", "bin_sort (cooperative)",
+                "bin_place", "blend_forward"],
+               ["pack_camera", "collapse_time_rows", "deform_kernel", "bin_sort (cooperative)", "bin_place", "blend_forward"])
+
+
+def launches_per_view(net):
+    return len(LAUNCH_LIST[0 if NETS[net]["Wd"] == 128 else 1])
+
+
+def parity_check(g4d, synth, wl, w, scene, mod, pc, cam, dev):
+    """Frame 0 of the benched workload, outside every timed region: the CUDA path against the CPU oracle (deformation
+    restatement pinned to the reference module + C rasterizer port).  oracle/ is the checker here, never the thing timed."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from util_scene import oracle_params_from_module, oracle_render
+        t0 = time.perf_counter()
+        bg = torch.tensor(w["bg"], dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            out = g4d.render(cam, pc, Pipe, bg)
+            cfg, prm = oracle_params_from_module(mod)
+            for t_ in prm.leaves():
+                t_.requires_grad_(False)
+            color, depth, radii, _, _ = oracle_render(cfg, prm, scene, cam, cam.time, w["bg"], sh_degree=3)
+        err = (out["render"].cpu() - color).abs()
+        derr = (out["depth"].cpu() - depth).abs()
+        return {"frame": 0, "against": "oracle (CPU)", "image_linf": float(err.max()), "image_median_err": float(err.median()),
+                "frac_pixels_gt_1e-4": float((err > 1e-4).float().mean()), "depth_linf": float(derr.max()),
+                "radii_mismatch_frac": float((out["radii"].cpu() != radii).float().mean()),
+                "ok": bool(float((err > 1e-4).float().mean()) <= 1e-3 and float(err.max()) <= 1e-2),
+                "seconds": time.perf_counter() - t0}
+    except Exception as e:       # the checker must never take the measurement down
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
+def gpu_eager_baseline(g4d, synth, w, scene, mod, dev):
+    """what the fused kernel replaces in train.py -- the reference's own deform_network module running
+    eager on this GPU (ATen grid_sample + cuBLAS SGEMM launches), CUDA events, same N / weights / inputs.  The reference
+    rasterizer cannot run here (its source is absent), so this covers the deformation half only; our deform-only entry
+    point (drop-in deform_network.forward, MODE 0) is timed beside it on the same tensors."""
+    try:
+        from oracle import deform_ref as dr
+        from oracle.ref_loader import reference_available, load_reference_deform_network, reference_origin
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from util_scene import oracle_params_from_module
+        if not reference_available():
+            return {"unavailable": "reference module not present (oracle/_ref not materialised)"}
+        cfg, prm = oracle_params_from_module(mod)
+        ref = load_reference_deform_network(cfg)
+        sd = ref.state_dict(); sd.update(dr.params_to_state_dict(prm)); ref.load_state_dict(sd)
+        ref = ref.to(dev)
+        n = w["n"]
+        ins = [scene[k].to(dev) for k in ("xyz", "scaling", "rotation", "opacity")]
+        shs = torch.cat([scene["features_dc"], scene["features_rest"]], dim=1).to(dev)
+        tt = torch.tensor(0.37, device=dev).repeat(n, 1)
+
+        def timeit(fn, iters=10, warm=3):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize(dev)
+            evs = []
+            for _ in range(iters):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record(); evs.append((a, b))
+            torch.cuda.synchronize(dev)
+            return float(np.median([a.elapsed_time(b) for a, b in evs]))
+
+        def ref_fwd():
+            with torch.no_grad():
+                return ref(*ins, shs, tt)
+
+        def our_fwd():
+            with torch.no_grad():
+                return mod(*ins, shs, tt)
+
+        leaves = [x.clone().requires_grad_(True) for x in ins + [shs]]
+
+        def ref_fwdbwd():
+            outs = ref(*leaves, tt)
+            sum(o.sum() for o in outs).backward()
+
+        def our_fwdbwd():
+            outs = mod(*leaves, tt)
+            sum(o.sum() for o in outs).backward()
+        with torch.no_grad():
+            err = max(float((a - b).abs().max()) for a, b in zip(ref_fwd(), our_fwd()))
+        res = {"what": "reference scene.deformation.deform_network eager on this GPU (deformation half only)",
+               "module_from": reference_origin(), "n": n,
+               "reference_eager_fwd_ms": timeit(ref_fwd), "g4d_deform_fwd_ms": timeit(our_fwd),
+               "reference_eager_fwd_bwd_ms": timeit(ref_fwdbwd, iters=5, warm=2), "g4d_deform_fwd_bwd_ms": timeit(our_fwdbwd, iters=5, warm=2),
+               "max_abs_output_diff": err}
+        res["fwd_speedup"] = res["reference_eager_fwd_ms"] / res["g4d_deform_fwd_ms"]
+        res["fwd_bwd_speedup"] = res["reference_eager_fwd_bwd_ms"] / res["g4d_deform_fwd_bwd_ms"]
+        return res
+    except Exception as e:
+        return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
 def run_train_steps(g4d, synth, lib, w, scene, mod, dev, dist, world, rank, steps, warmup, flush):
@@ -398,48 +569,47 @@ def run_train_steps(g4d, synth, lib, w, scene, mod, dev, dist, world, rank, step
         if it >= warmup:
             evs.append((a, b))
     torch.cuda.synchronize(dev)
-    ms = torch.tensor([sum(x.elapsed_time(y) for x, y in evs) / len(evs)], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = _max_over_ranks(dist, dev, sum(x.elapsed_time(y) for x, y in evs) / len(evs))
     ctx = lib.Workspace.get(dev.index)._free_contexts
     st = ctx[-1].stage_times() if ctx else {}
-    return {"ms_per_step": float(ms.item()), "step_ms": [round(x.elapsed_time(y), 3) for x, y in evs],
+    mod.fused_grad_accumulation = False
+    for p in params:
+        p.grad = None
+    return {"ms_per_step": ms, "step_ms": [round(x.elapsed_time(y), 3) for x, y in evs],
             "views_per_step_per_gpu": B, "global_batch": B * world,
+            "arithmetic": "forward MLP 3xTF32 (fp32-accurate); backward MLP BF16 hi+lo, 3 products (~16 mantissa bits) vs the "
+                          "reference's fp32 SGEMM; everything else fp32",
             "includes": "2x fused fwd+bwd (network gradients accumulated straight into the flat bucket), L1 loss, one flat-bucket all-reduce (%d floats), fused Adam" % bucket.numel,
             "last_view_stage_ms": st}
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_reference_arm(steps: int, warmup: int, quiet: bool = False):
-    """The reference's CPU implementation of the path on the host cores: deformation = the reference's own PyTorch module
-    when /root/reference is present (build container), else the oracle port; rasterizer = oracle C port with OpenMP
-    (the reference rasterizer's source is absent -> kind 'port').  One step = one full C3 view."""
+def cpu_reference_arm(workload: str, steps: int, warmup: int):
+    """The reference's CPU implementation of the path on the host cores: deformation = the reference's OWN PyTorch module
+    (imported from /root/reference in the build container, from the unmodified copies in oracle/_ref on the GPU box);
+    rasterizer = oracle C port with OpenMP (the reference rasterizer's source is absent).  One step = one full view of
+    the workload; the torch thread count is the best of a small sweep (reported)."""
     from oracle import deform_ref as dr
     from oracle import raster_ref as rr
-    from oracle.ref_loader import reference_available, load_reference_deform_network
-    g4d, synth, w, scene, mod = build_scene("cpu")
+    from oracle.ref_loader import reference_available, load_reference_deform_network, reference_origin
+    g4d, synth, w, scene, mod = build_scene(workload)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from util_scene import cam_tuple, oracle_params_from_module
     cores = os.cpu_count() or 1
-    torch.set_num_threads(min(cores, 32))     # the element-wise CPU kernels stop scaling (and start thrashing) beyond that
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     cfg, prm = oracle_params_from_module(mod)
     for t_ in prm.leaves():
         t_.requires_grad_(False)
-    kind = "port"
-    ref_net = None
+    kind, origin, ref_net = "port", "oracle/deform_ref.py (restatement)", None
     if reference_available():
         ref_net = load_reference_deform_network(cfg)
         sd = ref_net.state_dict(); sd.update(dr.params_to_state_dict(prm)); ref_net.load_state_dict(sd)
-        kind = "reference(deform)+port(rasterizer)"
+        kind, origin = "reference(deform)+port(rasterizer)", reference_origin()
     cams = synth.orbit_cameras(max(8, steps + warmup), w["width"], w["height"], radius=w["radius"], focal=w["focal"], timestamps=300)
     shs = torch.cat([scene["features_dc"], scene["features_rest"]], dim=1)
     n = w["n"]
-    times, t_def, t_ras = [], [], []
-    rr.lib()
-    for i in range(steps + warmup):
-        cam = cams[i % len(cams)]
-        t0 = time.perf_counter()
+
+    def deform(cam):
         with torch.no_grad():
             if ref_net is not None:
                 pts, sc, rot, op, sh = ref_net(scene["xyz"], scene["scaling"], scene["rotation"], scene["opacity"], shs,
@@ -448,6 +618,21 @@ def cpu_reference_arm(steps: int, warmup: int, quiet: bool = False):
                 pts, sc, rot, op, sh = dr.deform_forward(cfg, prm, scene["xyz"], scene["scaling"], scene["rotation"],
                                                          scene["opacity"], shs, cam.time)
             s, r, o = dr.activate(sc, rot, op)
+        return pts, s, r, o, sh
+    # thread sweep for the PyTorch-CPU deformation (element-wise ATen kernels stop scaling well before 128 threads)
+    sweep = {}
+    for th in sorted({min(cores, x) for x in (8, 16, 32, 64, cores)}):
+        torch.set_num_threads(th)
+        deform(cams[0])
+        t0 = time.perf_counter(); deform(cams[0]); sweep[th] = time.perf_counter() - t0
+    best = min(sweep, key=sweep.get)
+    torch.set_num_threads(best)
+    times, t_def, t_ras = [], [], []
+    rr.lib()
+    for i in range(steps + warmup):
+        cam = cams[i % len(cams)]
+        t0 = time.perf_counter()
+        pts, s, r, o, sh = deform(cam)
         t1 = time.perf_counter()
         rc, _ = cam_tuple(cam, w["bg"], sh_degree=3)
         rr.rasterize_forward(rc, pts.numpy(), s.numpy(), r.numpy(), o.numpy(), sh.numpy())
@@ -456,12 +641,14 @@ def cpu_reference_arm(steps: int, warmup: int, quiet: bool = False):
             times.append(dt); t_def.append(t1 - t0); t_ras.append(dt - (t1 - t0))
     ms = 1e3 * float(np.mean(times))
     fps = 1e3 / ms
-    cb = {"value": fps, "unit": UNIT, "cores": cores, "kind": kind,
-          "sample": "%d full C3 view(s) (300k Gaussians, 1352x1014): PyTorch-CPU deformation (%.2f s/view) + OpenMP C rasterizer "
-                    "oracle (%.2f s/view), forward" % (len(times), float(np.mean(t_def)), float(np.mean(t_ras)))}
-    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": "C3: 300k Gaussians, 1352x1014, dynerf net, host CPU, %d threads" % cores},
+    cb = {"value": fps, "unit": UNIT, "cores": cores, "kind": kind, "deform_module_from": origin,
+          "torch_threads": best, "torch_thread_sweep_s_per_view": {str(k): round(v, 3) for k, v in sweep.items()},
+          "sample": "%d full %s view(s) (%dk Gaussians, %dx%d): PyTorch-CPU deformation (%.2f s/view, %d threads) + OpenMP C "
+                    "rasterizer port (%.2f s/view, %d threads), forward" % (len(times), workload, n // 1000, w["width"], w["height"],
+                                                                            float(np.mean(t_def)), best, float(np.mean(t_ras)), cores)}
+    line = {"impl": "reference", "metric": metric_name(workload), "value": fps, "unit": UNIT, "n_gpus": 1, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD_TEXT[workload], "views_per_step": 1, "host": "CPU, %d cores" % cores},
             "cpu_baseline": cb, "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     return line
@@ -471,8 +658,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = min(args.steps, 20)
-    line = cpu_reference_arm(steps=steps, warmup=min(args.warmup, 3))
+    steps = min(args.steps, 8)          # one step = one full view (~1-2 s of CPU work): bounded sample
+    line = cpu_reference_arm(args.workload, steps=steps, warmup=min(args.warmup, 2))
     line["n_gpus"] = args.gpus
     line["steps"] = steps
     print(json.dumps(line))
@@ -482,13 +669,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="g4d", choices=["g4d", "reference"])
+    ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4"])
+    ap.add_argument("--views-per-step", dest="views_per_step", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-host-sync", dest="no_host_sync", action="store_true",
-                    help="capacity-bounded binning without the per-forward host round trip (default: exact sizing with one "
-                         "host sync per forward, the reference's behaviour -- measured faster at this scale because the "
-                         "padded sort costs more than the bubble it removes)")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--host-sync", dest="host_sync", action="store_true",
+                    help="size the instance buffer exactly with one host read of R per forward (the reference's behaviour) "
+                         "instead of the default capacity-bounded device-side binning")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -1,6 +1,7 @@
 """Import the REFERENCE's own ``scene.deformation.deform_network`` on CPU (this container only).
 
-TEST INFRASTRUCTURE ONLY.  /root/reference does not exist on the GPU box; callers must check
+TEST / BASELINE INFRASTRUCTURE ONLY.  /root/reference does not exist on the GPU box: there the unmodified copies that
+``oracle/make_ref.py`` put into ``oracle/_ref/`` at build() time are imported instead; callers must check
 ``reference_available()`` first.  Used by ``oracle/make_golden_deform.py`` (golden vectors), by the
 ``not gpu`` tests that pin ``oracle/deform_ref.py``, and by ``bench.py --impl reference`` when present.
 
@@ -17,11 +18,19 @@ import sys
 import types
 from argparse import Namespace
 
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ROOT = os.environ.get("G4D_REFERENCE_ROOT", "/root/reference")
+if not os.path.isfile(os.path.join(REF_ROOT, "scene", "deformation.py")):
+    # GPU box: the unmodified copies made by oracle/make_ref.py at build() time (git-ignored, shipped with the snapshot)
+    REF_ROOT = os.path.join(_HERE, "_ref")
 
 
 def reference_available() -> bool:
     return os.path.isfile(os.path.join(REF_ROOT, "scene", "deformation.py"))
+
+
+def reference_origin() -> str:
+    return "oracle/_ref (copied from /root/reference at build time)" if REF_ROOT.endswith("_ref") else REF_ROOT
 
 
 def _install_shims():
