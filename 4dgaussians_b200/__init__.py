@@ -11,5 +11,6 @@ from . import _lib  # noqa: F401
 from .deformation import deform_network  # noqa: F401
 from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer  # noqa: F401
 from .renderer import render  # noqa: F401
+from . import losses  # noqa: F401
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "deform_network", "render"]

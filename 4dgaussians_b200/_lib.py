@@ -22,18 +22,19 @@ OPT_SYNC_MODE, OPT_INSTANCE_CAPACITY, OPT_TIGHT_CULL, OPT_STAGE_TIMING, OPT_TENS
 STAGES = ("prep", "geom", "scan", "emit", "sort", "ranges", "blend", "blend_bwd", "geom_bwd", "deform_bwd")
 
 BUF = dict(depth=1, rect=2, tiles_touched=3, xy=4, conic_opacity=5, rgb=6, sorted_keys=7, sorted_ids=8, ranges=9,
-           final_T=10, n_contrib=11, clamped=12, deformed=13)
+           final_T=10, n_contrib=11, clamped=12, deformed=13, deformed_shs=14)
 
 # every symbol include/g4d.h declares (tests/test_abi.py checks the .so exports all of them)
 ABI_SYMBOLS = [
     "g4d_abi_version", "g4d_last_error", "g4d_workspace_create", "g4d_workspace_destroy", "g4d_context_create",
     "g4d_context_destroy", "g4d_context_stats", "g4d_deform_forward", "g4d_deform_backward", "g4d_rasterize_forward",
     "g4d_rasterize_backward", "g4d_render_forward", "g4d_render_backward", "g4d_workspace_set_option", "g4d_context_read",
-    "g4d_context_stage_times", "g4d_debug_umma", "g4d_debug_tc_cycles",
+    "g4d_context_stage_times", "g4d_debug_tc_cycles", "g4d_l1_loss", "g4d_l1_loss_backward", "g4d_ssim", "g4d_ssim_backward",
+    "g4d_plane_regulation",
 ]
 
 fp = C.c_void_p   # device pointers travel as integers
-ABI_VERSION = 2
+ABI_VERSION = 3
 CAM_DEBUG, CAM_NO_GRAD = 1, 2      # G4DCamera.debug bits
 
 
@@ -110,7 +111,6 @@ def load():
         lib.g4d_context_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
         lib.g4d_context_read.restype = C.c_int64
         lib.g4d_context_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
-        lib.g4d_debug_umma.argtypes = [C.c_void_p, C.POINTER(C.c_int), fp, fp, fp, C.c_void_p]
         lib.g4d_debug_tc_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         lib.g4d_deform_forward.argtypes = [C.c_void_p, C.POINTER(DeformParams), C.c_int64] + [fp] * 5 + [C.c_float] + \
             [fp] * 6 + [C.c_void_p]
@@ -122,10 +122,28 @@ def load():
                                            fp, fp, fp, C.c_void_p]
         lib.g4d_render_backward.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(DeformParams), C.POINTER(DeformGrads),
                                             C.POINTER(Gaussians), fp, C.POINTER(GaussianGrads), C.c_void_p]
+        lib.g4d_l1_loss.argtypes = [C.c_void_p, fp, fp, C.c_int64, C.c_float, fp, C.c_void_p]
+        lib.g4d_l1_loss_backward.argtypes = [C.c_void_p, fp, fp, C.c_int64, C.c_float, fp, fp, C.c_void_p]
+        lib.g4d_ssim.argtypes = [C.c_void_p, fp, fp, C.c_int32, C.c_int32, C.c_int32, C.c_float, fp, fp, C.c_void_p]
+        lib.g4d_ssim_backward.argtypes = [C.c_void_p, fp, fp, C.c_int32, C.c_int32, C.c_int32, C.c_float, fp, fp, fp, C.c_void_p]
+        lib.g4d_plane_regulation.argtypes = [C.c_void_p, C.POINTER(DeformParams), C.POINTER(DeformGrads), C.c_float, C.c_float,
+                                             C.c_float, fp, fp, C.c_void_p]
         if lib.g4d_abi_version() != ABI_VERSION:
             raise G4DError("libg4d.so ABI version mismatch")
         _lib = lib
         return lib
+
+
+SELFTEST_LIB_PATH = os.path.join(HERE, "libg4d_selftest.so")
+
+
+def load_selftest():
+    """The tcgen05 building-block self test lives in its own tiny library (tests / tools only; not in libg4d.so)."""
+    if not os.path.isfile(SELFTEST_LIB_PATH):
+        raise G4DError("libg4d_selftest.so is not built (run __graft_entry__.build())")
+    lib = C.CDLL(SELFTEST_LIB_PATH)
+    lib.g4d_selftest_umma.argtypes = [C.POINTER(C.c_int), fp, fp, fp, C.c_void_p]
+    return lib
 
 
 def check(rc: int, what: str = "g4d"):
@@ -205,7 +223,7 @@ class Context:
             "xy": (np.float32, (-1, 2)), "conic_opacity": (np.float32, (-1, 4)), "rgb": (np.float32, (-1, 3)),
             "sorted_keys": (np.uint64, (-1,)), "sorted_ids": (np.uint32, (-1,)), "ranges": (np.uint32, (-1, 2)),
             "final_T": (np.float32, (-1,)), "n_contrib": (np.uint32, (-1,)), "clamped": (np.uint8, (-1, 3)),
-            "deformed": (np.float32, (-1, 11))}[name]
+            "deformed": (np.float32, (-1, 11)), "deformed_shs": (np.float32, (-1, 16, 3))}[name]
         return raw.view(dt).reshape(shape)
 
     def __del__(self):

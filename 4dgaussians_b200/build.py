@@ -1,8 +1,9 @@
 """Build recipe for libg4d.so (hand-written sm_100a kernels behind the C-ABI of include/g4d.h).
 
 In-tree build with plain nvcc (no torch dependency): the .so travels to the GPU box with the snapshot.
-``g4d_geom.cu`` is compiled with -fmad=false (bit-exact index stages, see its header); the other
-translation units use the default FMA contraction.
+``g4d_geom.cu`` and ``g4d_deform_tc.cu`` -- the two translation units that contain the projection maths -- are compiled
+with -fmad=false (bit-exact index stages, see g4d_math.cuh); the others use the default FMA contraction.  The tcgen05
+building-block self test (``g4d_tc_selftest.cu``) goes into its own ``libg4d_selftest.so`` (tests / tools only).
 """
 from __future__ import annotations
 
@@ -15,6 +16,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libg4d.so")
+SELFTEST_OUT = os.path.join(HERE, "libg4d_selftest.so")     # tcgen05 building-block self test: tests / tools only
 OBJ = os.path.join(HERE, "build")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -23,9 +25,10 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 UNITS = {
     "g4d_geom.cu": ["-fmad=false"],
     "g4d_raster.cu": [],
+    "g4d_bin.cu": [],
+    "g4d_loss.cu": [],
     "g4d_backward.cu": [],
     "g4d_api.cu": [],
-    "g4d_tc_selftest.cu": [],
     "g4d_deform_tc.cu": ["-fmad=false"],
     "g4d_deform_tc_bwd.cu": [],
 }
@@ -47,7 +50,7 @@ def _sources_mtime() -> float:
 
 
 def needs_build() -> bool:
-    return not os.path.isfile(OUT) or os.path.getmtime(OUT) < _sources_mtime()
+    return not os.path.isfile(OUT) or not os.path.isfile(SELFTEST_OUT) or os.path.getmtime(OUT) < _sources_mtime()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -68,11 +71,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return obj
 
     with ThreadPoolExecutor(max_workers=4) as ex:
-        objs = list(ex.map(compile_one, UNITS.items()))
-    cmd = [nvcc] + ARCH + ["-shared", "-o", OUT] + objs + ["-lcudart"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+        objs = list(ex.map(compile_one, list(UNITS.items()) + [("g4d_tc_selftest.cu", [])]))
+    selftest_obj = objs.pop()
+    for out, oo in ((OUT, objs), (SELFTEST_OUT, [selftest_obj])):
+        cmd = [nvcc] + ARCH + ["-shared", "-o", out] + oo + ["-lcudart"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     with open(os.path.join(OBJ, "ptxas.log"), "w") as f:
         for k, v in logs.items():
             f.write("==== %s ====\n%s\n" % (k, v))

@@ -75,18 +75,18 @@ struct G4DWorkspace {
     float* w0t = nullptr;
     float* w1t[G4D_NUM_HEADS] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     DevBuf trow;        // time rows for the context-free deform entry points
-    DevBuf temp;        // CUB temp storage
     DevBuf scratch;     // misc per-call scratch (deform backward)
     uint32_t* h_pinned = nullptr;
 };
 
 struct G4DContext {
     G4DWorkspace* ws = nullptr;
-    DevBuf cam, geom, bin, img, fused, gscratch, gdeform, trow, relu, feat;
+    DevBuf cam, geom, bin, binaux, img, fused, gscratch, gdeform, trow, relu, feat;
     bool relu_saved = false;
     int64_t n = 0;
     int H = 0, W = 0, grid_x = 0, grid_y = 0;
     int64_t R = 0, capacity = 0;
+    bool learned = false;             // R of an earlier exact forward is known (no-sync mode needs a learnt capacity)
     bool has_forward = false, is_fused = false, fused_sh = false, deformed = false;
     GeomBuffers g{};
     BinBuffers b{};
@@ -130,13 +130,13 @@ int ensure_geom(G4DContext* c, int64_t n) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
     const size_t o0 = take(N * 16), o1 = take(N * 16), o2 = take(N * 8), o3 = take(N * 4), o4 = take(N * 8), o5 = take(N * 4),
-                 o6 = take(N * 4), o7 = take(N), o8 = take(N * 4), o9 = take(N * 16);
+                 o7 = take(N), o8 = take(N * 4);
     G4D_CUDA(c->geom.ensure(off));
     char* base = c->geom.as<char>();
     c->g.rec0 = (float4*)(base + o0); c->g.rec1 = (float4*)(base + o1); c->g.rec2 = (float2*)(base + o2);
     c->g.radii = (int32_t*)(base + o3); c->g.rect = (uint2*)(base + o4); c->g.tiles_touched = (uint32_t*)(base + o5);
-    c->g.offsets = (uint32_t*)(base + o6); c->g.clamped = (uint8_t*)(base + o7);
-    c->g.perm = (uint32_t*)(base + o8); c->g.dkeys = (uint32_t*)(base + o9);
+    c->g.clamped = (uint8_t*)(base + o7);
+    c->g.perm = (uint32_t*)(base + o8);
     return G4D_OK;
 }
 
@@ -157,15 +157,9 @@ int ensure_image(G4DContext* c, int H, int W) {
 int ensure_bin(G4DContext* c, int64_t r) {
     const size_t R = (size_t)(r > 0 ? r : 1);
     if ((int64_t)R <= c->capacity && c->bin.p) return G4D_OK;
-    const size_t cap = 2 * R + 1024;   // generous head-room: a regrow is a cudaFree + cudaMalloc (device sync, up to 100+ ms)
-    size_t off = 0;
-    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
-    const size_t o0 = take(cap * 8), o1 = take(cap * 8), o2 = take(cap * 4), o3 = take(cap * 4);
-    G4D_CUDA(c->bin.ensure(off));
-    char* base = c->bin.as<char>();
-    c->b.keys_unsorted = (uint64_t*)(base + o0); c->b.keys_sorted = (uint64_t*)(base + o1);
-    c->b.ids_unsorted = (uint32_t*)(base + o2); c->b.ids_sorted = (uint32_t*)(base + o3);
-    c->capacity = (int64_t)cap;
+    G4D_CUDA(c->bin.ensure(R * 4));          // DevBuf grows by 1.5x: the one growth factor of the instance list
+    c->b.ids_sorted = c->bin.as<uint32_t>();
+    c->capacity = (int64_t)(c->bin.cap / 4);
     return G4D_OK;
 }
 
@@ -332,74 +326,52 @@ int check_pending(G4DContext* c) {
     return G4D_OK;
 }
 
-// stages after the per-Gaussian projection: scan -> R -> emit -> sort -> ranges -> blend
+// stages after the per-Gaussian projection: bin_sort (depth order, per-tile counts, ranges, R) -> bin_place -> blend
 int bin_and_blend(G4DContext* c, const G4DCamera* cam, int64_t n, float* out_color, float* out_depth, cudaStream_t st) {
     G4DWorkspace* ws = c->ws;
     const CameraDev* dcam = c->cam.as<CameraDev>();
     int rc;
-    int64_t R = 0;
     const int num_tiles = c->grid_x * c->grid_y;
-    int tile_bits = 0;
-    while ((1 << tile_bits) < num_tiles) ++tile_bits;
-    // no-sync needs a capacity learnt from an earlier (synchronous) forward on this context
-    const bool nosync = !ws->sync_mode && !(cam->debug & G4D_CAM_DEBUG) && c->capacity > 0 && c->R > 0 && n > 0;
+    const uint32_t kNoCap = 0xFFFFFFFFu;
     if (n > 0) {
-        const size_t tb = depth_order_temp_bytes(n);
-        G4D_CUDA(ws->temp.ensure(tb));
+        if (ws->sm_count > 1024) return fail(G4D_ERR_ARG, "more than 1024 SMs are not supported by the binning kernel");
+        G4D_CUDA(c->binaux.ensure(bin_aux_bytes(n, num_tiles, ws->sm_count)));
+        // no-sync needs a capacity learnt from an earlier (exact) forward on this context
+        const bool nosync = !ws->sync_mode && !(cam->debug & G4D_CAM_DEBUG) && c->capacity > 0 && c->learned;
+        if (nosync && ws->min_capacity > c->capacity && (rc = ensure_bin(c, ws->min_capacity)) != G4D_OK) return rc;
+        const uint32_t cap_now = (uint32_t)(c->capacity < (int64_t)kNoCap ? c->capacity : (int64_t)kNoCap);
+        BinLayout lay{};
         {
             StageTimer tm(c, G4D_STAGE_SCAN, st);
-            if (ws->tight_cull) G4D_CUDA(launch_cull_count(n, c->g, st));
-            // Gaussians in depth order first: the 64-bit (tile | depth) sort then only has to sort on the tile bits
-            G4D_CUDA(launch_depth_order(n, c->g, ws->temp.p, tb, st));
+            G4D_CUDA(launch_bin_sort(n, c->grid_x, c->grid_y, c->g, c->binaux.p, c->b.ranges, nosync ? cap_now : kNoCap,
+                                     ws->tight_cull, ws->sm_count, &lay, st));
         }
         if (!nosync) {
-            G4D_CUDA(cudaMemcpyAsync(ws->h_pinned, c->g.offsets + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            G4D_CUDA(cudaStreamSynchronize(st));   // the one host sync of the path (as in the reference, A.2)
-            R = (int64_t)ws->h_pinned[0];
+            G4D_CUDA(cudaMemcpyAsync(ws->h_pinned, &lay.ctl->R, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            G4D_CUDA(cudaStreamSynchronize(st));   // exact mode: the one host sync of the path (as in the reference, A.2)
+            const int64_t R = (int64_t)ws->h_pinned[0];
+            c->R = R; c->learned = true;
+            int64_t want = R;
+            if (!ws->sync_mode) want = R + R / 2;                 // head-room for the asynchronous forwards that follow
+            if (want < ws->min_capacity) want = ws->min_capacity;
+            if ((rc = ensure_bin(c, want)) != G4D_OK) return rc;
+        } else {
+            // capacity-bounded, no host round trip: the placement clamps to the capacity, R arrives asynchronously and an
+            // overflow is reported by the next call on this context
+            G4D_CUDA(cudaMemcpyAsync(c->h_r, &lay.ctl->R, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            G4D_CUDA(cudaEventRecord(c->ev_r, st));
+            c->pending = true; c->used_capacity = c->capacity;
         }
-    }
-    if ((rc = debug_sync(cam, st, "preprocess/scan")) != G4D_OK) return rc;
-    if (!nosync) {
-        c->R = R;
-        int64_t want = R;
-        if (!ws->sync_mode) want = R + R / 2;                 // head-room for the asynchronous forwards that follow
-        if (want < ws->min_capacity) want = ws->min_capacity;
-        if ((rc = ensure_bin(c, want)) != G4D_OK) return rc;
-        if (R > 0) {
-            {
-                StageTimer tm(c, G4D_STAGE_EMIT, st);
-                G4D_CUDA(launch_emit_keys(dcam, n, c->g, c->b, c->capacity, ws->tight_cull, st));
-            }
-            const size_t sb = sort_temp_bytes(c->capacity);   // sized for the capacity, not R: no regrow while R wanders
-            G4D_CUDA(ws->temp.ensure(sb));
-            StageTimer tm(c, G4D_STAGE_SORT, st);
-            G4D_CUDA(launch_sort(c->b, R, 32, 32 + tile_bits, ws->temp.p, sb, st));
-        }
-        {
-            StageTimer tm(c, G4D_STAGE_RANGES, st);
-            G4D_CUDA(launch_tile_ranges(c->b, R, num_tiles, st));
-        }
-    } else {
-        // capacity-bounded, no host round trip: unused slots carry all-ones keys whose tile field (one extra sorted bit)
-        // exceeds every real tile, so they collect behind the last tile and are ignored by the range builder
-        if (ws->min_capacity > c->capacity && (rc = ensure_bin(c, ws->min_capacity)) != G4D_OK) return rc;
-        const int64_t cap = c->capacity;
-        G4D_CUDA(cudaMemcpyAsync(c->h_r, c->g.offsets + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        G4D_CUDA(cudaEventRecord(c->ev_r, st));
-        c->pending = true; c->used_capacity = cap;
+        if ((rc = debug_sync(cam, st, "bin_sort")) != G4D_OK) return rc;
         {
             StageTimer tm(c, G4D_STAGE_EMIT, st);
-            G4D_CUDA(cudaMemsetAsync(c->b.keys_unsorted, 0xFF, (size_t)cap * 8, st));
-            G4D_CUDA(launch_emit_keys(dcam, n, c->g, c->b, cap, ws->tight_cull, st));
+            const uint32_t cap_place = (uint32_t)(c->capacity < (int64_t)kNoCap ? c->capacity : (int64_t)kNoCap);
+            G4D_CUDA(launch_bin_place(c->grid_x, c->grid_y, c->g, lay, c->b.ids_sorted, cap_place, ws->tight_cull, st));
         }
-        const size_t sb = sort_temp_bytes(cap);
-        G4D_CUDA(ws->temp.ensure(sb));
-        {
-            StageTimer tm(c, G4D_STAGE_SORT, st);
-            G4D_CUDA(launch_sort(c->b, cap, 32, 32 + tile_bits + 1, ws->temp.p, sb, st));
-        }
-        StageTimer tm(c, G4D_STAGE_RANGES, st);
-        G4D_CUDA(launch_tile_ranges(c->b, cap, num_tiles, st));
+    } else {
+        c->R = 0;
+        G4D_CUDA(cudaMemsetAsync(c->b.ranges, 0, sizeof(uint2) * (size_t)num_tiles, st));
+        if ((rc = ensure_bin(c, 1)) != G4D_OK) return rc;
     }
     if ((rc = debug_sync(cam, st, "binning")) != G4D_OK) return rc;
     {
@@ -465,7 +437,7 @@ G4DWorkspace* g4d_workspace_create(int device) {
 void g4d_workspace_destroy(G4DWorkspace* ws) {
     if (!ws) return;
     cudaSetDevice(ws->device);
-    ws->packed.release(); ws->tc_packed.release(); ws->tc_bwd_packed.release(); ws->tc_feat.release(); ws->trow.release(); ws->temp.release(); ws->scratch.release();
+    ws->packed.release(); ws->tc_packed.release(); ws->tc_bwd_packed.release(); ws->tc_feat.release(); ws->trow.release(); ws->scratch.release();
     if (ws->h_pinned) cudaFreeHost(ws->h_pinned);
     delete ws;
 }
@@ -488,7 +460,7 @@ void g4d_context_destroy(G4DContext* c) {
     if (c->ev_created) for (int i = 0; i < 2 * G4D_STAGE_COUNT; ++i) cudaEventDestroy(c->ev[i]);
     if (c->ev_r) cudaEventDestroy(c->ev_r);
     if (c->h_r) cudaFreeHost(c->h_r);
-    c->cam.release(); c->geom.release(); c->bin.release(); c->img.release(); c->fused.release(); c->gscratch.release(); c->gdeform.release(); c->relu.release(); c->feat.release();
+    c->cam.release(); c->geom.release(); c->bin.release(); c->binaux.release(); c->img.release(); c->fused.release(); c->gscratch.release(); c->gdeform.release(); c->relu.release(); c->feat.release();
     c->trow.release();
     delete c;
 }
@@ -654,7 +626,21 @@ int64_t g4d_context_read(G4DContext* c, int which, void* host_dst, int64_t bytes
             ok = pull(c->g.rec1, N * 16); std::vector<char> t1 = tmp; ok = ok && pull(c->g.rec2, N * 8); outv.resize(N * 12);
             for (size_t i = 0; i < N && ok; ++i) { memcpy(&outv[i * 12], &t1[i * 16 + 8], 8); memcpy(&outv[i * 12 + 8], &tmp[i * 8], 4); }
         } break;
-        case G4D_BUF_SORTED_KEYS: ok = pull(c->b.keys_sorted, R * 8); outv = tmp; outv.resize(R * 8); break;
+        case G4D_BUF_SORTED_KEYS: {
+            // the (tile | depth bits) keys of the reference's sorted list are implicit in (ranges, ids, depth): rebuilt here
+            ok = pull(c->b.ids_sorted, R * 4); std::vector<char> ids = tmp;
+            ok = ok && pull(c->b.ranges, Tn * 8); std::vector<char> rg = tmp;
+            ok = ok && pull(c->g.rec2, N * 8);
+            outv.resize(R * 8);
+            for (size_t t = 0; t < Tn && ok; ++t) {
+                uint32_t lo, hi; memcpy(&lo, &rg[t * 8], 4); memcpy(&hi, &rg[t * 8 + 4], 4);
+                for (size_t i = lo; i < hi && i < R; ++i) {
+                    uint32_t id, db; memcpy(&id, &ids[i * 4], 4); memcpy(&db, &tmp[(size_t)id * 8 + 4], 4);
+                    const uint64_t key = ((uint64_t)t << 32) | db;
+                    memcpy(&outv[i * 8], &key, 8);
+                }
+            }
+        } break;
         case G4D_BUF_SORTED_IDS: ok = pull(c->b.ids_sorted, R * 4); outv = tmp; outv.resize(R * 4); break;
         case G4D_BUF_RANGES: ok = pull(c->b.ranges, Tn * 8); outv = tmp; outv.resize(Tn * 8); break;
         case G4D_BUF_FINAL_T: ok = pull(c->im.final_T, P * 4); outv = tmp; outv.resize(P * 4); break;
@@ -676,6 +662,10 @@ int64_t g4d_context_read(G4DContext* c, int which, void* host_dst, int64_t bytes
                 memcpy(dst + i * 11, &m[i * 3], 12); memcpy(dst + i * 11 + 3, &s[i * 3], 12);
                 memcpy(dst + i * 11 + 6, &r[i * 4], 16); dst[i * 11 + 10] = o[i];
             }
+        } break;
+        case G4D_BUF_DEFORMED_SHS: {
+            if (!c->is_fused || !c->fused_sh || !c->fo.shs) return fail(G4D_ERR_STATE, "G4D_BUF_DEFORMED_SHS needs a fused forward with the SHS head active");
+            ok = pull(c->fo.shs, N * 192); outv = tmp; outv.resize(N * 192);
         } break;
         default: return fail(G4D_ERR_ARG, "unknown buffer id");
     }
@@ -830,16 +820,54 @@ int g4d_render_backward(G4DContext* c, const G4DCamera* cam, const G4DDeformPara
     return debug_sync(cam, st, "deform_backward");
 }
 
-int g4d_debug_umma(G4DWorkspace* ws, const int* cfg, const float* A, const float* B, float* D, void* stream) {
-    if (!ws || !cfg || !A || !B || !D) return fail(G4D_ERR_ARG, "NULL argument");
-    cudaStream_t st = (cudaStream_t)stream;
+// ------------------------------------------------------------------------------------------------------
+int g4d_l1_loss(G4DWorkspace* ws, const float* out, const float* gt, int64_t numel, float scale, float* loss_accum, void* stream) {
+    if (!ws || numel < 0 || (numel > 0 && (!out || !gt)) || !loss_accum) return fail(G4D_ERR_ARG, "g4d_l1_loss: bad argument");
     G4D_CUDA(cudaSetDevice(ws->device));
-    G4D_CUDA(ws->scratch.ensure((size_t)2 * 128 * 128 * 4 + 256));
-    if (cfg[6] == 16) {   // kind::f16 / bf16x2 variant: cfg = {N, K, a_mode, b_mode, pack_hi_first, single_pass, 16, 0}
-        G4D_CUDA(launch_umma16_selftest(cfg, A, B, D, st));
-        return G4D_OK;
-    }
-    G4D_CUDA(launch_umma_selftest(cfg, A, B, ws->scratch.as<float>(), D, st));
+    G4D_CUDA(launch_l1_loss(out, gt, numel, scale, loss_accum, ws->sm_count, (cudaStream_t)stream));
+    return G4D_OK;
+}
+
+int g4d_l1_loss_backward(G4DWorkspace* ws, const float* out, const float* gt, int64_t numel, float scale, const float* upstream,
+                         float* grad_out, void* stream) {
+    if (!ws || numel < 0 || (numel > 0 && (!out || !gt || !grad_out))) return fail(G4D_ERR_ARG, "g4d_l1_loss_backward: bad argument");
+    G4D_CUDA(cudaSetDevice(ws->device));
+    G4D_CUDA(launch_l1_grad(out, gt, numel, scale, upstream, grad_out, ws->sm_count, (cudaStream_t)stream));
+    return G4D_OK;
+}
+
+int g4d_ssim(G4DWorkspace* ws, const float* img1, const float* img2, int32_t channels, int32_t height, int32_t width, float scale,
+             float* ssim_accum, float* saved, void* stream) {
+    if (!ws || channels < 0 || height < 0 || width < 0 || !img1 || !img2) return fail(G4D_ERR_ARG, "g4d_ssim: bad argument");
+    if (channels > 65535) return fail(G4D_ERR_ARG, "g4d_ssim: more than 65535 channels");
+    G4D_CUDA(cudaSetDevice(ws->device));
+    const size_t P = (size_t)channels * height * width;
+    G4D_CUDA(launch_ssim_forward(img1, img2, channels, height, width, scale, ssim_accum, saved, saved ? saved + P : nullptr,
+                                 saved ? saved + 2 * P : nullptr, (cudaStream_t)stream));
+    return G4D_OK;
+}
+
+int g4d_ssim_backward(G4DWorkspace* ws, const float* img1, const float* img2, int32_t channels, int32_t height, int32_t width,
+                      float scale, const float* upstream, const float* saved, float* grad_img1, void* stream) {
+    if (!ws || channels < 0 || height < 0 || width < 0 || !img1 || !img2 || !saved || !grad_img1)
+        return fail(G4D_ERR_ARG, "g4d_ssim_backward: bad argument");
+    if (channels > 65535) return fail(G4D_ERR_ARG, "g4d_ssim: more than 65535 channels");
+    G4D_CUDA(cudaSetDevice(ws->device));
+    const size_t P = (size_t)channels * height * width;
+    G4D_CUDA(launch_ssim_backward(img1, img2, channels, height, width, scale, upstream, saved, saved + P, saved + 2 * P, grad_img1,
+                                  (cudaStream_t)stream));
+    return G4D_OK;
+}
+
+int g4d_plane_regulation(G4DWorkspace* ws, const G4DDeformParams* prm, G4DDeformGrads* grads, float plane_tv_weight,
+                         float time_smoothness_weight, float l1_time_planes_weight, const float* upstream, float* loss_accum,
+                         void* stream) {
+    if (!ws) return fail(G4D_ERR_ARG, "workspace is NULL");
+    int rc = check_params(prm);
+    if (rc != G4D_OK) return rc;
+    G4D_CUDA(cudaSetDevice(ws->device));
+    G4D_CUDA(launch_plane_regulation(*prm, grads, plane_tv_weight, time_smoothness_weight, l1_time_planes_weight, upstream, loss_accum,
+                                     ws->sm_count, (cudaStream_t)stream));
     return G4D_OK;
 }
 

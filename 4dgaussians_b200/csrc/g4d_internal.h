@@ -16,17 +16,47 @@ struct GeomBuffers {
     int32_t* radii;
     uint2* rect;         // x = minx | miny<<16, y = maxx | maxy<<16   (tile units)
     uint32_t* tiles_touched;
-    uint32_t* offsets;   // inclusive scan of tiles_touched IN DEPTH ORDER: offsets[k] belongs to Gaussian perm[k]
-    uint32_t* perm;      // Gaussian indices sorted by (depth bits, index); invisible ones last
-    uint32_t* dkeys;     // [4][N] scratch of the depth sort: keys in / keys out / iota / (unused)
+    uint32_t* perm;      // the VISIBLE Gaussians' indices sorted by (depth bits, index)   (bin_sort_kernel)
     uint8_t* clamped;    // bit ch set when the forward clamped colour channel ch at 0
 };
 
 struct BinBuffers {
-    uint64_t* keys_unsorted; uint64_t* keys_sorted;
-    uint32_t* ids_unsorted; uint32_t* ids_sorted;
-    uint2* ranges;       // [tiles] (start, end)
+    uint32_t* ids_sorted;   // [capacity] Gaussian index of every (tile, Gaussian) instance, tile-major, depth-ordered per tile
+    uint2* ranges;          // [tiles] (start, end) into ids_sorted
 };
+
+// ---- binning (g4d_bin.cu) ---------------------------------------------------------------------------------------
+struct BinCtl { uint32_t n_visible, R, overflow, pad; };   // device-resident results of one forward's binning
+struct BinSortArgs {
+    int64_t n;
+    const float2* rec2; const uint32_t* tiles_touched; const uint2* rect; const float4* rec0; const float4* rec1;
+    uint32_t *kA, *vA, *kB, *vB;   // [N] ping-pong buffers of the depth sort
+    uint32_t* perm;                // [N] out: visible Gaussians in depth order
+    uint32_t* H;                   // [chunks][256] digit histograms of the current pass
+    uint32_t* S;                   // [chunks] tiles_touched sums of equal-count slices
+    uint32_t* chunk_start;         // [chunks + 1] positions in perm
+    uint32_t* M;                   // [chunks][tiles] instance counts, then exclusive prefix over the chunks
+    uint32_t* tile_total;          // [tiles]
+    uint32_t* tile_start;          // [tiles] exclusive scan of tile_total (unclamped)
+    uint2* ranges;                 // [tiles] clamped to the capacity
+    BinCtl* ctl;
+    int grid_x, grid_y, num_tiles, count_band_rows;
+    uint32_t capacity; int tight;
+};
+struct BinPlaceArgs {
+    const uint32_t* perm; const uint2* rect; const float4* rec0; const float4* rec1;
+    const uint32_t* chunk_start; const uint32_t* M; const uint32_t* tile_start;
+    uint32_t* ids; uint32_t capacity;
+    int grid_x, grid_y, num_tiles, band_rows, tight;
+};
+struct BinLayout { uint32_t* chunk_start; uint32_t* M; uint32_t* tile_start; BinCtl* ctl; int chunks; };
+size_t bin_aux_bytes(int64_t n, int num_tiles, int sm_count);
+// depth sort + chunking + per-(chunk, tile) counts + scans: ranges, tile_start, ctl->R.  One cooperative launch.
+cudaError_t launch_bin_sort(int64_t n, int grid_x, int grid_y, const GeomBuffers& g, void* aux, uint2* ranges, uint32_t capacity,
+                            int tight, int sm_count, BinLayout* out, cudaStream_t st);
+// stable counting placement of every instance into its tile segment
+cudaError_t launch_bin_place(int grid_x, int grid_y, const GeomBuffers& g, const BinLayout& lay, uint32_t* ids, uint32_t capacity,
+                             int tight, cudaStream_t st);
 
 struct ImageBuffers {
     float* final_T;      // [H*W]
@@ -94,17 +124,6 @@ cudaError_t launch_deform(const DeformDesc& d, int mode, const CameraDev* cam, f
                           float* out_rotation, float* out_opacity, float* out_shs, GeomBuffers g, FusedOutputs fo,
                           int32_t* out_radii, int sm_count, cudaStream_t st, const TcWeights* tw = nullptr);
 
-size_t scan_temp_bytes(int64_t n);
-// depth order of the visible Gaussians + inclusive scan of tiles_touched in that order (g.perm, g.offsets)
-size_t depth_order_temp_bytes(int64_t n);
-cudaError_t launch_depth_order(int64_t n, GeomBuffers g, void* temp, size_t temp_bytes, cudaStream_t st);
-size_t sort_temp_bytes(int64_t r);
-cudaError_t launch_scan(const uint32_t* in, uint32_t* out, int64_t n, void* temp, size_t temp_bytes, cudaStream_t st);
-cudaError_t launch_cull_count(int64_t n, GeomBuffers g, cudaStream_t st);
-cudaError_t launch_emit_keys(const CameraDev* cam, int64_t n, GeomBuffers g, BinBuffers b, int64_t capacity, int tight,
-                             cudaStream_t st);
-cudaError_t launch_sort(BinBuffers b, int64_t r, int begin_bit, int end_bit, void* temp, size_t temp_bytes, cudaStream_t st);
-cudaError_t launch_tile_ranges(BinBuffers b, int64_t r, int num_tiles, cudaStream_t st);
 cudaError_t launch_blend_forward(const CameraDev* cam, int grid_x, int grid_y, GeomBuffers g, BinBuffers b, ImageBuffers im,
                                  float* out_color, float* out_depth, int warp_cull, cudaStream_t st);
 cudaError_t launch_blend_backward(const CameraDev* cam, int grid_x, int grid_y, GeomBuffers g, BinBuffers b, ImageBuffers im,
@@ -130,6 +149,18 @@ cudaError_t launch_activate_preprocess(const CameraDev* cam, int64_t n, const fl
 cudaError_t launch_activation_backward(int64_t n, const FusedOutputs& fo, float* g_scales, float* g_rotations,
                                        float* g_opacities, cudaStream_t st);
 
+// ---- losses either side of the path (g4d_loss.cu) -------------------------------------------------------------------
+cudaError_t launch_l1_loss(const float* a, const float* b, int64_t n, float scale, float* loss, int sm_count, cudaStream_t st);
+cudaError_t launch_l1_grad(const float* a, const float* b, int64_t n, float scale, const float* upstream, float* grad, int sm_count,
+                           cudaStream_t st);
+cudaError_t launch_plane_regulation(const G4DDeformParams& prm, const G4DDeformGrads* grads, float w_plane_tv, float w_time_smooth,
+                                    float w_l1_time, const float* upstream, float* loss, int sm_count, cudaStream_t st);
+cudaError_t launch_ssim_forward(const float* x, const float* y, int C, int H, int W, float scale, float* loss, float* dmu, float* dxx,
+                                float* dxy, cudaStream_t st);
+cudaError_t launch_ssim_backward(const float* x, const float* y, int C, int H, int W, float scale, const float* upstream,
+                                 const float* dmu, const float* dxx, const float* dxy, float* grad, cudaStream_t st);
+
+// tcgen05 building-block self test: g4d_tc_selftest.cu -> libg4d_selftest.so (test-only library, not in libg4d.so)
 cudaError_t launch_umma16_selftest(const int cfg[8], const float* A, const float* B, float* D, cudaStream_t st);
 cudaError_t launch_umma_selftest(const int cfg[8], const float* A, const float* B, float* scratch_packed, float* D, cudaStream_t st);
 

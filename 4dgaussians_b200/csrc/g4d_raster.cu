@@ -1,228 +1,12 @@
-// g4d_raster.cu -- tile binning (scan, key emission, radix sort, tile ranges) and the per-tile front-to-back
-// alpha compositing forward / back-to-front backward.   SURVEY.md Appendix A.2-A.4.
+// g4d_raster.cu -- the per-tile front-to-back alpha compositing forward / back-to-front backward.
+// SURVEY.md Appendix A.3-A.4 (binning, A.2, lives in g4d_bin.cu).
 // Reference stage replaced: the CUDA rasterizer behind /root/reference/gaussian_renderer/__init__.py:120-128.
 #include <cstdlib>
 
-#include <cub/cub.cuh>
-
 #include "g4d_internal.h"
+#include "raster_cull.cuh"
 
 namespace g4d {
-
-// ------------------------------------------------------------------------------------------------------
-size_t scan_temp_bytes(int64_t n) {
-    size_t b = 0;
-    cub::DeviceScan::InclusiveSum(nullptr, b, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
-    return b;
-}
-size_t sort_temp_bytes(int64_t r) {
-    size_t b = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, b, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
-                                    (uint32_t*)nullptr, (int)r);
-    return b;
-}
-cudaError_t launch_scan(const uint32_t* in, uint32_t* out, int64_t n, void* temp, size_t temp_bytes, cudaStream_t st) {
-    if (n == 0) return cudaSuccess;
-    return cub::DeviceScan::InclusiveSum(temp, temp_bytes, in, out, (int)n, st);
-}
-
-// ---- depth order -------------------------------------------------------------------------------------------------
-// The reference sorts R (tile | depth) 64-bit keys on 32 + log2(tiles) bits (A.2).  A stable sort of the N Gaussians by
-// depth bits followed by key emission IN THAT ORDER and a stable sort of the R keys on the tile bits alone gives the
-// identical sequence (ties: depth-equal entries keep Gaussian-index order in both) with 2 instead of 6 passes over R.
-struct PermutedCount {
-    const uint32_t* tt; const uint32_t* perm;
-    __host__ __device__ uint32_t operator()(int k) const { return tt[perm[k]]; }
-};
-__global__ void __launch_bounds__(256) depth_keys_kernel(int64_t n, GeomBuffers g) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    g.dkeys[i] = g.tiles_touched[i] ? __float_as_uint(g.rec2[i].y) : 0xFFFFFFFFu;   // depth > 0.2: sign bit clear, order-preserving
-    g.dkeys[2 * n + i] = (uint32_t)i;
-}
-size_t depth_order_temp_bytes(int64_t n) {
-    size_t a = 0, b = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
-                                    (uint32_t*)nullptr, (int)n);
-    cub::CountingInputIterator<int> cnt(0);
-    cub::TransformInputIterator<uint32_t, PermutedCount, cub::CountingInputIterator<int>> it(cnt, PermutedCount{nullptr, nullptr});
-    cub::DeviceScan::InclusiveSum(nullptr, b, it, (uint32_t*)nullptr, (int)n);
-    return a > b ? a : b;
-}
-cudaError_t launch_depth_order(int64_t n, GeomBuffers g, void* temp, size_t temp_bytes, cudaStream_t st) {
-    if (n == 0) return cudaSuccess;
-    depth_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, g);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, g.dkeys, g.dkeys + n, g.dkeys + 2 * n, g.perm, (int)n, 0, 32, st);
-    if (e != cudaSuccess) return e;
-    cub::CountingInputIterator<int> cnt(0);
-    cub::TransformInputIterator<uint32_t, PermutedCount, cub::CountingInputIterator<int>> it(cnt, PermutedCount{g.tiles_touched, g.perm});
-    return cub::DeviceScan::InclusiveSum(temp, temp_bytes, it, g.offsets, (int)n, st);
-}
-
-// ---- exact-image tile culling (G4D_OPT_TIGHT_CULL) -------------------------------------------------------------
-// A (Gaussian, tile) pair can be dropped without changing a single pixel when even the best-placed point of the
-// tile's pixel rectangle has alpha = opacity * exp(-q/2) < 1/255 (the blend stage skips such contributions, A.3).
-// q is a convex quadratic, so its minimum over the rectangle is 0 (centre inside) or lies on one of the 4 edges.
-// The 1e-4 margin covers the different rounding of the per-pixel evaluation in the blend kernel.
-G4D_D float edge_min(float a, float b, float c, float fixed, float lo, float hi) {
-    // min over t in [lo,hi] of a*fixed^2 + 2*b*fixed*t + c*t^2
-    float t = -b * fixed / c;
-    t = fminf(fmaxf(t, lo), hi);
-    return a * fixed * fixed + 2.f * b * fixed * t + c * t * t;
-}
-// can the Gaussian reach alpha >= 1/255 anywhere in the pixel rectangle [x0, x1] x [y0, y1] (inclusive pixel centres)?
-G4D_D bool rect_contributes(float4 r0, float4 r1, float x0, float x1, float y0, float y1) {
-    const float A = r0.z, B = r0.w, C = r1.x, op = r1.y;
-    const float dx0 = r0.x - x1, dx1 = r0.x - x0;
-    const float dy0 = r0.y - y1, dy1 = r0.y - y0;
-    float qmin;
-    if (dx0 <= 0.f && dx1 >= 0.f && dy0 <= 0.f && dy1 >= 0.f) qmin = 0.f;
-    else {
-        qmin = fminf(fminf(edge_min(A, B, C, dx0, dy0, dy1), edge_min(A, B, C, dx1, dy0, dy1)),
-                     fminf(edge_min(C, B, A, dy0, dx0, dx1), edge_min(C, B, A, dy1, dx0, dx1)));
-        qmin = fmaxf(qmin, 0.f);
-    }
-    return op * __expf(-0.5f * qmin) * 1.0001f >= kAlphaMin;
-}
-G4D_D bool tile_contributes(float4 r0, float4 r1, int tx, int ty) {
-    const float A = r0.z, B = r0.w, C = r1.x, op = r1.y;
-    const float dx0 = r0.x - (float)(tx * kTile + kTile - 1), dx1 = r0.x - (float)(tx * kTile);
-    const float dy0 = r0.y - (float)(ty * kTile + kTile - 1), dy1 = r0.y - (float)(ty * kTile);
-    float qmin;
-    if (dx0 <= 0.f && dx1 >= 0.f && dy0 <= 0.f && dy1 >= 0.f) qmin = 0.f;
-    else {
-        qmin = fminf(fminf(edge_min(A, B, C, dx0, dy0, dy1), edge_min(A, B, C, dx1, dy0, dy1)),
-                     fminf(edge_min(C, B, A, dy0, dx0, dx1), edge_min(C, B, A, dy1, dx0, dx1)));
-        qmin = fmaxf(qmin, 0.f);
-    }
-    return op * __expf(-0.5f * qmin) * 1.0001f >= kAlphaMin;
-}
-
-// tight mode: tiles_touched := number of tiles of the rect that can contribute (same predicate as emit_keys_kernel,
-// same translation unit, hence bit-identical decisions).
-// Warp-cooperative: a warp owns 32 consecutive Gaussians; for each visible one (broadcast by shuffle) the 32 lanes test
-// 32 tiles of its rect at a time -- a thread-per-Gaussian loop serialises on the largest rect of the warp.
-struct TileJob { float4 r0, r1; int minx, miny, w, ntiles; };
-G4D_D TileJob bcast_job(const float4& r0, const float4& r1, uint2 rc, int src) {
-    TileJob j;
-    j.r0.x = __shfl_sync(0xffffffffu, r0.x, src); j.r0.y = __shfl_sync(0xffffffffu, r0.y, src);
-    j.r0.z = __shfl_sync(0xffffffffu, r0.z, src); j.r0.w = __shfl_sync(0xffffffffu, r0.w, src);
-    j.r1.x = __shfl_sync(0xffffffffu, r1.x, src); j.r1.y = __shfl_sync(0xffffffffu, r1.y, src);
-    j.r1.z = 0.f; j.r1.w = 0.f;
-    const uint32_t rx = __shfl_sync(0xffffffffu, rc.x, src), ry = __shfl_sync(0xffffffffu, rc.y, src);
-    j.minx = rx & 0xFFFF; j.miny = rx >> 16;
-    const int maxx = ry & 0xFFFF, maxy = ry >> 16;
-    j.w = maxx - j.minx;
-    j.ntiles = j.w * (maxy - j.miny);
-    return j;
-}
-
-__global__ void __launch_bounds__(256) cull_count_kernel(int64_t n, GeomBuffers g) {
-    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const bool vis = gi < n && g.tiles_touched[gi] != 0;
-    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-    uint2 rc = make_uint2(0u, 0u);
-    if (vis) { r0 = g.rec0[gi]; r1 = g.rec1[gi]; rc = g.rect[gi]; }
-    uint32_t todo = __ballot_sync(0xffffffffu, vis);
-    uint32_t mine = 0;
-    while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const TileJob j = bcast_job(r0, r1, rc, src);
-        uint32_t cnt = 0;
-        for (int base = 0; base < j.ntiles; base += 32) {
-            const int t = base + lane;
-            const int ty = t / j.w, tx = t - ty * j.w;
-            const bool c = t < j.ntiles && tile_contributes(j.r0, j.r1, j.minx + tx, j.miny + ty);
-            cnt += __popc(__ballot_sync(0xffffffffu, c));
-        }
-        if (lane == src) mine = cnt;
-    }
-    if (vis) g.tiles_touched[gi] = mine;
-}
-
-cudaError_t launch_cull_count(int64_t n, GeomBuffers g, cudaStream_t st) {
-    if (n == 0) return cudaSuccess;
-    cull_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, g);
-    return cudaGetLastError();
-}
-
-// A.2: one (tile | depth bits) key and the Gaussian index per touched tile, at consecutive slots from offsets[i-1],
-// tiles in row-major order of the rect (warp-cooperative like cull_count_kernel)
-__global__ void __launch_bounds__(256) emit_keys_kernel(const CameraDev* __restrict__ cam, int64_t n, GeomBuffers g,
-                                                        BinBuffers b, int64_t capacity, int tight) {
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // position in depth order
-    const int lane = threadIdx.x & 31;
-    const uint32_t gi = k < n ? g.perm[k] : 0u;
-    const bool vis = k < n && g.tiles_touched[gi] != 0;
-    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-    uint2 rc = make_uint2(0u, 0u);
-    uint32_t dbits = 0, off0 = 0;
-    if (vis) {
-        rc = g.rect[gi];
-        dbits = __float_as_uint(g.rec2[gi].y);
-        off0 = k == 0 ? 0u : g.offsets[k - 1];
-        if (tight) { r0 = g.rec0[gi]; r1 = g.rec1[gi]; }
-    }
-    const int gx = cam->grid_x;
-    uint32_t todo = __ballot_sync(0xffffffffu, vis);
-    while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const TileJob j = bcast_job(r0, r1, rc, src);
-        const uint32_t db = __shfl_sync(0xffffffffu, dbits, src);
-        int64_t off = (int64_t)__shfl_sync(0xffffffffu, off0, src);
-        const uint32_t id = __shfl_sync(0xffffffffu, gi, src);
-        for (int base = 0; base < j.ntiles; base += 32) {
-            const int t = base + lane;
-            const int ty = t / j.w, tx = t - ty * j.w;
-            const int x = j.minx + tx, y = j.miny + ty;
-            const bool c = t < j.ntiles && (!tight || tile_contributes(j.r0, j.r1, x, y));
-            const uint32_t m = __ballot_sync(0xffffffffu, c);
-            if (c) {
-                const int64_t slot = off + __popc(m & ((1u << lane) - 1u));
-                if (slot < capacity) {
-                    b.keys_unsorted[slot] = ((uint64_t)(uint32_t)(y * gx + x) << 32) | db;
-                    b.ids_unsorted[slot] = id;
-                }
-            }
-            off += __popc(m);
-        }
-    }
-}
-
-cudaError_t launch_emit_keys(const CameraDev* cam, int64_t n, GeomBuffers g, BinBuffers b, int64_t capacity, int tight,
-                             cudaStream_t st) {
-    if (n == 0) return cudaSuccess;
-    emit_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cam, n, g, b, capacity, tight);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_sort(BinBuffers b, int64_t r, int begin_bit, int end_bit, void* temp, size_t temp_bytes, cudaStream_t st) {
-    if (r == 0) return cudaSuccess;
-    return cub::DeviceRadixSort::SortPairs(temp, temp_bytes, b.keys_unsorted, b.keys_sorted, b.ids_unsorted, b.ids_sorted,
-                                           (int)r, begin_bit, end_bit, st);
-}
-
-__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint64_t* __restrict__ keys, int64_t r, uint2* ranges,
-                                                          uint32_t num_tiles) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= r) return;
-    const uint32_t t = (uint32_t)(keys[i] >> 32);
-    if (t >= num_tiles) return;   // padding slots of the capacity-bounded (no-sync) mode
-    if (i == 0 || (uint32_t)(keys[i - 1] >> 32) != t) ranges[t].x = (uint32_t)i;
-    if (i == r - 1 || (uint32_t)(keys[i + 1] >> 32) != t) ranges[t].y = (uint32_t)(i + 1);
-}
-
-cudaError_t launch_tile_ranges(BinBuffers b, int64_t r, int num_tiles, cudaStream_t st) {
-    cudaError_t e = cudaMemsetAsync(b.ranges, 0, sizeof(uint2) * (size_t)num_tiles, st);
-    if (e != cudaSuccess || r == 0) return e;
-    tile_ranges_kernel<<<(unsigned)((r + 255) / 256), 256, 0, st>>>(b.keys_sorted, r, b.ranges, (uint32_t)num_tiles);
-    return cudaGetLastError();
-}
 
 // ------------------------------------------------------------------------------------------------------
 // A.3 blend forward: one 16x16 CTA per tile, instances staged through shared memory in batches of 256.

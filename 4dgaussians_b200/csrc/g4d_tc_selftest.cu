@@ -258,3 +258,14 @@ cudaError_t launch_umma16_selftest(const int cfg[8], const float* A, const float
 }
 
 }  // namespace g4d
+
+// ---- C entry of the stand-alone self-test library (libg4d_selftest.so; NOT part of libg4d.so / include/g4d.h) -------------
+// cfg = {N, K, layout_mode, swap_desc, a_cols_per_k, use_tma, single_pass | 16 for the bf16 variant, version_bit}
+extern "C" int g4d_selftest_umma(const int* cfg, const float* A, const float* B, float* D, void* stream) {
+    if (!cfg || !A || !B || !D) return -2;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cfg[6] == 16) return g4d::launch_umma16_selftest(cfg, A, B, D, st) == cudaSuccess ? 0 : -1;
+    static float* scratch = nullptr;
+    if (!scratch && cudaMalloc(&scratch, (size_t)2 * 128 * 128 * 4 + 256) != cudaSuccess) return -3;
+    return g4d::launch_umma_selftest(cfg, A, B, scratch, D, st) == cudaSuccess ? 0 : -1;
+}

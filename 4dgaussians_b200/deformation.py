@@ -237,6 +237,17 @@ class deform_network(nn.Module):
             off += n
         return out
 
+    def alloc_plane_grads(self) -> List[torch.Tensor]:
+        """zeroed channel-last gradient sinks for the planes only (one allocation), level-major"""
+        planes = [p for lvl in self.deformation_net.grid.grids for p in lvl]
+        buf = torch.zeros(sum(p.numel() for p in planes), device=planes[0].device, dtype=torch.float32)
+        out, off = [], 0
+        for p in planes:
+            b, c, h, w = p.shape
+            out.append(buf[off:off + p.numel()].view(b, h, w, c).permute(0, 3, 1, 2))
+            off += p.numel()
+        return out
+
     # Opt-in (default off, autograd semantics untouched): when True and every parameter already owns a `.grad` with the
     # parameter's own memory layout (e.g. views of a dp.FlatGradBucket), the backward kernels -- which ACCUMULATE with
     # atomics anyway -- add straight into those tensors and autograd receives None for the parameters: no per-view

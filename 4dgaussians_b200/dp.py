@@ -25,6 +25,7 @@ class FlatGradBucket:
         dev, dt = self.params[0].device, self.params[0].dtype
         self.numel = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(self.numel, device=dev, dtype=dt)
+        self._views: List[torch.Tensor] = []
         off = 0
         for p in self.params:
             n = p.numel()
@@ -34,14 +35,48 @@ class FlatGradBucket:
                 view = seg.view(b, h, w, c).permute(0, 3, 1, 2)
             else:
                 view = seg.view(p.shape)
-            p.grad = view
+            self._views.append(view)
             off += n
+        self.attach()
+
+    def attach(self):
+        """(Re-)install the bucket views as the parameters' ``.grad``.  Needed after ``optimizer.zero_grad(set_to_none=True)``
+        (the reference does that every step, train.py:292): autograd would otherwise allocate fresh ``.grad`` tensors outside
+        the bucket and the all-reduce would run over a stale buffer.  Prefer ``bucket.zero_()`` to ``zero_grad``."""
+        for p, v in zip(self.params, self._views):
+            p.grad = v
+
+    def detached(self) -> List[int]:
+        """indices of parameters whose ``.grad`` is no longer the bucket view (None, or a tensor autograd / the caller
+        allocated elsewhere)"""
+        return [i for i, (p, v) in enumerate(zip(self.params, self._views))
+                if p.grad is None or p.grad.data_ptr() != v.data_ptr() or p.grad.stride() != v.stride()]
 
     def zero_(self):
         self.flat.zero_()
 
-    def allreduce_mean(self, dist=None, world_size: int = 1):
-        """Sum over ranks then divide: the loss is a mean over the global batch of views (train.py:197-201)."""
+    def allreduce_mean(self, dist=None, world_size: int = 1, on_detached: str = "raise"):
+        """Sum over ranks then divide: the loss is a mean over the global batch of views (train.py:197-201).
+
+        Every parameter's ``.grad`` must still be its bucket view, otherwise the collective would reduce a stale buffer while
+        the optimizer consumes un-reduced local gradients and the ranks diverge silently.  ``on_detached``: "raise"
+        (default), or "adopt" = copy the stray gradients into the bucket and re-attach (e.g. after
+        ``zero_grad(set_to_none=True)``).  After densify / prune replaced parameters, build a NEW bucket."""
+        bad = self.detached()
+        if bad:
+            if on_detached != "adopt":
+                raise RuntimeError(
+                    "FlatGradBucket: .grad of %d parameter(s) (first: index %d) is no longer a view of the bucket -- "
+                    "optimizer.zero_grad(set_to_none=True) or a parameter swap (densify / prune) detached it. Use bucket.zero_() "
+                    "instead of zero_grad, call bucket.attach() before the backward, or rebuild the bucket after changing "
+                    "the parameter set." % (len(bad), bad[0]))
+            for i in bad:
+                g = self.params[i].grad
+                if g is not None:
+                    self._views[i].copy_(g)
+                else:
+                    self._views[i].zero_()
+            self.attach()
         if dist is not None and world_size > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
             self.flat.div_(world_size)

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define G4D_ABI_VERSION 2
+#define G4D_ABI_VERSION 3
 #define G4D_CAM_DEBUG 1
 #define G4D_CAM_NO_GRAD 2
 #define G4D_MAX_LEVELS 4
@@ -169,10 +169,34 @@ int g4d_render_forward(G4DContext *ctx, const G4DCamera *cam, const G4DDeformPar
 int g4d_render_backward(G4DContext *ctx, const G4DCamera *cam, const G4DDeformParams *prm, G4DDeformGrads *pgrads,
                         const G4DGaussians *g, const float *dL_dcolor, G4DGaussianGrads *ggrads, void *stream);
 
+/* ---- losses either side of the path -----------------------------------------------
+ * Every `*_accum` is a DEVICE float that is ADDED to (caller zeroes); `upstream` is a DEVICE float holding dL/d(loss
+ * term) (what autograd hands the backward of a scalar), NULL = 1.
+ *   g4d_l1_loss            <- utils/loss_utils.py:20-21  l1_loss(network_output, gt) = |a - b|.mean(): scale = 1 / numel
+ *   g4d_ssim               <- utils/loss_utils.py:37-66  ssim(img1, img2): 11x11 Gaussian window (sigma 1.5), zero padding,
+ *                             mean over [channels, H, W]: scale = 1 / (channels * H * W); `saved` (3 * channels * H * W
+ *                             floats, may be NULL when no backward follows) keeps the per-pixel partial derivatives
+ *   g4d_plane_regulation   <- scene/gaussian_model.py:538-577 compute_regulation(time_smoothness_weight, l1_time_planes_weight,
+ *                             plane_tv_weight) with scene/regulation.py:22-28 compute_plane_smoothness: value and, when
+ *                             `grads` is given, the plane gradients ACCUMULATED into grads->planes (other fields unused) */
+int g4d_l1_loss(G4DWorkspace *ws, const float *out, const float *gt, int64_t numel, float scale, float *loss_accum,
+                void *stream);
+int g4d_l1_loss_backward(G4DWorkspace *ws, const float *out, const float *gt, int64_t numel, float scale,
+                         const float *upstream, float *grad_out, void *stream);
+int g4d_ssim(G4DWorkspace *ws, const float *img1, const float *img2, int32_t channels, int32_t height, int32_t width,
+             float scale, float *ssim_accum, float *saved, void *stream);
+int g4d_ssim_backward(G4DWorkspace *ws, const float *img1, const float *img2, int32_t channels, int32_t height,
+                      int32_t width, float scale, const float *upstream, const float *saved, float *grad_img1,
+                      void *stream);
+int g4d_plane_regulation(G4DWorkspace *ws, const G4DDeformParams *prm, G4DDeformGrads *grads, float plane_tv_weight,
+                         float time_smoothness_weight, float l1_time_planes_weight, const float *upstream,
+                         float *loss_accum, void *stream);
+
 /* ---- options / introspection --------------------------------------------------------------------*/
-enum { G4D_OPT_SYNC_MODE = 1,  /* 1 (default): size the instance buffer exactly (one host sync per
-                                  forward, like the reference); 0: no host sync, capacity-bounded, overflow
-                                  reported by the NEXT call on the context / g4d_context_stats */
+enum { G4D_OPT_SYNC_MODE = 1,  /* 1 (default): size the instance buffer exactly (one host read of R per
+                                  forward, like the reference); 0: R stays on the device, the placement is
+                                  capacity-bounded (capacity learnt from the context's first forward + 50 %),
+                                  an overflow is reported by the NEXT call on the context / g4d_context_stats */
        G4D_OPT_INSTANCE_CAPACITY = 2, /* minimum instance capacity for no-sync mode */
        G4D_OPT_TIGHT_CULL = 3, /* 0 (default): reference tile rects; 1: drop (Gaussian,tile) pairs that
                                   provably contribute nothing (images identical, fewer instances) */
@@ -199,7 +223,8 @@ enum { G4D_BUF_DEPTH = 1,      /* float  [N]  view-space depth                  
        G4D_BUF_FINAL_T = 10,   /* float  [H,W]                                    */
        G4D_BUF_N_CONTRIB = 11, /* uint32 [H,W]                                    */
        G4D_BUF_CLAMPED = 12,   /* uint8  [N,3]                                    */
-       G4D_BUF_DEFORMED = 13   /* float  [N,11] (xyz, scale, rot, opacity) post-activation, fused path */ };
+       G4D_BUF_DEFORMED = 13,  /* float  [N,11] (xyz, scale, rot, opacity) post-activation, fused path */
+       G4D_BUF_DEFORMED_SHS = 14 /* float [N,48] deformed SH coefficients (fused path with the SHS head active) */ };
 int64_t g4d_context_read(G4DContext *ctx, int which, void *host_dst, int64_t bytes);
 
 /* per-stage device time (ms) of the LAST forward / backward on this context, measured with CUDA events on the
@@ -207,16 +232,14 @@ int64_t g4d_context_read(G4DContext *ctx, int which, void *host_dst, int64_t byt
  * not run hold 0.  Returns G4D_STAGE_COUNT or an error. */
 enum { G4D_STAGE_PREP = 0,        /* camera pack, weight pack, time-row collapse            */
        G4D_STAGE_GEOM = 1,        /* deform+activate+project (fused) or preprocess           */
-       G4D_STAGE_SCAN = 2, G4D_STAGE_EMIT = 3, G4D_STAGE_SORT = 4, G4D_STAGE_RANGES = 5,
+       G4D_STAGE_SCAN = 2,        /* bin_sort: depth order, per-(chunk,tile) counts, tile ranges, R (one cooperative launch) */
+       G4D_STAGE_EMIT = 3,        /* bin_place: stable counting placement of the instances   */
+       G4D_STAGE_SORT = 4, G4D_STAGE_RANGES = 5, /* unused since ABI 3 (no separate sort / range kernels) */
        G4D_STAGE_BLEND = 6,
        G4D_STAGE_BLEND_BWD = 7, G4D_STAGE_GEOM_BWD = 8, G4D_STAGE_DEFORM_BWD = 9,
        G4D_STAGE_COUNT = 10 };
 int g4d_context_stage_times(G4DContext *ctx, float *out_ms, int capacity);
 
-/* DEBUG: single-CTA self test of the tcgen05 building blocks: D[128,N] = A[128,K] * B[N,K]^T (3xTF32, A through TMEM,
- * B through shared memory).  cfg = {N, K, layout_mode, swap_desc, a_cols_per_k, use_tma, single_pass, version_bit}.
- * A, B, D are device fp32; not on any product path. */
-int g4d_debug_umma(G4DWorkspace *ws, const int *cfg, const float *A, const float *B, float *D, void *stream);
 /* DEBUG: mean per-CTA cycles the last tensor-core deform launch spent in each of its 12 phases (G4D_OPT_TC_DEBUG). */
 int g4d_debug_tc_cycles(G4DWorkspace *ws, double *out12);
 

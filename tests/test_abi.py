@@ -33,7 +33,7 @@ def test_exports_every_declared_symbol(lib):
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(g4d_lib.ABI_SYMBOLS) == names
-    assert lib.g4d_abi_version() == 2
+    assert lib.g4d_abi_version() == 3
 
 
 def test_struct_sizes_match_c(tmp_path):

@@ -68,3 +68,23 @@ def test_single_rank_is_identity():
     (p * 2).sum().backward()
     b.allreduce_mean(None, 1)
     assert torch.equal(p.grad, torch.full((3, 2), 2.0)) and dp.shard_views(5, 0, 1) == [0, 1, 2, 3, 4]
+
+
+def test_bucket_detects_detached_grads():
+    """zero_grad(set_to_none=True) (train.py:292) detaches .grad from the bucket; the collective must not run over
+    a stale buffer silently."""
+    p = torch.nn.Parameter(torch.ones(3, 2)); q = torch.nn.Parameter(torch.ones(4))
+    b = dp.FlatGradBucket([p, q])
+    opt = torch.optim.SGD([p, q], lr=0.1)
+    (p.sum() + q.sum()).backward()
+    b.allreduce_mean(None, 1)
+    opt.zero_grad(set_to_none=True)
+    assert b.detached() == [0, 1]
+    (3 * p.sum() + q.sum()).backward()            # autograd allocates fresh .grad tensors outside the bucket
+    with pytest.raises(RuntimeError, match="no longer a view of the bucket"):
+        b.allreduce_mean(None, 1)
+    b.allreduce_mean(None, 1, on_detached="adopt")
+    assert b.detached() == [] and torch.equal(b.flat, torch.cat([torch.full((6,), 3.0), torch.ones(4)]))
+    b.zero_(); b.attach()
+    (p.sum() * 2).backward()
+    assert torch.equal(p.grad, torch.full((3, 2), 2.0)) and p.grad.data_ptr() == b.flat.data_ptr()

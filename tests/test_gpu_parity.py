@@ -15,8 +15,8 @@ import torch
 
 from oracle import deform_ref as dr
 from oracle import raster_ref as rr
-from util_scene import (OracleRaster, cam_tuple, g4d, make_module, oracle_params_from_module, oracle_render, raster_inputs,
-                        rel_err, rel_err_bulk, synth)
+from util_scene import (OracleRaster, cam_tuple, g4d, kink_rows, make_module, oracle_params_from_module, oracle_render,
+                        raster_inputs, rel_err, rel_err_bulk, synth)
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -129,6 +129,37 @@ def test_rasterizer_edge_cases():
              opacities=torch.zeros(1, 1), scales=torch.ones(1, 3), rotations=torch.ones(1, 4), cov3D_precomp=None)
 
 
+def test_gaussian_exactly_on_tile_edges():
+    """SURVEY 8c fixture: a Gaussian whose 3-sigma extent ends EXACTLY on tile boundaries (centre at pixel (64, 48) of a
+    129 x 97 image, radius 16 -> extent [48, 80] x [32, 64]), plus neighbours; rects, bins and pixels against the oracle."""
+    cam = synth.make_camera(0.0, 129, 97, radius=4.0)
+    rc, _ = cam_tuple(cam, (0.2, 0.2, 0.2), sh_degree=0)
+    g = torch.Generator().manual_seed(5)
+    n = 40
+    m3 = (torch.rand(n, 3, generator=g) - 0.5) * 0.8
+    sc = torch.full((n, 3), 0.03); ro = torch.nn.functional.normalize(torch.randn(n, 4, generator=g), dim=-1)
+    op = torch.full((n, 1), 0.7); sh = torch.zeros(n, 16, 3); sh[:, 0] = torch.rand(n, 3, generator=g)
+    m3[0] = 0.0; ro[0] = torch.tensor([1.0, 0, 0, 0])
+    found = None
+    for k in range(100, 140):          # isotropic scale that makes ceil(3 sigma) = 16 exactly
+        sc[0] = k * 1e-3
+        f = rr.rasterize_forward(rc, m3.numpy(), sc.numpy(), ro.numpy(), op.numpy(), sh.numpy())
+        if int(f["radii"][0]) == 16:
+            found = f
+            break
+    assert found is not None
+    px, py = found["proj"].xy[0]
+    assert px == 64.0 and py == 48.0 and list(found["proj"].rect[0]) == [3, 2, 5, 4]     # (64 - 16) / 16 = 3, (48 - 16) / 16 = 2
+    rast = g4d.GaussianRasterizer(_settings(cam, (0.2, 0.2, 0.2), 0))
+    m3r = m3.cuda().requires_grad_(True)
+    color, radii, depth = rast(means3D=m3r, means2D=torch.zeros(n, 3, device="cuda"), shs=sh.cuda(), colors_precomp=None,
+                               opacities=op.cuda(), scales=sc.cuda(), rotations=ro.cuda(), cov3D_precomp=None)
+    ctx = color.grad_fn.lease.ctx
+    assert np.array_equal(radii.cpu().numpy(), found["radii"]) and np.array_equal(ctx.read("rect"), found["proj"].rect)
+    assert np.array_equal(ctx.read("sorted_ids"), found["bin"].ids) and np.array_equal(ctx.read("ranges"), found["bin"].ranges)
+    assert np.abs(color.detach().cpu().numpy() - found["color"]).max() <= IMG_TOL
+
+
 # --------------------------------------------------------------------------------------------------- deformation
 def _deform_inputs(n, seed, dev="cuda"):
     from oracle.make_golden_deform import synth_inputs
@@ -173,7 +204,8 @@ def test_deform_forward_vs_reference_golden(name):
             assert float((o.cpu() - torch.from_numpy(z[f"t{ti}_{nm}"])).abs().max()) <= 3e-5, (name, nm)
 
 
-@pytest.mark.parametrize("net,n", [("small64", 700), ("small128", 517), ("dynerf", 1500), ("dnerf", 1300), ("hypernerf", 2050)])
+@pytest.mark.parametrize("net,n", [("small64", 700), ("small128", 517), ("small128", 300), ("dynerf", 1500), ("dnerf", 1300),
+                                   ("hypernerf", 2050)])
 def test_deform_backward_vs_oracle(net, n):
     t = 0.61
     mod = make_module(net, seed=4)
@@ -198,6 +230,56 @@ def test_deform_backward_vs_oracle(net, n):
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
             continue
         e = rel_err(p.grad.cpu().numpy(), ref_g.numpy())
+        assert e <= GRAD_TOL, (k, e)
+
+
+@pytest.mark.parametrize("net,n", [("small128", 517), ("small128", 300), ("small64", 700), ("dynerf", 1500), ("hypernerf", 2050)])
+def test_deform_backward_disagrees_only_at_kinks(net, n):
+    """The loosened bounds of test_deform_backward_vs_oracle (p99.9 <= 2e-3, max <= 5e-2) are explained, not assumed:
+    (a) every Gaussian whose input gradient is off by more than 2e-3 sits at a kink of the network (a ReLU pre-activation
+        within 2e-6 of 0 or a HexPlane coordinate within 2e-4 texels of a grid line, fp64 on the oracle), where the one-sided
+        derivatives differ and an fp32 forward may land on either side;
+    (b) with the upstream gradient of exactly those Gaussians zeroed on both sides, EVERY gradient -- per-Gaussian inputs,
+        planes, all MLP weights -- agrees to the strict 2e-3 with no percentile and no 3x factor."""
+    t = 0.61
+    mod = make_module(net, seed=4)
+    cfg, prm = oracle_params_from_module(mod)
+    ins, probes = _deform_inputs(n, 6)
+    kink = kink_rows(cfg, prm, ins[0], t)
+    assert float(kink.float().mean()) <= 0.05, float(kink.float().mean())      # the statement must not be vacuous
+
+    def run(mask_rows):
+        mod.zero_grad(set_to_none=True)
+        for q in prm.leaves():
+            q.grad = None
+        pr = [p.clone() for p in probes]
+        if mask_rows:
+            for p in pr:
+                p[kink] = 0
+        dev_in = [x.clone().requires_grad_(True) for x in ins]
+        outs = mod(*dev_in, torch.tensor(t).repeat(n, 1).cuda())
+        sum((o * p.cuda()).sum() for o, p in zip(outs, pr)).backward()
+        cpu_in = [x.cpu().clone().requires_grad_(True) for x in ins]
+        w = dr.deform_forward(cfg, prm, *cpu_in, t)
+        sum((o * p).sum() for o, p in zip(w, pr)).backward()
+        return dev_in, cpu_in
+    # (a) unmasked: the rows that disagree are kink rows
+    dev_in, cpu_in = run(False)
+    for a, b, nm in zip(dev_in, cpu_in, ("xyz", "scales", "rot", "opacity", "shs")):
+        got, ref = a.grad.cpu().numpy().reshape(n, -1), b.grad.numpy().reshape(n, -1)
+        row_err = np.abs(got - ref).max(axis=1) / max(1e-3, np.abs(ref).max())
+        bad = row_err > GRAD_TOL
+        assert not np.any(bad & ~kink.numpy()), (nm, int(bad.sum()), int((bad & ~kink.numpy()).sum()), float(row_err[~kink.numpy()].max()))
+    # (b) kink rows silenced: strict agreement everywhere
+    dev_in, cpu_in = run(True)
+    for a, b, nm in zip(dev_in, cpu_in, ("xyz", "scales", "rot", "opacity", "shs")):
+        e = rel_err(a.grad.cpu().numpy(), b.grad.numpy())
+        assert e <= GRAD_TOL, (nm, e)
+    osd = dr.params_to_state_dict(prm)
+    for k, p in mod.named_parameters():
+        if k not in osd or not p.requires_grad or osd[k].grad is None:
+            continue
+        e = rel_err(p.grad.cpu().numpy(), osd[k].grad.numpy())
         assert e <= GRAD_TOL, (k, e)
 
 
@@ -279,6 +361,52 @@ def test_fused_render_backward(ci, stage):
                 assert e <= 3 * GRAD_TOL, (k, e)
     else:
         assert all(p.grad is None for p in mod.parameters())
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
+def test_fused_render_every_sh_degree_and_points_outside_aabb(deg):
+    """SURVEY 8c fixtures: active_sh_degree 0..3 through the FUSED path (the tensor-core kernel evaluates the SH colour in
+    its own epilogue), with an aabb smaller than the point cloud so that a third of the Gaussians sample the HexPlane
+    through the border clamp."""
+    c = dict(FUSED_CASES[2]); c["deg"] = deg
+    scene = synth.make_scene(c["n"], seed=11, scale_mean=c["scale"])
+    aabb = scene["aabb"] * 0.8                                  # ~1/3 of the points now lie outside the box
+    mod = make_module(c["net"], seed=2, aabb=aabb)
+    pc = synth.SyntheticGaussianModel(scene, mod, sh_degree=deg, requires_grad=False)
+    cam = synth.make_camera(c["theta"], c["wh"][0], c["wh"][1], radius=c["radius"], time=c["t"])
+    inside = ((scene["xyz"] <= aabb[0]) & (scene["xyz"] >= aabb[1])).all(dim=1)
+    assert 0.2 < float((~inside).float().mean()) < 0.8
+    with torch.no_grad():
+        out = g4d.render(cam, pc, _Pipe(), torch.tensor(c["bg"], device="cuda"))
+        cfg, prm = oracle_params_from_module(mod)
+        color, depth, radii, rc, _ = oracle_render(cfg, prm, scene, cam, c["t"], c["bg"], sh_degree=deg)
+    err = (out["render"].cpu() - color).abs()
+    assert float((err > IMG_TOL).float().mean()) <= 1e-3 and float(err.max()) <= 1e-2 and float(err.median()) <= 1e-6
+    assert (out["radii"].cpu().numpy() != radii.numpy()).mean() <= 2e-3
+
+
+def test_batched_views_single_backward_matches_per_view_backward():
+    """The reference's batch_size > 1 pattern (train.py:161-225): several render() forwards, ONE loss over the stacked
+    images, a single backward.  Every view keeps its own context (records, ReLU bits, staged features) while the workspace
+    scratch is shared; gradients must equal the sum of per-view backward passes."""
+    c = FUSED_CASES[2]
+    views = [(c["theta"], 0.2), (c["theta"] + 40.0, 0.5), (c["theta"] - 70.0, 0.9)]
+    weights = [torch.rand(3, c["wh"][1], c["wh"][0], generator=torch.Generator().manual_seed(i)).cuda() for i in range(len(views))]
+    grads = []
+    for mode in ("stacked", "per_view"):
+        scene, mod, pc, _ = _fused_setup(c)
+        bg = torch.tensor(c["bg"], device="cuda")
+        cams = [synth.make_camera(th, c["wh"][0], c["wh"][1], radius=c["radius"], time=t) for th, t in views]
+        if mode == "stacked":
+            imgs = [g4d.render(cam, pc, _Pipe, bg)["render"] for cam in cams]
+            (torch.stack(imgs) * torch.stack(weights)).sum().backward()
+        else:
+            for cam, w_ in zip(cams, weights):
+                (g4d.render(cam, pc, _Pipe, bg)["render"] * w_).sum().backward()
+        grads.append([p.grad.clone() for p in pc.gaussian_parameters()] + [p.grad.clone() for p in mod.flat_parameters() if p.grad is not None])
+    assert len(grads[0]) == len(grads[1])
+    for a, b in zip(*grads):
+        assert float((a - b).abs().max()) <= 2e-5 * max(1e-3, float(b.abs().max())), float((a - b).abs().max())
 
 
 def test_fused_grad_accumulation_matches_autograd_accumulation():
@@ -373,14 +501,14 @@ def test_full_size_binning_properties():
 def test_tcgen05_building_blocks_selftest():
     """D[128,N] = A[128,K] B[N,K]^T through TMEM / tcgen05.mma kind::tf32 with 3xTF32: fp32-level accuracy."""
     import ctypes as C
-    lib = g4d._lib.load()
-    ws = g4d._lib.Workspace.get(0)
+    lib = g4d._lib.load_selftest()      # own tiny library: the self test is not part of the product libg4d.so
     for (N, K, tma) in ((128, 128, 1), (128, 32, 1), (48, 64, 0), (16, 64, 1)):
         gen = torch.Generator().manual_seed(N + K)
         A = torch.randn(128, K, generator=gen).cuda(); B = torch.randn(N, K, generator=gen).cuda()
         D = torch.zeros(128, N, device="cuda")
         cfg = (C.c_int * 8)(N, K, 0, 0, 1, tma, 0, 1)
-        g4d._lib.check(lib.g4d_debug_umma(ws.handle, cfg, A.data_ptr(), B.data_ptr(), D.data_ptr(), 0), "g4d_debug_umma")
+        assert lib.g4d_selftest_umma(cfg, A.data_ptr(), B.data_ptr(), D.data_ptr(), 0) == 0
+        torch.cuda.synchronize()
         ref = A.double() @ B.double().t()
         assert float((D.double() - ref).abs().max() / ref.abs().max()) <= 2e-6, (N, K)
 

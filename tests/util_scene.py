@@ -110,3 +110,40 @@ def rel_err_bulk(got, ref, floor=1e-3, q=99.9):
     got = np.asarray(got, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
     e = np.abs(got - ref).reshape(-1) / max(floor, np.abs(ref).max())
     return float(np.percentile(e, q)), float(e.max())
+
+
+def kink_rows(cfg, prm, xyz, t, delta_act=2e-6, delta_grid=2e-4):
+    """[N] bool: Gaussians sitting within rounding distance of a NON-DIFFERENTIABLE point of the deformation network,
+    evaluated in fp64 on the oracle: a pre-activation of an active ReLU within delta_act of 0, or a HexPlane sample
+    coordinate within delta_grid (in texels) of a grid line, where floor() picks the bilinear cell.  On such rows an fp32
+    implementation may legitimately take the other branch, and the gradient is then the (equally valid) one-sided
+    derivative of the neighbouring piece.  Everywhere else gradients must agree to the stated tolerance."""
+    from oracle import deform_ref as dr
+    with torch.no_grad():
+        x64 = xyz.detach().double().cpu()
+        n = x64.shape[0]
+        planes = [[p.detach().double() for p in lvl] for lvl in prm.planes]
+        aabb = prm.aabb.detach().double()
+        tt = torch.full((n,), float(t), dtype=torch.float64)
+        p = dr.normalize(x64, aabb)
+        q = torch.cat([p, tt.reshape(-1, 1)], dim=-1)
+        mask = torch.zeros(n, dtype=torch.bool)
+        for l, lvl in enumerate(planes):
+            for k, (c0, c1) in enumerate(dr.PLANE_AXES):
+                _, _, H, W = lvl[k].shape
+                for coord, size in ((q[:, c0], W), (q[:, c1], H)):
+                    g = (coord + 1.0) / 2.0 * (size - 1)          # unclamped: far outside the aabb the border rule is smooth
+                    mask |= ((g - torch.round(g)).abs() < delta_grid) & (g > -delta_grid) & (g < size - 1 + delta_grid)
+        feat = dr.hexplane_features(planes, x64, aabb, tt)
+        hidden = feat @ prm.w0.detach().double().t() + prm.b0.detach().double()
+        mask |= (hidden.abs() < delta_act).any(dim=1)
+        active = {"pos": not cfg.no_dx, "scales": not cfg.no_ds, "rotations": not cfg.no_dr, "opacity": not cfg.no_do,
+                  "shs": not cfg.no_dshs}
+        a = torch.relu(hidden)
+        for name, on in active.items():
+            if not on:
+                continue
+            w1, b1, _, _ = prm.heads[name]
+            z = a @ w1.detach().double().t() + b1.detach().double()
+            mask |= (z.abs() < delta_act).any(dim=1)
+    return mask

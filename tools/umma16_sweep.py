@@ -10,7 +10,7 @@ sys.path.insert(0, ROOT)
 import torch
 
 g4d = importlib.import_module("4dgaussians_b200")
-lib = g4d._lib.load()
+lib = g4d._lib.load_selftest()
 ws = g4d._lib.Workspace.get(0)
 cases = []
 for (N, K) in ((128, 128), (48, 64), (128, 48), (16, 128)):
@@ -25,7 +25,7 @@ for c in (only or cases):
     A = torch.randn(128, K, generator=g).cuda(); B = torch.randn(N, K, generator=g).cuda()
     D = torch.full((128, N), float("nan"), device="cuda")
     try:
-        rc = lib.g4d_debug_umma(ws.handle, (C.c_int * 8)(*c), A.data_ptr(), B.data_ptr(), D.data_ptr(), 0)
+        rc = lib.g4d_selftest_umma((C.c_int * 8)(*c), A.data_ptr(), B.data_ptr(), D.data_ptr(), 0)
         torch.cuda.synchronize()
         ref = A.double() @ B.double().t()
         err = (D.double() - ref).abs().max().item() / ref.abs().max().item()

@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 def one(cfg):
     import torch
     g4d = importlib.import_module("4dgaussians_b200")
-    lib = g4d._lib.load()
+    lib = g4d._lib.load_selftest()
     ws = g4d._lib.Workspace.get(0)
     N, K = cfg[0], cfg[1]
     g = torch.Generator().manual_seed(0)
@@ -22,7 +22,7 @@ def one(cfg):
     B = (torch.randn(N, K, generator=g)).cuda()
     D = torch.full((128, N), float("nan"), device="cuda")
     arr = (C.c_int * 8)(*cfg)
-    rc = lib.g4d_debug_umma(ws.handle, arr, A.data_ptr(), B.data_ptr(), D.data_ptr(), 0)
+    rc = lib.g4d_selftest_umma(arr, A.data_ptr(), B.data_ptr(), D.data_ptr(), 0)
     torch.cuda.synchronize()
     ref = (A.double() @ B.double().t())
     err = (D.double() - ref).abs().max().item()
