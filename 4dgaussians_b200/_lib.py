@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "g4d_context_destroy", "g4d_context_stats", "g4d_deform_forward", "g4d_deform_backward", "g4d_rasterize_forward",
     "g4d_rasterize_backward", "g4d_render_forward", "g4d_render_backward", "g4d_workspace_set_option", "g4d_context_read",
     "g4d_context_stage_times", "g4d_debug_tc_cycles", "g4d_l1_loss", "g4d_l1_loss_backward", "g4d_ssim", "g4d_ssim_backward",
-    "g4d_plane_regulation",
+    "g4d_plane_regulation", "g4d_dist2_knn3", "g4d_adam_step",
 ]
 
 fp = C.c_void_p   # device pointers travel as integers
@@ -70,6 +70,10 @@ class Gaussians(C.Structure):
 class GaussianGrads(C.Structure):
     _fields_ = [("xyz", fp), ("scaling", fp), ("rotation", fp), ("opacity", fp), ("features_dc", fp),
                 ("features_rest", fp), ("means2D", fp)]
+
+
+class AdamSegment(C.Structure):
+    _fields_ = [("begin", C.c_int64), ("end", C.c_int64), ("lr", C.c_float), ("reserved", C.c_float)]
 
 
 class Stats(C.Structure):
@@ -128,6 +132,9 @@ def load():
         lib.g4d_ssim_backward.argtypes = [C.c_void_p, fp, fp, C.c_int32, C.c_int32, C.c_int32, C.c_float, fp, fp, fp, C.c_void_p]
         lib.g4d_plane_regulation.argtypes = [C.c_void_p, C.POINTER(DeformParams), C.POINTER(DeformGrads), C.c_float, C.c_float,
                                              C.c_float, fp, fp, C.c_void_p]
+        lib.g4d_adam_step.argtypes = [C.c_void_p, fp, fp, fp, fp, C.c_int64, C.POINTER(AdamSegment), C.c_int32, C.c_float, C.c_float,
+                                      C.c_float, C.c_int64, C.c_float, C.c_void_p]
+        lib.g4d_dist2_knn3.argtypes = [C.c_void_p, C.c_int64, fp, fp, C.c_void_p]
         if lib.g4d_abi_version() != ABI_VERSION:
             raise G4DError("libg4d.so ABI version mismatch")
         _lib = lib
@@ -176,12 +183,15 @@ class Workspace:
         check(load().g4d_workspace_set_option(self.handle, option, int(value)), "g4d_workspace_set_option")
 
     def acquire_context(self) -> "Context":
-        if self._free_contexts:
-            return self._free_contexts.pop()
+        while self._free_contexts:
+            ctx = self._free_contexts.pop()
+            if ctx.handle:
+                return ctx
         return Context(self)
 
     def release_context(self, ctx: "Context"):
-        self._free_contexts.append(ctx)
+        if ctx.handle:      # (a context finalised in the same GC pass as its lease must not be resurrected into the pool)
+            self._free_contexts.append(ctx)
 
 
 class Context:

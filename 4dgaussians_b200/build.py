@@ -27,6 +27,8 @@ UNITS = {
     "g4d_raster.cu": [],
     "g4d_bin.cu": [],
     "g4d_loss.cu": [],
+    "g4d_knn.cu": ["-fmad=false"],
+    "g4d_optim.cu": [],
     "g4d_backward.cu": [],
     "g4d_api.cu": [],
     "g4d_deform_tc.cu": ["-fmad=false"],

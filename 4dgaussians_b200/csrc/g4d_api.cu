@@ -237,8 +237,11 @@ int deform_backward_dispatch(G4DWorkspace* ws, const DeformDesc& d, const G4DDef
         return G4D_OK;
     }
     if ((rc = refresh_packed(ws, prm, st)) != G4D_OK) return rc;
-    G4D_CUDA(ws->scratch.ensure(deform_backward_scratch_bytes(d, n)));
-    G4D_CUDA(launch_deform_backward(d, *prm, *grads, time, n, xyz, go, gi, ws->scratch.as<float>(), ws->sm_count, st));
+    DeformDesc df = d;                       // the transposes may just have been (re)allocated: take the current pointers
+    df.w0t = ws->w0t;
+    for (int h = 0; h < G4D_NUM_HEADS; ++h) df.w1t[h] = ws->w1t[h];
+    G4D_CUDA(ws->scratch.ensure(deform_backward_scratch_bytes(df, n)));
+    G4D_CUDA(launch_deform_backward(df, *prm, *grads, time, n, xyz, go, gi, ws->scratch.as<float>(), ws->sm_count, st));
     return G4D_OK;
 }
 
@@ -519,14 +522,14 @@ int g4d_deform_forward(G4DWorkspace* ws, const G4DDeformParams* prm, int64_t n, 
     if ((prm->head_mask & G4D_HEAD_SHS) && n > 0 && (!shs || !out_shs)) return fail(G4D_ERR_ARG, "shs / out_shs required when the SHS head is active");
     cudaStream_t st = (cudaStream_t)stream;
     G4D_CUDA(cudaSetDevice(ws->device));
-    if ((rc = refresh_packed(ws, prm, st)) != G4D_OK) return rc;
     float* trow[G4D_MAX_LEVELS][3] = {};
     if ((rc = setup_trow(ws->trow, trow, prm)) != G4D_OK) return rc;
     G4D_CUDA(launch_collapse_time_rows(*prm, nullptr, time, false, trow, st));
+    const bool use_tc = ws->tensor_cores && tc_deform_supported(make_desc(ws, prm, trow));
+    if (!use_tc && (rc = refresh_packed(ws, prm, st)) != G4D_OK) return rc;     // FP32 transposes: only the FFMA kernels read them
     const DeformDesc d = make_desc(ws, prm, trow);
     GeomBuffers g{};
     FusedOutputs fo{};
-    const bool use_tc = ws->tensor_cores && tc_deform_supported(d);
     if (use_tc && (rc = refresh_tc(ws, prm, st)) != G4D_OK) return rc;
     if (use_tc && (rc = attach_tc_debug(ws, st)) != G4D_OK) return rc;
     if ((rc = attach_relu_bits(ws, use_tc, true, relu_bits, n, st)) != G4D_OK) return rc;
@@ -687,11 +690,10 @@ int g4d_deform_backward(G4DWorkspace* ws, const G4DDeformParams* prm, G4DDeformG
     if (n < 0 || (n > 0 && !xyz)) return fail(G4D_ERR_ARG, "xyz required");
     cudaStream_t st = (cudaStream_t)stream;
     G4D_CUDA(cudaSetDevice(ws->device));
-    if ((rc = refresh_packed(ws, prm, st)) != G4D_OK) return rc;
     float* trow[G4D_MAX_LEVELS][3] = {};
     if ((rc = setup_trow(ws->trow, trow, prm)) != G4D_OK) return rc;
     G4D_CUDA(launch_collapse_time_rows(*prm, nullptr, time, false, trow, st));
-    const DeformDesc d = make_desc(ws, prm, trow);
+    const DeformDesc d = make_desc(ws, prm, trow);      // (the dispatcher refreshes the weight images its path needs)
     const float* go[G4D_NUM_HEADS] = {g_out_xyz, g_out_scaling, g_out_rotation, g_out_opacity, g_out_shs};
     float* gi[G4D_NUM_HEADS] = {g_in_xyz, g_in_scaling, g_in_rotation, g_in_opacity, g_in_shs};
     return deform_backward_dispatch(ws, d, prm, grads, time, n, xyz, go, gi, relu_bits, nullptr, st);
@@ -725,7 +727,6 @@ int g4d_render_forward(G4DContext* c, const G4DCamera* cam, const G4DDeformParam
         StageTimer tm(c, G4D_STAGE_PREP, st);
         G4D_CUDA(launch_pack_camera(*cam, dcam, st));
         if (prm) {
-            if ((rc = refresh_packed(ws, prm, st)) != G4D_OK) return rc;
             if ((rc = setup_trow(c->trow, c->trow_ptr, prm)) != G4D_OK) return rc;
             G4D_CUDA(launch_collapse_time_rows(*prm, dcam, cam->time, false, c->trow_ptr, st));
         }
@@ -733,8 +734,9 @@ int g4d_render_forward(G4DContext* c, const G4DCamera* cam, const G4DDeformParam
     StageTimer* geom_tm = new StageTimer(c, G4D_STAGE_GEOM, st);
     struct Del { StageTimer*& p; ~Del() { delete p; p = nullptr; } } del{geom_tm};
     if (prm) {
+        const bool use_tc = ws->tensor_cores && tc_deform_supported(make_desc(ws, prm, c->trow_ptr));
+        if (!use_tc && (rc = refresh_packed(ws, prm, st)) != G4D_OK) return rc;
         const DeformDesc d = make_desc(ws, prm, c->trow_ptr);
-        const bool use_tc = ws->tensor_cores && tc_deform_supported(d);
         if (use_tc && (rc = refresh_tc(ws, prm, st)) != G4D_OK) return rc;
         if (use_tc && (rc = attach_tc_debug(ws, st)) != G4D_OK) return rc;
         c->relu_saved = use_tc && !(cam->debug & G4D_CAM_NO_GRAD);
@@ -868,6 +870,31 @@ int g4d_plane_regulation(G4DWorkspace* ws, const G4DDeformParams* prm, G4DDeform
     G4D_CUDA(cudaSetDevice(ws->device));
     G4D_CUDA(launch_plane_regulation(*prm, grads, plane_tv_weight, time_smoothness_weight, l1_time_planes_weight, upstream, loss_accum,
                                      ws->sm_count, (cudaStream_t)stream));
+    return G4D_OK;
+}
+
+int g4d_adam_step(G4DWorkspace* ws, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel,
+                  const G4DAdamSegment* segments, int32_t num_segments, float beta1, float beta2, float eps, int64_t step,
+                  float grad_scale, void* stream) {
+    if (!ws || numel < 0 || (numel > 0 && (!param || !grad || !exp_avg || !exp_avg_sq || !segments)) || step < 1)
+        return fail(G4D_ERR_ARG, "g4d_adam_step: bad argument");
+    if ((numel & 3) || num_segments < 0 || num_segments > G4D_ADAM_MAX_SEGMENTS)
+        return fail(G4D_ERR_ARG, "g4d_adam_step: numel must be a multiple of 4 and at most 16 segments");
+    for (int i = 0; i < num_segments; ++i)
+        if (segments[i].begin < 0 || segments[i].end < segments[i].begin || segments[i].end > numel || (i && segments[i].begin < segments[i - 1].end))
+            return fail(G4D_ERR_ARG, "g4d_adam_step: segments must be sorted, disjoint and inside [0, numel)");
+    G4D_CUDA(cudaSetDevice(ws->device));
+    G4D_CUDA(launch_adam_flat(param, grad, exp_avg, exp_avg_sq, numel, segments, num_segments, beta1, beta2, eps, step, grad_scale,
+                              ws->sm_count, (cudaStream_t)stream));
+    return G4D_OK;
+}
+
+int g4d_dist2_knn3(G4DWorkspace* ws, int64_t n, const float* xyz, float* out_mean_dist2, void* stream) {
+    if (!ws || n < 0 || (n > 0 && (!xyz || !out_mean_dist2))) return fail(G4D_ERR_ARG, "g4d_dist2_knn3: bad argument");
+    if (n >= (1ll << 31)) return fail(G4D_ERR_ARG, "n too large");
+    G4D_CUDA(cudaSetDevice(ws->device));
+    G4D_CUDA(ws->scratch.ensure(knn_scratch_bytes(n)));
+    G4D_CUDA(launch_knn_dist2(n, xyz, out_mean_dist2, ws->scratch.p, ws->sm_count, (cudaStream_t)stream));
     return G4D_OK;
 }
 

@@ -1,18 +1,26 @@
 // g4d_bin.cu -- tile binning as TWO hand-written launches, no library sort, no host round trip:
 //
 //   bin_sort_kernel  (cooperative, persistent, one 1024-thread CTA per SM, grid-wide syncs between phases)
-//       1. LSD radix sort (4 x 8 bits, stable) of the VISIBLE Gaussians by the bits of their view-space depth; the first
-//          pass compacts away the invisible ones while it scatters.  Ties keep Gaussian-index order.   -> perm[n_visible]
+//       0. min / max of the visible Gaussians' depth bits -> the keys are sorted as (bits - min): 24-27 significant bits
+//          instead of 32, i.e. 3 radix passes instead of 4
+//       1. LSD radix sort (9-bit digits, stable) of the VISIBLE Gaussians by depth; the first pass compacts away the
+//          invisible ones while it scatters.  Ties keep Gaussian-index order.                            -> perm[n_visible]
 //       2. the depth-ordered list is cut into one chunk per CTA with equal numbers of tile instances (near Gaussians cover
 //          many more tiles than far ones)                                                                  -> chunk_start
-//       3. every chunk counts its instances per tile (shared-memory histogram)                            -> M[chunk][tile]
-//       4. per tile: exclusive scan over the chunks, then an exclusive scan over the tiles             -> ranges[tile], R
-//   bin_place_kernel (one CTA per chunk)
+//       3. every chunk counts its instances per tile (shared-memory histogram)                            -> M[tile][chunk]
+//       4. per tile: exclusive scan over the chunks (one warp per tile), then an exclusive scan over the tiles
+//                                                                                                -> ranges[tile], R
+//   bin_place_kernel (one 1024-thread CTA per chunk, tile rows processed in bands that fit shared memory)
 //       every warp walks its share of the chunk IN DEPTH ORDER and drops each (Gaussian, tile) instance at
-//       tile_start[tile] + M[chunk][tile] + (instances of earlier warps of the chunk) + (its own running count): a stable
+//       tile_start[tile] + M[tile][chunk] + (instances of earlier warps of the chunk) + (its own running count): a stable
 //       counting placement.  Because the Gaussians arrive depth-sorted, every tile's segment comes out depth-sorted: the
 //       reference's sort of R 64-bit (tile | depth) keys (6 radix passes over 12 B x R) is replaced by ONE 4-byte write per
 //       instance, and the sorted list / tile ranges are bit-identical to the reference's (tests: sorted ids, ranges, keys).
+//
+// Both walks are PAIR-parallel: a warp flattens the (Gaussian, tile) pairs of 32 consecutive Gaussians (prefix sum of their
+// tile counts, binary search by shuffle) and handles 32 pairs per step whatever the rect sizes -- a far chunk holds thousands
+// of 1-4 tile Gaussians, a near one a few 1000-tile ones.  Pairs of one step that fall on the same tile are ranked with
+// match.any in lane (= depth) order.
 //
 // The instance count R never has to visit the host: the placement clamps to the buffer capacity and the overflow is
 // reported through the context (G4D_OPT_SYNC_MODE = 0); in the default exact mode the host reads R between the two
@@ -32,7 +40,8 @@ namespace g4d {
 namespace {
 
 constexpr int kBinThreads = 1024;
-constexpr int kRadix = 256;
+constexpr int kDigitBits = 9;
+constexpr int kRadix = 1 << kDigitBits;
 constexpr uint32_t kSortSmemBytes = 32u * kRadix * 4u;   // per-warp digit counters of one scatter round
 
 // inclusive scan of v over the 1024 threads of the block; total = block sum.  s_w: 33 words of shared scratch.
@@ -65,16 +74,19 @@ __device__ __forceinline__ uint32_t block_scan_incl(uint32_t v, uint32_t* s_w, u
 
 struct SortShared {
     uint32_t hist[kRadix];
-    uint32_t part[8 * kRadix];   // [0,4): totals of a quarter of the CTAs per digit, [4,8): totals of the CTAs before mine
+    uint32_t part[4 * kRadix];   // [0,2): totals of one half of the CTAs per digit, [2,4): totals of the CTAs before mine
     uint32_t base[kRadix];       // running output position per digit for my slice
     uint32_t sw[33];
+    uint32_t mm[2];
 };
 
-// One stable LSD pass.  FIRST: input = the N raw Gaussians (key = depth bits, value = index), invisible ones are dropped.
+// One stable LSD pass over digit (key >> shift) & 511.  FIRST: input = the N raw Gaussians (key = depth bits - kmin,
+// value = index), invisible ones are dropped.
 template <bool FIRST, bool LAST>
 __device__ __forceinline__ uint32_t radix_pass(const BinSortArgs& a, cg::grid_group& grid, SortShared& s, uint32_t* wc, int shift,
-                                               uint32_t count, const uint32_t* __restrict__ kin, const uint32_t* __restrict__ vin,
-                                               uint32_t* __restrict__ kout, uint32_t* __restrict__ vout) {
+                                               uint32_t kmin, uint32_t count, const uint32_t* __restrict__ kin,
+                                               const uint32_t* __restrict__ vin, uint32_t* __restrict__ kout,
+                                               uint32_t* __restrict__ vout) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t G = gridDim.x, c = blockIdx.x;
     const uint32_t per = (count + G - 1) / G;
@@ -82,7 +94,7 @@ __device__ __forceinline__ uint32_t radix_pass(const BinSortArgs& a, cg::grid_gr
     auto load = [&](uint32_t i, uint32_t& key, uint32_t& val) -> bool {
         if (FIRST) {
             if (a.tiles_touched[i] == 0) return false;
-            key = __float_as_uint(a.rec2[i].y);   // depth > 0.2: sign bit clear, integer order = float order
+            key = __float_as_uint(a.rec2[i].y) - kmin;   // depth > 0.2: sign bit clear, integer order = float order
             val = i;
             return true;
         }
@@ -94,15 +106,15 @@ __device__ __forceinline__ uint32_t radix_pass(const BinSortArgs& a, cg::grid_gr
     __syncthreads();
     for (uint32_t i = lo + tid; i < hi; i += kBinThreads) {
         uint32_t key, val;
-        if (load(i, key, val)) atomicAdd(&s.hist[(key >> shift) & 255u], 1u);
+        if (load(i, key, val)) atomicAdd(&s.hist[(key >> shift) & (kRadix - 1)], 1u);
     }
     __syncthreads();
     if (tid < kRadix) a.H[c * kRadix + tid] = s.hist[tid];
     grid.sync();
     // ---- (b) my output base per digit = (all smaller digits of every CTA) + (same digit of the CTAs before me)
     {
-        const uint32_t d = tid & 255u, q = tid >> 8;
-        const uint32_t qs = (G + 3) / 4, c0 = q * qs, c1 = min(G, c0 + qs);
+        const uint32_t d = tid & (kRadix - 1), q = tid >> kDigitBits;       // 2 halves of the CTA range
+        const uint32_t qs = (G + 1) / 2, c0 = q * qs, c1 = min(G, c0 + qs);
         uint32_t tot = 0, bef = 0;
         for (uint32_t cc = c0; cc < c1; ++cc) {
             const uint32_t v = __ldcg(a.H + cc * kRadix + d);
@@ -110,14 +122,11 @@ __device__ __forceinline__ uint32_t radix_pass(const BinSortArgs& a, cg::grid_gr
             if (cc < c) bef += v;
         }
         s.part[q * kRadix + d] = tot;
-        s.part[(4 + q) * kRadix + d] = bef;
+        s.part[(2 + q) * kRadix + d] = bef;
     }
     __syncthreads();
     uint32_t tot = 0, bef = 0;
-    if (tid < kRadix) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { tot += s.part[q * kRadix + tid]; bef += s.part[(4 + q) * kRadix + tid]; }
-    }
+    if (tid < kRadix) { tot = s.part[tid] + s.part[kRadix + tid]; bef = s.part[2 * kRadix + tid] + s.part[3 * kRadix + tid]; }
     uint32_t total;
     const uint32_t incl = block_scan_incl(tot, s.sw, total);
     if (tid < kRadix) s.base[tid] = incl - tot + bef;
@@ -129,8 +138,8 @@ __device__ __forceinline__ uint32_t radix_pass(const BinSortArgs& a, cg::grid_gr
         const uint32_t i = b0 + tid;
         uint32_t key = 0, val = 0;
         const bool valid = i < hi && load(i, key, val);
-        const uint32_t digit = (key >> shift) & 255u;
-        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? digit : (256u + (uint32_t)lane));
+        const uint32_t digit = (key >> shift) & (kRadix - 1);
+        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? digit : ((uint32_t)kRadix + (uint32_t)lane));
         const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
         if (valid && rank == 0) wc[warp * kRadix + digit] = __popc(peers);
         __syncthreads();
@@ -156,30 +165,61 @@ __device__ __forceinline__ uint32_t radix_pass(const BinSortArgs& a, cg::grid_gr
     return total;
 }
 
-// number of tile instances of the Gaussians of one chunk, per tile of the band [y0, y1): shared-memory histogram
-__device__ __forceinline__ void count_chunk_band(const BinSortArgs& a, uint32_t cs, uint32_t ce, int y0, int y1, uint32_t* cnt) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t k0 = cs + warp * 32u; k0 < ce; k0 += kBinThreads) {
+// ---- pair-parallel walk ------------------------------------------------------------------------------------------------
+// Visits the (Gaussian, tile) pairs of perm[ks, ke) restricted to the tile rows [y0, y1), in list order, 32 pairs per step:
+// f(active, tile index inside the band, Gaussian id) is called by all 32 lanes (inactive lanes pad the last step).
+template <class F>
+__device__ __forceinline__ void walk_pairs(const uint32_t* __restrict__ perm, const uint2* __restrict__ rect,
+                                           const float4* __restrict__ rec0, const float4* __restrict__ rec1, int tight, uint32_t ks,
+                                           uint32_t ke, int y0, int y1, int grid_x, F&& f) {
+    const int lane = threadIdx.x & 31;
+    for (uint32_t k0 = ks; k0 < ke; k0 += 32u) {
         const uint32_t k = k0 + lane;
-        const bool valid = k < ce;
+        uint32_t gi = 0, xy = 0, w = 1, nt = 0;
         float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-        uint2 rc = make_uint2(0u, 0u);
-        if (valid) {
-            const uint32_t gi = a.perm[k];
-            rc = a.rect[gi];
-            if (a.tight) { r0 = a.rec0[gi]; r1 = a.rec1[gi]; }
+        if (k < ke) {
+            gi = perm[k];
+            const uint2 rc = rect[gi];
+            const int minx = (int)(rc.x & 0xFFFFu), maxx = (int)(rc.y & 0xFFFFu);
+            const int miny = max((int)(rc.x >> 16), y0), maxy = min((int)(rc.y >> 16), y1);
+            w = (uint32_t)max(maxx - minx, 1);
+            nt = maxy > miny ? (uint32_t)((maxx - minx) * (maxy - miny)) : 0u;
+            xy = (uint32_t)minx | ((uint32_t)miny << 16);
+            if (tight) { r0 = rec0[gi]; r1 = rec1[gi]; }
         }
-        uint32_t todo = __ballot_sync(0xffffffffu, valid);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const TileJob j = bcast_job(r0, r1, rc, src, y0, y1);
-            for (int b = 0; b < j.ntiles; b += 32) {
-                const int t = b + lane;
-                const int ty = t / j.w, tx = t - ty * j.w;
-                if (t < j.ntiles && (!a.tight || tile_contributes(j.r0, j.r1, j.minx + tx, j.miny + ty)))
-                    atomicAdd(&cnt[(j.miny + ty - y0) * a.grid_x + j.minx + tx], 1u);
+        uint32_t incl = nt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t excl = incl - nt;
+        for (uint32_t b = 0; b < total; b += 32u) {
+            const uint32_t flat = b + lane;
+            const bool active = flat < total;
+            int g = 0;                       // owner = number of Gaussians whose inclusive prefix is <= flat
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) {
+                const uint32_t v = __shfl_sync(0xffffffffu, incl, (g + sft - 1) & 31);
+                if (v <= flat) g += sft;
             }
+            g &= 31;
+            const uint32_t oxy = __shfl_sync(0xffffffffu, xy, g), ow = __shfl_sync(0xffffffffu, w, g);
+            const uint32_t oex = __shfl_sync(0xffffffffu, excl, g), oid = __shfl_sync(0xffffffffu, gi, g);
+            const uint32_t t = active ? flat - oex : 0u;
+            const uint32_t ty = t / ow, tx = t - ty * ow;
+            const int x = (int)(oxy & 0xFFFFu) + (int)tx, y = (int)(oxy >> 16) + (int)ty;
+            bool on = active;
+            if (tight) {
+                float4 q0, q1;
+                q0.x = __shfl_sync(0xffffffffu, r0.x, g); q0.y = __shfl_sync(0xffffffffu, r0.y, g);
+                q0.z = __shfl_sync(0xffffffffu, r0.z, g); q0.w = __shfl_sync(0xffffffffu, r0.w, g);
+                q1.x = __shfl_sync(0xffffffffu, r1.x, g); q1.y = __shfl_sync(0xffffffffu, r1.y, g);
+                q1.z = 0.f; q1.w = 0.f;
+                on = on && tile_contributes(q0, q1, x, y);
+            }
+            f(on, (y - y0) * grid_x + x, oid);
         }
     }
 }
@@ -190,15 +230,55 @@ __global__ void __launch_bounds__(kBinThreads, 1) bin_sort_kernel(BinSortArgs a)
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) uint32_t dyn[];   // scatter: per-warp digit counters; count: tile histogram of a band
     __shared__ SortShared s;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t G = gridDim.x, c = blockIdx.x;
     const uint32_t N = (uint32_t)a.n;
 
-    // ---- 1. depth order of the visible Gaussians
-    const uint32_t nvis = radix_pass<true, false>(a, grid, s, dyn, 0, N, nullptr, nullptr, a.kA, a.vA);
-    radix_pass<false, false>(a, grid, s, dyn, 8, nvis, a.kA, a.vA, a.kB, a.vB);
-    radix_pass<false, false>(a, grid, s, dyn, 16, nvis, a.kB, a.vB, a.kA, a.vA);
-    radix_pass<false, true>(a, grid, s, dyn, 24, nvis, a.kA, a.vA, nullptr, a.perm);
+    // ---- 0. range of the visible depth bits
+    {
+        const uint32_t per = (N + G - 1) / G;
+        const uint32_t lo = min(c * per, N), hi = min(lo + per, N);
+        uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+        for (uint32_t i = lo + tid; i < hi; i += kBinThreads) {
+            if (a.tiles_touched[i] != 0) {
+                const uint32_t k = __float_as_uint(a.rec2[i].y);
+                mn = min(mn, k); mx = max(mx, k);
+            }
+        }
+        mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
+        if (tid == 0) { s.mm[0] = 0xFFFFFFFFu; s.mm[1] = 0u; }
+        __syncthreads();
+        if (lane == 0) { atomicMin(&s.mm[0], mn); atomicMax(&s.mm[1], mx); }
+        __syncthreads();
+        if (tid == 0) { a.S[c] = s.mm[0]; a.S[G + c] = s.mm[1]; }
+    }
+    grid.sync();
+    uint32_t kmin, kbits;
+    {
+        uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+        for (uint32_t j = lane; j < G; j += 32) { mn = min(mn, __ldcg(a.S + j)); mx = max(mx, __ldcg(a.S + G + j)); }
+        mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
+        kmin = mn <= mx ? mn : 0u;
+        const uint32_t span = mn <= mx ? mx - mn : 0u;
+        kbits = span ? 32u - (uint32_t)__clz((int)span) : 1u;
+    }
+    // (S is reused by phase 2, several grid-wide syncs later)
+
+    // ---- 1. depth order of the visible Gaussians: ceil(kbits / 9) stable passes (uniform over the grid)
+    const int passes = (int)((kbits + kDigitBits - 1) / kDigitBits);
+    uint32_t nvis;
+    if (passes == 1) {
+        nvis = radix_pass<true, true>(a, grid, s, dyn, 0, kmin, N, nullptr, nullptr, nullptr, a.perm);
+    } else {
+        nvis = radix_pass<true, false>(a, grid, s, dyn, 0, kmin, N, nullptr, nullptr, a.kA, a.vA);
+        uint32_t *ki = a.kA, *vi = a.vA, *ko = a.kB, *vo = a.vB;
+        for (int p = 1; p < passes - 1; ++p) {
+            radix_pass<false, false>(a, grid, s, dyn, p * kDigitBits, 0u, nvis, ki, vi, ko, vo);
+            uint32_t* t0 = ki; ki = ko; ko = t0;
+            t0 = vi; vi = vo; vo = t0;
+        }
+        radix_pass<false, true>(a, grid, s, dyn, (passes - 1) * kDigitBits, 0u, nvis, ki, vi, nullptr, a.perm);
+    }
 
     // ---- 2. chunks of (nearly) equal instance counts along the depth order
     const uint32_t per = (nvis + G - 1) / G;
@@ -237,42 +317,50 @@ __global__ void __launch_bounds__(kBinThreads, 1) bin_sort_kernel(BinSortArgs a)
     }
     grid.sync();
 
-    // ---- 3. instances per (chunk, tile)
+    // ---- 3. instances per (tile, chunk): shared-memory histogram of my chunk, band by band
     const uint32_t cs = __ldcg(a.chunk_start + c), ce = __ldcg(a.chunk_start + c + 1);
-    for (int y0 = 0; y0 < a.grid_y; y0 += a.count_band_rows) {
-        const int y1 = min(a.grid_y, y0 + a.count_band_rows);
-        const int bn = (y1 - y0) * a.grid_x;
-        for (int j = tid; j < bn; j += kBinThreads) dyn[j] = 0;
-        __syncthreads();
-        count_chunk_band(a, cs, ce, y0, y1, dyn);
-        __syncthreads();
-        uint32_t* row = a.M + (size_t)c * a.num_tiles + (size_t)y0 * a.grid_x;
-        for (int j = tid; j < bn; j += kBinThreads) row[j] = dyn[j];
-        __syncthreads();
+    {
+        const uint32_t len = ce - cs, wper = (len + 31) / 32;
+        const uint32_t ks = cs + min((uint32_t)warp * wper, len), ke = cs + min((uint32_t)(warp + 1) * wper, len);
+        for (int y0 = 0; y0 < a.grid_y; y0 += a.count_band_rows) {
+            const int y1 = min(a.grid_y, y0 + a.count_band_rows);
+            const int bn = (y1 - y0) * a.grid_x;
+            for (int j = tid; j < bn; j += kBinThreads) dyn[j] = 0;
+            __syncthreads();
+            walk_pairs(a.perm, a.rect, a.rec0, a.rec1, a.tight, ks, ke, y0, y1, a.grid_x, [&](bool on, int tile, uint32_t) {
+                const uint32_t peers = __match_any_sync(0xffffffffu, on ? (uint32_t)tile : (0x80000000u + (uint32_t)lane));
+                if (on && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&dyn[tile], (uint32_t)__popc(peers));
+            });
+            __syncthreads();
+            for (int j = tid; j < bn; j += kBinThreads) a.M[(size_t)(y0 * a.grid_x + j) * G + c] = dyn[j];
+            __syncthreads();
+        }
     }
     grid.sync();
 
-    // ---- 4. per tile: exclusive scan over the chunks (in place); then exclusive scan over the tiles
-    const uint32_t tps = ((uint32_t)a.num_tiles + G - 1) / G;           // tiles per CTA
-    const uint32_t t_lo = min(c * tps, (uint32_t)a.num_tiles), t_hi = min(t_lo + tps, (uint32_t)a.num_tiles);
-    for (uint32_t t = t_lo + tid; t < t_hi; t += kBinThreads) {
+    // ---- 4. per tile: exclusive scan over the chunks (one warp per tile); then exclusive scan over the tiles
+    for (uint32_t t = c * 32u + warp; t < (uint32_t)a.num_tiles; t += G * 32u) {
+        uint32_t* row = a.M + (size_t)t * G;
         uint32_t run = 0;
-        uint32_t* col = a.M + t;
-        uint32_t j = 0;
-        for (; j + 8 <= G; j += 8) {
-            uint32_t v[8];
+        for (uint32_t j0 = 0; j0 < G; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            const uint32_t v = j < G ? __ldcg(row + j) : 0u;
+            uint32_t x = v;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = __ldcg(col + (size_t)(j + u) * a.num_tiles);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { col[(size_t)(j + u) * a.num_tiles] = run; run += v[u]; }
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            if (j < G) row[j] = run + x - v;
+            run += __shfl_sync(0xffffffffu, x, 31);
         }
-        for (; j < G; ++j) { const uint32_t v = __ldcg(col + (size_t)j * a.num_tiles); col[(size_t)j * a.num_tiles] = run; run += v; }
-        a.tile_total[t] = run;
+        if (lane == 0) a.tile_total[t] = run;
     }
     grid.sync();
     {
-        // start of my tile slice = sum of every tile before it
-        uint32_t sum = 0;
+        const uint32_t tps = ((uint32_t)a.num_tiles + G - 1) / G;           // tiles per CTA
+        const uint32_t t_lo = min(c * tps, (uint32_t)a.num_tiles), t_hi = min(t_lo + tps, (uint32_t)a.num_tiles);
+        uint32_t sum = 0;                                                   // start of my slice = sum of every tile before it
         for (uint32_t t = tid; t < t_lo; t += kBinThreads) sum += __ldcg(a.tile_total + t);
         uint32_t before;
         block_scan_incl(sum, s.sw, before);
@@ -285,11 +373,12 @@ __global__ void __launch_bounds__(kBinThreads, 1) bin_sort_kernel(BinSortArgs a)
             if (t < t_hi) {
                 const uint32_t start = run + incl - v;
                 a.tile_start[t] = start;
-                a.ranges[t] = make_uint2(min(start, a.capacity), min(start + v, a.capacity));
+                // empty tiles keep (0, 0) like the reference's zero-initialised range array (identifyTileRanges, A.2)
+                a.ranges[t] = v ? make_uint2(min(start, a.capacity), min(start + v, a.capacity)) : make_uint2(0u, 0u);
             }
             run += tot;
         }
-        if (c == G - 1 && tid == 0) {     // the last slice ends at R (empty trailing slices all live in the last CTAs: run = R there too)
+        if (c == G - 1 && tid == 0) {     // the last slice ends at R
             a.ctl->n_visible = nvis;
             a.ctl->R = run;
             a.ctl->overflow = run > a.capacity ? 1u : 0u;
@@ -298,69 +387,53 @@ __global__ void __launch_bounds__(kBinThreads, 1) bin_sort_kernel(BinSortArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// stable counting placement: CTA = chunk, warp = contiguous share of the chunk, lanes = tiles of one Gaussian's rect
-template <bool COUNT>
-__device__ __forceinline__ void place_walk(const BinPlaceArgs& a, uint32_t ws, uint32_t we, int y0, int y1, uint32_t* row) {
-    const int lane = threadIdx.x & 31;
-    for (uint32_t k0 = ws; k0 < we; k0 += 32u) {
-        const uint32_t k = k0 + lane;
-        const bool valid = k < we;
-        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-        uint2 rc = make_uint2(0u, 0u);
-        uint32_t gi = 0;
-        if (valid) {
-            gi = a.perm[k];
-            rc = a.rect[gi];
-            if (a.tight) { r0 = a.rec0[gi]; r1 = a.rec1[gi]; }
-        }
-        uint32_t todo = __ballot_sync(0xffffffffu, valid);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const TileJob j = bcast_job(r0, r1, rc, src, y0, y1);
-            const uint32_t id = __shfl_sync(0xffffffffu, gi, src);
-            for (int b = 0; b < j.ntiles; b += 32) {
-                const int t = b + lane;
-                const int ty = t / j.w, tx = t - ty * j.w;
-                if (t < j.ntiles && (!a.tight || tile_contributes(j.r0, j.r1, j.minx + tx, j.miny + ty))) {
-                    uint32_t* p = row + (j.miny + ty - y0) * a.grid_x + j.minx + tx;   // lanes hold distinct tiles
-                    const uint32_t slot = *p;
-                    *p = slot + 1;
-                    if (!COUNT && slot < a.capacity) a.ids[slot] = id;
-                }
-                __syncwarp();   // the next step (possibly another Gaussian on the same tile) must see these counters
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(512) bin_place_kernel(BinPlaceArgs a) {
-    extern __shared__ __align__(16) uint32_t rows[];   // [warps][tiles of the band]
-    const int tid = threadIdx.x, warp = tid >> 5, nw = blockDim.x >> 5;
-    const uint32_t c = blockIdx.x;
+// stable counting placement: CTA = chunk, warp = contiguous share of the chunk, lane = one (Gaussian, tile) pair
+__global__ void __launch_bounds__(kBinThreads, 1) bin_place_kernel(BinPlaceArgs a) {
+    extern __shared__ __align__(16) uint32_t rows[];   // [32 warps][tiles of the band]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t c = blockIdx.x, G = gridDim.x;
     const uint32_t cs = a.chunk_start[c], ce = a.chunk_start[c + 1];
     if (cs >= ce) return;
-    const uint32_t len = ce - cs, per = (len + nw - 1) / nw;
-    const uint32_t ws = cs + min((uint32_t)warp * per, len), we = cs + min((uint32_t)(warp + 1) * per, len);
+    const uint32_t len = ce - cs, per = (len + 31) / 32;
+    const uint32_t ks = cs + min((uint32_t)warp * per, len), ke = cs + min((uint32_t)(warp + 1) * per, len);
+    const uint32_t lt = (1u << lane) - 1u;
     for (int y0 = 0; y0 < a.grid_y; y0 += a.band_rows) {
         const int y1 = min(a.grid_y, y0 + a.band_rows);
         const int bn = (y1 - y0) * a.grid_x;
-        for (int j = tid; j < nw * bn; j += blockDim.x) rows[j] = 0;
+        uint32_t* row = rows + warp * bn;
+        for (int j = tid; j < 32 * bn; j += kBinThreads) rows[j] = 0;
         __syncthreads();
-        place_walk<true>(a, ws, we, y0, y1, rows + warp * bn);
+        // (i) my warp's instance count per tile (plain read-modify-write: one writer per tile and step)
+        walk_pairs(a.perm, a.rect, a.rec0, a.rec1, a.tight, ks, ke, y0, y1, a.grid_x, [&](bool on, int tile, uint32_t) {
+            const uint32_t peers = __match_any_sync(0xffffffffu, on ? (uint32_t)tile : (0x80000000u + (uint32_t)lane));
+            if (on && (peers & lt) == 0) row[tile] += (uint32_t)__popc(peers);
+            __syncwarp();
+        });
         __syncthreads();
-        const uint32_t* mrow = a.M + (size_t)c * a.num_tiles + (size_t)y0 * a.grid_x;
-        const uint32_t* tstart = a.tile_start + (size_t)y0 * a.grid_x;
-        for (int t = tid; t < bn; t += blockDim.x) {
-            uint32_t run = mrow[t] + tstart[t];
-            for (int w = 0; w < nw; ++w) {
+        // (ii) start slot of every warp in every tile: tile start + earlier chunks + earlier warps of my chunk
+        for (int t = tid; t < bn; t += kBinThreads) {
+            const size_t gt = (size_t)y0 * a.grid_x + t;
+            uint32_t run = a.M[gt * G + c] + a.tile_start[gt];
+#pragma unroll 8
+            for (int w = 0; w < 32; ++w) {
                 const uint32_t v = rows[w * bn + t];
                 rows[w * bn + t] = run;
                 run += v;
             }
         }
         __syncthreads();
-        place_walk<false>(a, ws, we, y0, y1, rows + warp * bn);
+        // (iii) place: pairs of one step on the same tile take consecutive slots in lane (= depth) order
+        walk_pairs(a.perm, a.rect, a.rec0, a.rec1, a.tight, ks, ke, y0, y1, a.grid_x, [&](bool on, int tile, uint32_t id) {
+            const uint32_t peers = __match_any_sync(0xffffffffu, on ? (uint32_t)tile : (0x80000000u + (uint32_t)lane));
+            uint32_t slot = 0;
+            if (on) slot = row[tile] + (uint32_t)__popc(peers & lt);
+            __syncwarp();
+            if (on) {
+                if ((peers & lt) == 0) row[tile] += (uint32_t)__popc(peers);
+                if (slot < a.capacity) a.ids[slot] = id;
+            }
+            __syncwarp();
+        });
         __syncthreads();
     }
 }
@@ -374,7 +447,7 @@ size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 size_t bin_aux_bytes(int64_t n, int num_tiles, int sm_count) {
     const size_t N = (size_t)(n > 0 ? n : 1), G = (size_t)sm_count;
-    return 4 * align256(N * 4) + align256(G * kRadix * 4) + align256(G * 4) + align256((G + 1) * 4) +
+    return 4 * align256(N * 4) + align256(G * kRadix * 4) + align256(2 * G * 4) + align256((G + 1) * 4) +
            align256(G * (size_t)num_tiles * 4) + 2 * align256((size_t)num_tiles * 4) + align256(sizeof(BinCtl));
 }
 
@@ -388,7 +461,7 @@ cudaError_t launch_bin_sort(int64_t n, int grid_x, int grid_y, const GeomBuffers
     a.n = n; a.rec2 = g.rec2; a.tiles_touched = g.tiles_touched; a.rect = g.rect; a.rec0 = g.rec0; a.rec1 = g.rec1;
     a.kA = (uint32_t*)take(N * 4); a.vA = (uint32_t*)take(N * 4); a.kB = (uint32_t*)take(N * 4); a.vB = (uint32_t*)take(N * 4);
     a.perm = g.perm;
-    a.H = (uint32_t*)take(G * kRadix * 4); a.S = (uint32_t*)take(G * 4); a.chunk_start = (uint32_t*)take((G + 1) * 4);
+    a.H = (uint32_t*)take(G * kRadix * 4); a.S = (uint32_t*)take(2 * G * 4); a.chunk_start = (uint32_t*)take((G + 1) * 4);
     a.M = (uint32_t*)take(G * (size_t)num_tiles * 4);
     a.tile_total = (uint32_t*)take((size_t)num_tiles * 4); a.tile_start = (uint32_t*)take((size_t)num_tiles * 4);
     a.ctl = (BinCtl*)take(sizeof(BinCtl));
@@ -412,21 +485,13 @@ cudaError_t launch_bin_place(int grid_x, int grid_y, const GeomBuffers& g, const
     a.perm = g.perm; a.rect = g.rect; a.rec0 = g.rec0; a.rec1 = g.rec1; a.chunk_start = lay.chunk_start; a.M = lay.M;
     a.tile_start = lay.tile_start; a.ids = ids; a.capacity = capacity; a.grid_x = grid_x; a.grid_y = grid_y;
     a.num_tiles = num_tiles; a.tight = tight;
-    int warps;
-    if ((size_t)num_tiles * 4 * 4 <= kPlaceSmemBudget) {
-        warps = (int)(kPlaceSmemBudget / ((size_t)num_tiles * 4));
-        if (warps > 16) warps = 16;
-        a.band_rows = grid_y;
-    } else {
-        warps = 4;
-        a.band_rows = (int)(kPlaceSmemBudget / ((size_t)warps * grid_x * 4));
-        if (a.band_rows < 1) return cudaErrorInvalidValue;
-        if (a.band_rows > grid_y) a.band_rows = grid_y;
-    }
-    const size_t smem = (size_t)warps * a.band_rows * grid_x * 4;
+    a.band_rows = (int)(kPlaceSmemBudget / ((size_t)32 * grid_x * 4));      // 32 per-warp counter rows per band
+    if (a.band_rows < 1) return cudaErrorInvalidValue;
+    if (a.band_rows > grid_y) a.band_rows = grid_y;
+    const size_t smem = (size_t)32 * a.band_rows * grid_x * 4;
     cudaError_t e = cudaFuncSetAttribute(bin_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    bin_place_kernel<<<lay.chunks, warps * 32, smem, st>>>(a);
+    bin_place_kernel<<<lay.chunks, kBinThreads, smem, st>>>(a);
     return cudaGetLastError();
 }
 

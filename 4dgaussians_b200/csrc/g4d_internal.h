@@ -160,6 +160,14 @@ cudaError_t launch_ssim_forward(const float* x, const float* y, int C, int H, in
 cudaError_t launch_ssim_backward(const float* x, const float* y, int C, int H, int W, float scale, const float* upstream,
                                  const float* dmu, const float* dxx, const float* dxy, float* grad, cudaStream_t st);
 
+// ---- flat Adam (g4d_optim.cu) ------------------------------------------------------------------------------------------
+cudaError_t launch_adam_flat(float* p, const float* g, float* m, float* v, int64_t numel, const G4DAdamSegment* segs, int nseg,
+                             float b1, float b2, float eps, int64_t step, float grad_scale, int sm_count, cudaStream_t st);
+
+// ---- 3-nearest-neighbour mean squared distance (g4d_knn.cu) ---------------------------------------------------------
+size_t knn_scratch_bytes(int64_t n);
+cudaError_t launch_knn_dist2(int64_t n, const float* xyz, float* out, void* scratch, int sm_count, cudaStream_t st);
+
 // tcgen05 building-block self test: g4d_tc_selftest.cu -> libg4d_selftest.so (test-only library, not in libg4d.so)
 cudaError_t launch_umma16_selftest(const int cfg[8], const float* A, const float* B, float* D, cudaStream_t st);
 cudaError_t launch_umma_selftest(const int cfg[8], const float* A, const float* B, float* scratch_packed, float* D, cudaStream_t st);

@@ -124,6 +124,7 @@ class deform_network(nn.Module):
         self.apply(_initialize_weights)
         self._version_seen = None
         self._param_version = 0
+        self._dirty = False
 
     # ---- reference surface -------------------------------------------------------------------------
     @property
@@ -178,15 +179,29 @@ class deform_network(nn.Module):
             if not p.is_contiguous() or p.dtype != torch.float32:
                 p.data = p.data.float().contiguous()
 
-    def param_version(self) -> int:
-        """Changes whenever any parameter tensor was modified in place (optimizer step, load_state_dict)."""
-        sig = tuple((p.data_ptr(), p._version) for p in self.flat_parameters())
-        if sig != self._version_seen:
+    def param_version(self, fresh: bool = False) -> int:
+        """Key of the library's packed weight images (transposes / TF32 / BF16 operand images of the MLP weights).
+
+        It changes whenever a parameter tensor was replaced or modified through an op that bumps ``Tensor._version``
+        (``load_state_dict``, ``copy_``, foreach / plain optimizers), whenever the head mask changes, after
+        ``invalidate_cache()``, and -- ``fresh=True`` -- on EVERY forward that a backward can follow: fused optimizers
+        (``torch.optim.Adam(fused=True)``) and writes through ``param.data`` update the weights WITHOUT bumping
+        ``_version``, so in training the images are simply rebuilt per forward (three tiny kernels over ~100k floats)."""
+        sig = (self.head_mask(),) + tuple((p.data_ptr(), p._version) for p in self.flat_parameters())
+        # a training forward is normally followed by an optimizer step the version counters may not show: the first
+        # no_grad forward after it refreshes once more (self._dirty)
+        if fresh or self._dirty or sig != self._version_seen:
             self._version_seen = sig
             self._param_version = next(_VERSION_COUNTER)
+        self._dirty = fresh
         return self._param_version
 
-    def c_params(self, keep: list) -> _lib.DeformParams:
+    def invalidate_cache(self):
+        """Call after changing weights in a way autograd's version counters cannot see (``p.data.copy_``, a custom fused
+        optimizer) while rendering under ``torch.no_grad()``; training forwards refresh the images on their own."""
+        self._version_seen = None
+
+    def c_params(self, keep: list, fresh: bool = False) -> _lib.DeformParams:
         self._ensure_layout()
         net = self.deformation_net
         kc = net.grid.grid_config[0]
@@ -216,7 +231,7 @@ class deform_network(nn.Module):
             seq = getattr(net, name)
             prm.w1[h], prm.b1[h] = seq[1].weight.data_ptr(), seq[1].bias.data_ptr()
             prm.w2[h], prm.b2[h] = seq[3].weight.data_ptr(), seq[3].bias.data_ptr()
-        prm.version = self.param_version()
+        prm.version = self.param_version(fresh)
         return prm
 
     def alloc_grads(self) -> List[torch.Tensor]:
@@ -328,7 +343,8 @@ class _DeformFunction(torch.autograd.Function):
         x, s, r, o, sh = (_f32c(v, nm) for v, nm in ((xyz, "point"), (scales, "scales"), (rotations, "rotations"),
                                                      (opacity, "opacity"), (shs, "shs")))
         keep = []
-        prm = module.c_params(keep)
+        needs_bwd = grad_mode and any(ctx.needs_input_grad)      # (grad mode is always off INSIDE Function.forward)
+        prm = module.c_params(keep, fresh=needs_bwd)
         hm = prm.head_mask
         ox = torch.empty_like(x)
         os_ = torch.empty_like(s) if s is not None else None
@@ -337,7 +353,6 @@ class _DeformFunction(torch.autograd.Function):
         osh = torch.empty_like(sh) if (sh is not None and (hm & _lib.HEAD_SHS)) else None
         ptr = lambda v: v.data_ptr() if v is not None else None
         # what autograd would save for the ReLU backward: one sign bit per hidden unit (only when a backward can follow)
-        needs_bwd = grad_mode and any(ctx.needs_input_grad)      # (grad mode is always off INSIDE Function.forward)
         relu_bits = torch.empty(_lib.relu_bits_words(n), device=dev, dtype=torch.int32) if needs_bwd else None
         with torch.cuda.device(dev):
             ws = _lib.Workspace.get(dev.index if dev.index is not None else torch.cuda.current_device())
@@ -359,7 +374,7 @@ class _DeformFunction(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         dev = x.device
         keep = []
-        prm = module.c_params(keep)
+        prm = module.c_params(keep, fresh=True)      # (keeps the "an optimizer step may follow" mark, see param_version)
         hm = prm.head_mask
         flat = module.flat_parameters()
         sinks = module.grad_sinks()

@@ -20,6 +20,13 @@ def install(patch_reference: bool = False):
     mod.GaussianRasterizer = rasterizer.GaussianRasterizer
     mod.__doc__ = "g4d drop-in for depth-diff-gaussian-rasterization (see 4dgaussians_b200/rasterizer.py)"
     sys.modules["diff_gaussian_rasterization"] = mod
+    from . import simple_knn
+    knn = types.ModuleType("simple_knn")
+    knn_c = types.ModuleType("simple_knn._C")
+    knn_c.distCUDA2 = simple_knn.distCUDA2
+    knn._C = knn_c
+    knn.__doc__ = "g4d drop-in for simple-knn (see 4dgaussians_b200/simple_knn.py)"
+    sys.modules["simple_knn"], sys.modules["simple_knn._C"] = knn, knn_c
     if patch_reference:
         try:
             import scene.deformation as sd  # type: ignore

@@ -54,9 +54,11 @@ class _FusedRender(torch.autograd.Function):
         radii = torch.empty(n, device=dev, dtype=torch.int32)
         keep = []
         cam = camera_from_settings(rs, time=t, keep=keep)
-        if not (grad_mode and any(ctx.needs_input_grad)):      # (grad mode is always off INSIDE Function.forward)
+        needs_bwd = grad_mode and any(ctx.needs_input_grad)    # (grad mode is always off INSIDE Function.forward)
+        if not needs_bwd:
             cam.debug |= _lib.CAM_NO_GRAD      # torch.no_grad() rendering: nothing is saved for a backward
-        prm = module.c_params(keep) if module is not None else None
+        # training forwards rebuild the packed weight images (fused optimizers do not bump Tensor._version)
+        prm = module.c_params(keep, fresh=needs_bwd) if module is not None else None
         g = _lib.Gaussians(n, x.data_ptr(), s.data_ptr(), r.data_ptr(), o.data_ptr(), dc.data_ptr(), rest.data_ptr())
         with torch.cuda.device(dev):
             lease = _ContextLease(_lib.Workspace.get(dev.index if dev.index is not None else torch.cuda.current_device()))
@@ -66,7 +68,7 @@ class _FusedRender(torch.autograd.Function):
         ctx.module, ctx.rs, ctx.t, ctx.n, ctx.lease = module, rs, t, n, lease
         # the C-ABI structs (and the tensors whose pointers they carry) are kept for the backward: rebuilding them costs the
         # host ~0.3 ms per view, during which the GPU has nothing queued behind the forward's last kernel
-        ctx.cstructs = (cam, prm, g, keep, module.param_version() if module is not None else None)
+        ctx.cstructs = (cam, prm, g, keep, int(prm.version) if prm is not None else None)
         ctx.save_for_backward(x, s, r, o, dc, rest)
         ctx.mark_non_differentiable(radii, depth)
         return color, radii, depth
@@ -78,9 +80,9 @@ class _FusedRender(torch.autograd.Function):
         dev, n, rs, module = x.device, ctx.n, ctx.rs, ctx.module
         gcol = _dev_f32(grad_color, 3 * int(rs.image_height) * int(rs.image_width), "grad_out_color")
         cam, prm, g, keep, version = ctx.cstructs
-        if module is not None and version != module.param_version():      # parameters replaced since the forward: rebuild
+        if module is not None and version != module._param_version:      # another forward ran since: take the current key
             keep = []
-            prm = module.c_params(keep)
+            prm = module.c_params(keep, fresh=True)
         pgrads, cg = [], None
         if module is not None:
             sinks = module.grad_sinks()

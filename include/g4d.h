@@ -192,6 +192,23 @@ int g4d_plane_regulation(G4DWorkspace *ws, const G4DDeformParams *prm, G4DDeform
                          float time_smoothness_weight, float l1_time_planes_weight, const float *upstream,
                          float *loss_accum, void *stream);
 
+/* ---- optimizer step of the data-parallel harness --------------------------------
+ * g4d_adam_step <- gaussians.optimizer.step() (train.py:290-292; groups scene/gaussian_model.py:165-183): torch.optim.Adam
+ * without weight decay over ONE flat buffer; segment i covers elements [begin, end) with its own learning rate (elements in
+ * no segment are left untouched); `numel` must be a multiple of 4 (pad the buffers); `step` is the 1-based step count;
+ * gradients are multiplied by grad_scale first (1 / world_size after a SUM all-reduce). */
+#define G4D_ADAM_MAX_SEGMENTS 16
+typedef struct G4DAdamSegment { int64_t begin, end; float lr; float reserved; } G4DAdamSegment;
+int g4d_adam_step(G4DWorkspace *ws, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t numel,
+                  const G4DAdamSegment *segments, int32_t num_segments, float beta1, float beta2, float eps, int64_t step,
+                  float grad_scale, void *stream);
+
+/* ---- scene initialisation -------------------------------------------------------
+ * g4d_dist2_knn3 <- simple_knn._C.distCUDA2(points) (scene/gaussian_model.py:22,148; submodule absent from the reference
+ * tree): for every point the mean of the squared distances to its 3 nearest OTHER points, fp32, exact (not approximate).
+ * xyz [N,3] device, out [N] device. */
+int g4d_dist2_knn3(G4DWorkspace *ws, int64_t n, const float *xyz, float *out_mean_dist2, void *stream);
+
 /* ---- options / introspection --------------------------------------------------------------------*/
 enum { G4D_OPT_SYNC_MODE = 1,  /* 1 (default): size the instance buffer exactly (one host read of R per
                                   forward, like the reference); 0: R stays on the device, the placement is

@@ -409,6 +409,36 @@ def test_batched_views_single_backward_matches_per_view_backward():
         assert float((a - b).abs().max()) <= 2e-5 * max(1e-3, float(b.abs().max())), float((a - b).abs().max())
 
 
+@pytest.mark.parametrize("net", ["dynerf", "small64"])
+@pytest.mark.parametrize("fused_opt", [True, False])
+def test_optimizer_updates_are_seen_by_the_next_forward(net, fused_opt):
+    """torch.optim.Adam(fused=True) updates the MLP weights WITHOUT bumping Tensor._version: the library's packed weight
+    images (TF32 / BF16 operand images, FFMA transposes) must still follow -- training forwards rebuild them.  After a few
+    optimizer steps the module must render exactly like a fresh module that loaded its state_dict."""
+    c = dict(FUSED_CASES[2]); c["net"] = net
+    scene, mod, pc, cam = _fused_setup(c)
+    bg = torch.tensor(c["bg"], device="cuda")
+    params = pc.gaussian_parameters() + list(mod.flat_parameters())
+    opt = torch.optim.Adam(params, lr=5e-3, fused=fused_opt)
+    for _ in range(3):
+        opt.zero_grad(set_to_none=True)
+        g4d.render(cam, pc, _Pipe, bg)["render"].square().mean().backward()
+        opt.step()
+    out = g4d.render(cam, pc, _Pipe, bg)                       # training-mode forward right after the last step
+    with torch.no_grad():
+        out_ng = g4d.render(cam, pc, _Pipe, bg)
+    fresh = g4d.deform_network(synth.hidden_args(net))
+    fresh.load_state_dict(mod.state_dict())
+    fresh = fresh.cuda()
+    scene2 = {k: v.detach().cpu() for k, v in zip(("xyz", "scaling", "rotation", "opacity", "features_dc", "features_rest"), pc.gaussian_parameters())}
+    pc2 = synth.SyntheticGaussianModel(scene2, fresh, sh_degree=c["deg"], requires_grad=False)
+    with torch.no_grad():
+        want = g4d.render(cam, pc2, _Pipe, bg)
+    assert float((out["render"] - want["render"]).abs().max()) <= 1e-6
+    # a no_grad forward after a version-less update relies on the images the last training forward rebuilt
+    assert float((out_ng["render"] - want["render"]).abs().max()) <= 1e-6
+
+
 def test_fused_grad_accumulation_matches_autograd_accumulation():
     """deform_network.fused_grad_accumulation: two views accumulated by the kernels straight into FlatGradBucket views give
     the same .grad as autograd's AccumulateGrad over per-view staging buffers."""
@@ -662,6 +692,8 @@ def test_no_sync_mode_matches_sync_mode_and_reports_overflow():
                                        opacities=ins[3], scales=ins[1], rotations=ins[2], cov3D_precomp=None)
         return color.clone(), depth.clone()
     cams = [synth.make_camera(th, 320, 240, radius=3.0) for th in (0.0, 40.0, 80.0, 120.0)]
+    ws.set_option(g4d._lib.OPT_INSTANCE_CAPACITY, 0)
+    ws._free_contexts.clear()
     ref = [render(c) for c in cams]
     try:
         ws.set_option(g4d._lib.OPT_SYNC_MODE, 0)
