@@ -342,12 +342,10 @@ int bin_and_blend(G4DContext* c, const G4DCamera* cam, int64_t n, float* out_col
         // no-sync needs a capacity learnt from an earlier (exact) forward on this context
         const bool nosync = !ws->sync_mode && !(cam->debug & G4D_CAM_DEBUG) && c->capacity > 0 && c->learned;
         if (nosync && ws->min_capacity > c->capacity && (rc = ensure_bin(c, ws->min_capacity)) != G4D_OK) return rc;
-        const uint32_t cap_now = (uint32_t)(c->capacity < (int64_t)kNoCap ? c->capacity : (int64_t)kNoCap);
         BinLayout lay{};
         {
             StageTimer tm(c, G4D_STAGE_SCAN, st);
-            G4D_CUDA(launch_bin_sort(n, c->grid_x, c->grid_y, c->g, c->binaux.p, c->b.ranges, nosync ? cap_now : kNoCap,
-                                     ws->tight_cull, ws->sm_count, &lay, st));
+            G4D_CUDA(launch_bin_sort(n, c->grid_x, c->grid_y, c->g, c->binaux.p, ws->tight_cull, ws->sm_count, &lay, st));
         }
         if (!nosync) {
             G4D_CUDA(cudaMemcpyAsync(ws->h_pinned, &lay.ctl->R, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -369,7 +367,7 @@ int bin_and_blend(G4DContext* c, const G4DCamera* cam, int64_t n, float* out_col
         {
             StageTimer tm(c, G4D_STAGE_EMIT, st);
             const uint32_t cap_place = (uint32_t)(c->capacity < (int64_t)kNoCap ? c->capacity : (int64_t)kNoCap);
-            G4D_CUDA(launch_bin_place(c->grid_x, c->grid_y, c->g, lay, c->b.ids_sorted, cap_place, ws->tight_cull, st));
+            G4D_CUDA(launch_bin_place(c->grid_x, c->grid_y, c->g, lay, c->b.ids_sorted, c->b.ranges, cap_place, ws->tight_cull, st));
         }
     } else {
         c->R = 0;

@@ -173,13 +173,21 @@ __device__ __forceinline__ void walk_pairs(const uint32_t* __restrict__ perm, co
                                            const float4* __restrict__ rec0, const float4* __restrict__ rec1, int tight, uint32_t ks,
                                            uint32_t ke, int y0, int y1, int grid_x, F&& f) {
     const int lane = threadIdx.x & 31;
+    // two-deep register prefetch: perm two groups ahead, rect one group ahead (both are L2 round trips; a far chunk holds
+    // thousands of 1-4 tile Gaussians, so the walk would otherwise be a chain of dependent gathers)
+    uint32_t gi_n = ks + lane < ke ? perm[ks + lane] : 0u;
+    uint32_t gi_nn = ks + 32u + lane < ke ? perm[ks + 32u + lane] : 0u;
+    uint2 rc_n = ks + lane < ke ? rect[gi_n] : make_uint2(0u, 0u);
     for (uint32_t k0 = ks; k0 < ke; k0 += 32u) {
         const uint32_t k = k0 + lane;
-        uint32_t gi = 0, xy = 0, w = 1, nt = 0;
+        const uint32_t gi = gi_n;
+        const uint2 rc = rc_n;
+        gi_n = gi_nn;
+        rc_n = k + 32u < ke ? rect[gi_n] : make_uint2(0u, 0u);
+        gi_nn = k + 64u < ke ? perm[k + 64u] : 0u;
+        uint32_t xy = 0, w = 1, nt = 0;
         float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
         if (k < ke) {
-            gi = perm[k];
-            const uint2 rc = rect[gi];
             const int minx = (int)(rc.x & 0xFFFFu), maxx = (int)(rc.y & 0xFFFFu);
             const int miny = max((int)(rc.x >> 16), y0), maxy = min((int)(rc.y >> 16), y1);
             w = (uint32_t)max(maxx - minx, 1);
@@ -195,6 +203,7 @@ __device__ __forceinline__ void walk_pairs(const uint32_t* __restrict__ perm, co
         }
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
         const uint32_t excl = incl - nt;
+        const float rw = __frcp_rn((float)w);
         for (uint32_t b = 0; b < total; b += 32u) {
             const uint32_t flat = b + lane;
             const bool active = flat < total;
@@ -207,8 +216,13 @@ __device__ __forceinline__ void walk_pairs(const uint32_t* __restrict__ perm, co
             g &= 31;
             const uint32_t oxy = __shfl_sync(0xffffffffu, xy, g), ow = __shfl_sync(0xffffffffu, w, g);
             const uint32_t oex = __shfl_sync(0xffffffffu, excl, g), oid = __shfl_sync(0xffffffffu, gi, g);
+            const float orw = __shfl_sync(0xffffffffu, rw, g);
             const uint32_t t = active ? flat - oex : 0u;
-            const uint32_t ty = t / ow, tx = t - ty * ow;
+            // t / ow without the integer-division sequence: t < 2^24 (tile rects), one correction step makes it exact
+            uint32_t ty = (uint32_t)((float)t * orw);
+            if (ty * ow > t) --ty;
+            else if ((ty + 1u) * ow <= t) ++ty;
+            const uint32_t tx = t - ty * ow;
             const int x = (int)(oxy & 0xFFFFu) + (int)tx, y = (int)(oxy >> 16) + (int)ty;
             bool on = active;
             if (tight) {
@@ -223,6 +237,9 @@ __device__ __forceinline__ void walk_pairs(const uint32_t* __restrict__ perm, co
         }
     }
 }
+
+// walk cost of a Gaussian in units of tile instances: its pairs plus a fixed per-Gaussian share of the group overhead
+__device__ __forceinline__ uint32_t chunk_weight(uint32_t tiles_touched) { return tiles_touched + 12u; }
 
 }  // namespace
 
@@ -250,7 +267,7 @@ __global__ void __launch_bounds__(kBinThreads, 1) bin_sort_kernel(BinSortArgs a)
         __syncthreads();
         if (lane == 0) { atomicMin(&s.mm[0], mn); atomicMax(&s.mm[1], mx); }
         __syncthreads();
-        if (tid == 0) { a.S[c] = s.mm[0]; a.S[G + c] = s.mm[1]; }
+        if (tid == 0) { a.S[c] = s.mm[0]; a.S[G + c] = s.mm[1]; if (c == 0) { a.ctl->R = 0u; a.ctl->overflow = 0u; } }
     }
     grid.sync();
     uint32_t kmin, kbits;
@@ -280,12 +297,12 @@ __global__ void __launch_bounds__(kBinThreads, 1) bin_sort_kernel(BinSortArgs a)
         radix_pass<false, true>(a, grid, s, dyn, (passes - 1) * kDigitBits, 0u, nvis, ki, vi, nullptr, a.perm);
     }
 
-    // ---- 2. chunks of (nearly) equal instance counts along the depth order
+    // ---- 2. chunks of (nearly) equal walk cost (instances + a per-Gaussian constant) along the depth order
     const uint32_t per = (nvis + G - 1) / G;
     const uint32_t lo = min(c * per, nvis), hi = min(lo + per, nvis);
     {
         uint32_t sum = 0;
-        for (uint32_t k = lo + tid; k < hi; k += kBinThreads) sum += a.tiles_touched[a.perm[k]];
+        for (uint32_t k = lo + tid; k < hi; k += kBinThreads) sum += chunk_weight(a.tiles_touched[a.perm[k]]);
         uint32_t total;
         block_scan_incl(sum, s.sw, total);
         if (tid == 0) a.S[c] = total;
@@ -304,7 +321,7 @@ __global__ void __launch_bounds__(kBinThreads, 1) bin_sort_kernel(BinSortArgs a)
         uint32_t run = my_excl;
         for (uint32_t b0 = lo; b0 < hi; b0 += kBinThreads) {
             const uint32_t k = b0 + tid;
-            const uint32_t tt = k < hi ? a.tiles_touched[a.perm[k]] : 0u;
+            const uint32_t tt = k < hi ? chunk_weight(a.tiles_touched[a.perm[k]]) : 0u;
             uint32_t tot;
             const uint32_t incl = block_scan_incl(tt, s.sw, tot);
             if (k < hi) {
@@ -338,110 +355,148 @@ __global__ void __launch_bounds__(kBinThreads, 1) bin_sort_kernel(BinSortArgs a)
     }
     grid.sync();
 
-    // ---- 4. per tile: exclusive scan over the chunks (one warp per tile); then exclusive scan over the tiles
-    for (uint32_t t = c * 32u + warp; t < (uint32_t)a.num_tiles; t += G * 32u) {
-        uint32_t* row = a.M + (size_t)t * G;
-        uint32_t run = 0;
-        for (uint32_t j0 = 0; j0 < G; j0 += 32) {
-            const uint32_t j = j0 + lane;
-            const uint32_t v = j < G ? __ldcg(row + j) : 0u;
-            uint32_t x = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-                if (lane >= o) x += y;
-            }
-            if (j < G) row[j] = run + x - v;
-            run += __shfl_sync(0xffffffffu, x, 31);
-        }
-        if (lane == 0) a.tile_total[t] = run;
-    }
-    grid.sync();
+    // ---- 4. per tile: exclusive scan over the chunks (one warp per tile) and the tile's total; R = sum of the totals.
+    //         (the exclusive scan over the TILES -- tile_start, ranges -- is done by the placement kernel: one grid-wide sync
+    //         less here, 5440 values re-scanned per CTA there)
     {
-        const uint32_t tps = ((uint32_t)a.num_tiles + G - 1) / G;           // tiles per CTA
-        const uint32_t t_lo = min(c * tps, (uint32_t)a.num_tiles), t_hi = min(t_lo + tps, (uint32_t)a.num_tiles);
-        uint32_t sum = 0;                                                   // start of my slice = sum of every tile before it
-        for (uint32_t t = tid; t < t_lo; t += kBinThreads) sum += __ldcg(a.tile_total + t);
-        uint32_t before;
-        block_scan_incl(sum, s.sw, before);
-        uint32_t run = before;
-        for (uint32_t b0 = t_lo; b0 < t_hi; b0 += kBinThreads) {
-            const uint32_t t = b0 + tid;
-            const uint32_t v = t < t_hi ? __ldcg(a.tile_total + t) : 0u;
-            uint32_t tot;
-            const uint32_t incl = block_scan_incl(v, s.sw, tot);
-            if (t < t_hi) {
-                const uint32_t start = run + incl - v;
-                a.tile_start[t] = start;
-                // empty tiles keep (0, 0) like the reference's zero-initialised range array (identifyTileRanges, A.2)
-                a.ranges[t] = v ? make_uint2(min(start, a.capacity), min(start + v, a.capacity)) : make_uint2(0u, 0u);
+        uint32_t my_total = 0;
+        for (uint32_t t = c * 32u + warp; t < (uint32_t)a.num_tiles; t += G * 32u) {
+            uint32_t* row = a.M + (size_t)t * G;
+            uint32_t run = 0;
+            for (uint32_t j0 = 0; j0 < G; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                const uint32_t v = j < G ? __ldcg(row + j) : 0u;
+                uint32_t x = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                    if (lane >= o) x += y;
+                }
+                if (j < G) row[j] = run + x - v;
+                run += __shfl_sync(0xffffffffu, x, 31);
             }
-            run += tot;
+            if (lane == 0) { a.tile_total[t] = run; my_total += run; }
         }
-        if (c == G - 1 && tid == 0) {     // the last slice ends at R
-            a.ctl->n_visible = nvis;
-            a.ctl->R = run;
-            a.ctl->overflow = run > a.capacity ? 1u : 0u;
+        uint32_t cta_total;
+        block_scan_incl(my_total, s.sw, cta_total);
+        if (tid == 0) {
+            if (cta_total) atomicAdd(&a.ctl->R, cta_total);
+            if (c == 0) a.ctl->n_visible = nvis;
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// stable counting placement: CTA = chunk, warp = contiguous share of the chunk, lane = one (Gaussian, tile) pair
-__global__ void __launch_bounds__(kBinThreads, 1) bin_place_kernel(BinPlaceArgs a) {
-    extern __shared__ __align__(16) uint32_t rows[];   // [32 warps][tiles of the band]
+// stable counting placement: CTA = chunk, warp = contiguous share of the chunk, lane = one (Gaussian, tile) pair.
+// Shared memory per band of tile rows: base[tiles] u32 (slot of the chunk's first instance in every tile) and 17 rows of u16
+// counters [16 warps + 1 total][tiles].  A chunk longer than kSubMax Gaussians is walked in sub-chunks (u16 range).
+constexpr int kPlaceThreads = 512, kPlaceWarps = kPlaceThreads / 32;
+constexpr uint32_t kSubMax = 16u * 4000u;
+
+__global__ void __launch_bounds__(kPlaceThreads, 1) bin_place_kernel(BinPlaceArgs a) {
+    extern __shared__ __align__(16) uint8_t place_smem[];
+    __shared__ uint32_t s_w[33];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t c = blockIdx.x, G = gridDim.x;
     const uint32_t cs = a.chunk_start[c], ce = a.chunk_start[c + 1];
-    if (cs >= ce) return;
-    const uint32_t len = ce - cs, per = (len + 31) / 32;
-    const uint32_t ks = cs + min((uint32_t)warp * per, len), ke = cs + min((uint32_t)(warp + 1) * per, len);
     const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t T = (uint32_t)a.num_tiles;
+    // block-wide exclusive scan helper over kPlaceThreads threads (returns exclusive value, total)
+    auto block_excl = [&](uint32_t v, uint32_t& total) {
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        __syncthreads();
+        if (lane == 31) s_w[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = lane < kPlaceWarps ? s_w[lane] : 0u;
+            uint32_t ws = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += y; }
+            s_w[lane] = ws - w;
+            if (lane == 31) s_w[32] = ws;
+        }
+        __syncthreads();
+        total = s_w[32];
+        return s_w[warp] + x - v;
+    };
     for (int y0 = 0; y0 < a.grid_y; y0 += a.band_rows) {
         const int y1 = min(a.grid_y, y0 + a.band_rows);
-        const int bn = (y1 - y0) * a.grid_x;
-        uint32_t* row = rows + warp * bn;
-        for (int j = tid; j < 32 * bn; j += kBinThreads) rows[j] = 0;
-        __syncthreads();
-        // (i) my warp's instance count per tile (plain read-modify-write: one writer per tile and step)
-        walk_pairs(a.perm, a.rect, a.rec0, a.rec1, a.tight, ks, ke, y0, y1, a.grid_x, [&](bool on, int tile, uint32_t) {
-            const uint32_t peers = __match_any_sync(0xffffffffu, on ? (uint32_t)tile : (0x80000000u + (uint32_t)lane));
-            if (on && (peers & lt) == 0) row[tile] += (uint32_t)__popc(peers);
-            __syncwarp();
-        });
-        __syncthreads();
-        // (ii) start slot of every warp in every tile: tile start + earlier chunks + earlier warps of my chunk
-        for (int t = tid; t < bn; t += kBinThreads) {
-            const size_t gt = (size_t)y0 * a.grid_x + t;
-            uint32_t run = a.M[gt * G + c] + a.tile_start[gt];
-#pragma unroll 8
-            for (int w = 0; w < 32; ++w) {
-                const uint32_t v = rows[w * bn + t];
-                rows[w * bn + t] = run;
-                run += v;
+        const uint32_t bn = (uint32_t)((y1 - y0) * a.grid_x), t0 = (uint32_t)(y0 * a.grid_x);
+        uint32_t* base = reinterpret_cast<uint32_t*>(place_smem);
+        uint16_t* rows = reinterpret_cast<uint16_t*>(place_smem + (size_t)a.band_rows * a.grid_x * 4);
+        uint16_t* row = rows + (size_t)warp * bn;
+        // ---- exclusive scan of the tile totals: start slot of every tile of the band (+ ranges / overflow, written once)
+        {
+            uint32_t before = 0;
+            for (uint32_t t = tid; t < t0; t += kPlaceThreads) before += __ldg(a.tile_total + t);
+            uint32_t run;
+            block_excl(before, run);          // run = sum of every tile before the band
+            for (uint32_t b0 = 0; b0 < bn; b0 += kPlaceThreads) {
+                const uint32_t t = b0 + tid;
+                const uint32_t v = t < bn ? __ldg(a.tile_total + t0 + t) : 0u;
+                uint32_t tot;
+                const uint32_t start = run + block_excl(v, tot);
+                if (t < bn) {
+                    base[t] = start + a.M[(size_t)(t0 + t) * G + c];
+                    // empty tiles keep (0, 0) like the reference's zero-initialised range array (identifyTileRanges, A.2)
+                    if (c == 0) a.ranges[t0 + t] = v ? make_uint2(min(start, a.capacity), min(start + v, a.capacity)) : make_uint2(0u, 0u);
+                }
+                run += tot;
             }
         }
         __syncthreads();
-        // (iii) place: pairs of one step on the same tile take consecutive slots in lane (= depth) order
-        walk_pairs(a.perm, a.rect, a.rec0, a.rec1, a.tight, ks, ke, y0, y1, a.grid_x, [&](bool on, int tile, uint32_t id) {
-            const uint32_t peers = __match_any_sync(0xffffffffu, on ? (uint32_t)tile : (0x80000000u + (uint32_t)lane));
-            uint32_t slot = 0;
-            if (on) slot = row[tile] + (uint32_t)__popc(peers & lt);
-            __syncwarp();
-            if (on) {
-                if ((peers & lt) == 0) row[tile] += (uint32_t)__popc(peers);
-                if (slot < a.capacity) a.ids[slot] = id;
+        for (uint32_t sub = cs; sub < ce; sub += kSubMax) {
+            const uint32_t se = min(ce, sub + kSubMax), len = se - sub, per = (len + kPlaceWarps - 1) / kPlaceWarps;
+            const uint32_t ks = sub + min((uint32_t)warp * per, len), ke = sub + min((uint32_t)(warp + 1) * per, len);
+            for (uint32_t j = tid; j < (kPlaceWarps + 1) * bn / 2 + 1; j += kPlaceThreads)
+                if (2 * j < (kPlaceWarps + 1) * bn) reinterpret_cast<uint32_t*>(rows)[j] = 0u;
+            __syncthreads();
+            // (i) my warp's instance count per tile (plain read-modify-write: one writer per tile and step)
+            walk_pairs(a.perm, a.rect, a.rec0, a.rec1, a.tight, ks, ke, y0, y1, a.grid_x, [&](bool on, int tile, uint32_t) {
+                const uint32_t peers = __match_any_sync(0xffffffffu, on ? (uint32_t)tile : (0x80000000u + (uint32_t)lane));
+                if (on && (peers & lt) == 0) row[tile] = (uint16_t)(row[tile] + __popc(peers));
+                __syncwarp();
+            });
+            __syncthreads();
+            // (ii) exclusive prefix over the warps; the sub-chunk's total per tile goes to the extra row
+            for (uint32_t t = tid; t < bn; t += kPlaceThreads) {
+                uint32_t run = 0;
+#pragma unroll
+                for (int w = 0; w < kPlaceWarps; ++w) {
+                    const uint32_t v = rows[(size_t)w * bn + t];
+                    rows[(size_t)w * bn + t] = (uint16_t)run;
+                    run += v;
+                }
+                rows[(size_t)kPlaceWarps * bn + t] = (uint16_t)run;
             }
-            __syncwarp();
-        });
-        __syncthreads();
+            __syncthreads();
+            // (iii) place: pairs of one step on the same tile take consecutive slots in lane (= depth) order
+            walk_pairs(a.perm, a.rect, a.rec0, a.rec1, a.tight, ks, ke, y0, y1, a.grid_x, [&](bool on, int tile, uint32_t id) {
+                const uint32_t peers = __match_any_sync(0xffffffffu, on ? (uint32_t)tile : (0x80000000u + (uint32_t)lane));
+                uint32_t slot = 0;
+                if (on) slot = base[tile] + row[tile] + (uint32_t)__popc(peers & lt);
+                __syncwarp();
+                if (on) {
+                    if ((peers & lt) == 0) row[tile] = (uint16_t)(row[tile] + __popc(peers));
+                    if (slot < a.capacity) a.ids[slot] = id;
+                }
+                __syncwarp();
+            });
+            __syncthreads();
+            if (se < ce)
+                for (uint32_t t = tid; t < bn; t += kPlaceThreads) base[t] += rows[(size_t)kPlaceWarps * bn + t];
+            __syncthreads();
+        }
     }
+    (void)T;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 namespace {
 constexpr size_t kCountSmemBudget = 160 * 1024;
-constexpr size_t kPlaceSmemBudget = 200 * 1024;
+constexpr size_t kPlaceSmemBudget = 224 * 1024;
 size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 }  // namespace
 
@@ -451,8 +506,8 @@ size_t bin_aux_bytes(int64_t n, int num_tiles, int sm_count) {
            align256(G * (size_t)num_tiles * 4) + 2 * align256((size_t)num_tiles * 4) + align256(sizeof(BinCtl));
 }
 
-cudaError_t launch_bin_sort(int64_t n, int grid_x, int grid_y, const GeomBuffers& g, void* aux, uint2* ranges, uint32_t capacity,
-                            int tight, int sm_count, BinLayout* out, cudaStream_t st) {
+cudaError_t launch_bin_sort(int64_t n, int grid_x, int grid_y, const GeomBuffers& g, void* aux, int tight, int sm_count,
+                            BinLayout* out, cudaStream_t st) {
     const int num_tiles = grid_x * grid_y;
     const size_t N = (size_t)(n > 0 ? n : 1), G = (size_t)sm_count;
     char* p = (char*)aux;
@@ -463,35 +518,36 @@ cudaError_t launch_bin_sort(int64_t n, int grid_x, int grid_y, const GeomBuffers
     a.perm = g.perm;
     a.H = (uint32_t*)take(G * kRadix * 4); a.S = (uint32_t*)take(2 * G * 4); a.chunk_start = (uint32_t*)take((G + 1) * 4);
     a.M = (uint32_t*)take(G * (size_t)num_tiles * 4);
-    a.tile_total = (uint32_t*)take((size_t)num_tiles * 4); a.tile_start = (uint32_t*)take((size_t)num_tiles * 4);
+    a.tile_total = (uint32_t*)take((size_t)num_tiles * 4);
     a.ctl = (BinCtl*)take(sizeof(BinCtl));
-    a.ranges = ranges; a.grid_x = grid_x; a.grid_y = grid_y; a.num_tiles = num_tiles; a.capacity = capacity; a.tight = tight;
+    a.grid_x = grid_x; a.grid_y = grid_y; a.num_tiles = num_tiles; a.tight = tight;
     int rows = (int)(kCountSmemBudget / ((size_t)grid_x * 4));
     if (rows < 1) return cudaErrorInvalidValue;
     a.count_band_rows = rows < grid_y ? rows : grid_y;
     size_t smem = (size_t)a.count_band_rows * grid_x * 4;
     if (smem < kSortSmemBytes) smem = kSortSmemBytes;
-    out->chunk_start = a.chunk_start; out->M = a.M; out->tile_start = a.tile_start; out->ctl = a.ctl; out->chunks = sm_count;
+    out->chunk_start = a.chunk_start; out->M = a.M; out->tile_total = a.tile_total; out->ctl = a.ctl; out->chunks = sm_count;
     cudaError_t e = cudaFuncSetAttribute(bin_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     void* args[] = {&a};
     return cudaLaunchCooperativeKernel((const void*)bin_sort_kernel, dim3((unsigned)sm_count), dim3(kBinThreads), args, smem, st);
 }
 
-cudaError_t launch_bin_place(int grid_x, int grid_y, const GeomBuffers& g, const BinLayout& lay, uint32_t* ids, uint32_t capacity,
-                             int tight, cudaStream_t st) {
+cudaError_t launch_bin_place(int grid_x, int grid_y, const GeomBuffers& g, const BinLayout& lay, uint32_t* ids, uint2* ranges,
+                             uint32_t capacity, int tight, cudaStream_t st) {
     const int num_tiles = grid_x * grid_y;
     BinPlaceArgs a{};
     a.perm = g.perm; a.rect = g.rect; a.rec0 = g.rec0; a.rec1 = g.rec1; a.chunk_start = lay.chunk_start; a.M = lay.M;
-    a.tile_start = lay.tile_start; a.ids = ids; a.capacity = capacity; a.grid_x = grid_x; a.grid_y = grid_y;
+    a.tile_total = lay.tile_total; a.ranges = ranges; a.ids = ids; a.capacity = capacity; a.grid_x = grid_x; a.grid_y = grid_y;
     a.num_tiles = num_tiles; a.tight = tight;
-    a.band_rows = (int)(kPlaceSmemBudget / ((size_t)32 * grid_x * 4));      // 32 per-warp counter rows per band
+    const size_t per_tile = 4 + (kPlaceWarps + 1) * 2;                      // base u32 + 17 u16 counters
+    a.band_rows = (int)(kPlaceSmemBudget / (per_tile * (size_t)grid_x));
     if (a.band_rows < 1) return cudaErrorInvalidValue;
     if (a.band_rows > grid_y) a.band_rows = grid_y;
-    const size_t smem = (size_t)32 * a.band_rows * grid_x * 4;
+    const size_t smem = per_tile * (size_t)a.band_rows * grid_x + 16;
     cudaError_t e = cudaFuncSetAttribute(bin_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    bin_place_kernel<<<lay.chunks, kBinThreads, smem, st>>>(a);
+    bin_place_kernel<<<lay.chunks, kPlaceThreads, smem, st>>>(a);
     return cudaGetLastError();
 }
 

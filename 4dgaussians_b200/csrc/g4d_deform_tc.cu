@@ -15,15 +15,24 @@
 //   * the tile's 128 result rows stay in registers of their owner threads, which finish the Gaussian
 //     (activations, EWA projection, SH colour) exactly like the SIMT path (geom_finish.cuh).
 //
-// TMEM map (512 columns): [0,128) A1 hi, [128,256) A1 lo, [256,384) D (layer-1 accumulators; D2 reuses [256,256+48)),
-// [384,512) X: feature operand (hi [384,384+F), lo [448,448+F)) then the head's hidden half (hi [384,448), lo [448,512)).
+// TMEM map (512 columns): [0,128) A1 hi, [128,256) A1 lo, [256,384) D0, [384,512) D1 = X.
+//   D0 / D1: the layer-1 accumulators of consecutive heads ALTERNATE between the two, so that the GEMM of head k+1 runs on
+//            the tensor pipe while the 256 epilogue threads drain head k (the SH head always gets D0; its layer-2 output D2
+//            reuses D0[0,48));
+//   X (= D1): feature operand of layer 0 (hi [384,384+F), lo [448,448+F)) at the start of a tile, the SH head's hidden half
+//            (hi [384,448), lo [448,512)) at its end -- both at times when no head GEMM owns D1.
+// W1 streaming: the 128 KB (hi | lo) image of a head is split into two K-halves of 64 KB, each with its own "landed" and
+// "consumed" mbarrier: while the MMAs of K-half 1 of head k run, the TMA of K-half 0 of head k+1 is already in flight, so
+// the tensor pipe never waits for a whole-image copy (measured before: 960 cycles of exposed TMA wait per head + the whole
+// epilogue serialised behind every GEMM).  The issuer thread drives this as a small non-blocking state machine (`pump`)
+// polled between the chunks of its own epilogue work and inside its waits.
 // Compiled with -fmad=false (it contains the projection, see g4d_math.cuh).
 #include "geom_finish.cuh"
 #include "tc_umma.cuh"
 
 namespace g4d {
 
-constexpr uint32_t kColA1Hi = 0, kColA1Lo = 128, kColD = 256, kColX = 384, kColXLo = 448;
+constexpr uint32_t kColA1Hi = 0, kColA1Lo = 128, kColD = 256, kColD1 = 384, kColX = 384, kColXLo = 448;
 
 struct TcSmem { uint32_t w1, w2, w0, bias, w2s, bars, acc, total; };
 
@@ -36,7 +45,7 @@ inline TcSmem tc_smem_layout(int F, int max_kp16) {
     s.w0 = take(2u * 128 * F * 4);
     s.bias = take((128 + G4D_NUM_HEADS * 128 + 64) * 4);
     s.w2s = take(4 * 128 * 16);
-    s.bars = take(64);
+    s.bars = take(128);     // 9 mbarriers
     s.acc = take(2 * 128 * 16);
     s.total = off;
     return s;
@@ -47,6 +56,7 @@ struct TcPackDesc {
     const float* src[1 + 2 * G4D_NUM_HEADS];
     float* dst[1 + 2 * G4D_NUM_HEADS];
     int rows_src[1 + 2 * G4D_NUM_HEADS], rows_dst[1 + 2 * G4D_NUM_HEADS], K[1 + 2 * G4D_NUM_HEADS];
+    int khalves[1 + 2 * G4D_NUM_HEADS];   // 1: image = (hi_k0 | lo_k0 | hi_k1 | lo_k1), each K-half canonical with K / 2 columns
     int start[2 + 2 * G4D_NUM_HEADS];
     int count;
 };
@@ -62,6 +72,13 @@ __global__ void tc_pack_weights_kernel(TcPackDesc p) {
     const float v = (int)n < p.rows_src[m] ? __ldg(p.src[m] + n * K + k) : 0.f;
     uint32_t hi, lo;
     tc::tf32_split(v, hi, lo);
+    if (p.khalves[m]) {
+        const uint32_t Kh = K >> 1, j = k / Kh, blk = p.rows_dst[m] * Kh;          // words per (part, K-half) block
+        const uint32_t off = tc::canon_off(n, k - j * Kh, Kh) >> 2;
+        reinterpret_cast<uint32_t*>(p.dst[m])[(2 * j) * blk + off] = hi;
+        reinterpret_cast<uint32_t*>(p.dst[m])[(2 * j + 1) * blk + off] = lo;
+        return;
+    }
     const uint32_t off = tc::canon_off(n, k, K) >> 2;
     reinterpret_cast<uint32_t*>(p.dst[m])[off] = hi;
     reinterpret_cast<uint32_t*>(p.dst[m])[p.rows_dst[m] * K + off] = lo;
@@ -79,8 +96,9 @@ cudaError_t launch_tc_pack_weights(const G4DDeformParams& prm, float* blob, TcWe
     const int F = prm.levels * prm.channels;
     int m = 0, total = 0;
     float* q = blob;
-    auto add = [&](const float* src, int rows_src, int rows_dst, int K) {
-        p.src[m] = src; p.dst[m] = q; p.rows_src[m] = rows_src; p.rows_dst[m] = rows_dst; p.K[m] = K; p.start[m] = total;
+    auto add = [&](const float* src, int rows_src, int rows_dst, int K, int khalves = 0) {
+        p.src[m] = src; p.dst[m] = q; p.rows_src[m] = rows_src; p.rows_dst[m] = rows_dst; p.K[m] = K; p.khalves[m] = khalves;
+        p.start[m] = total;
         total += rows_dst * K; float* r = q; q += 2 * (size_t)rows_dst * K; ++m; return r;
     };
     out->w0 = add(prm.w0, 128, 128, F);
@@ -88,7 +106,7 @@ cudaError_t launch_tc_pack_weights(const G4DDeformParams& prm, float* blob, TcWe
         out->kp16[h] = h == 4 ? 48 : 16;
         out->w1[h] = nullptr; out->w2[h] = nullptr;
         if (!(prm.head_mask & (1 << h))) continue;
-        out->w1[h] = add(prm.w1[h], 128, 128, 128);
+        out->w1[h] = add(prm.w1[h], 128, 128, 128, 1);
         out->w2[h] = add(prm.w2[h], head_out(h), out->kp16[h], 128);
     }
     p.start[m] = total; p.count = m;
@@ -178,6 +196,29 @@ __device__ __forceinline__ void store_relu_half(uint32_t* base, int slot, int64_
     *reinterpret_cast<uint2*>(base + ((size_t)slot * (size_t)n + (size_t)gi) * 4 + word0) = make_uint2(lo, hi);
 }
 
+// non-blocking probe of an mbarrier phase (mbar_wait spins on the blocking form)
+__device__ __forceinline__ bool mbar_test(void* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+
+// The issuer thread's view of the W1 stream.  Loads and GEMMs are numbered q = 0, 1, ... over (tile, active head) in
+// program order; each consists of two K-halves j.  th / mh = 2 q + j of the next TMA / MMA half to issue.
+struct TcPump {
+    uint32_t th, mh;        // next TMA half, next MMA half
+    uint32_t total;         // number of (tile, head) GEMMs of this CTA
+    int32_t allow;          // highest GEMM index that may START (its D buffer is free and A1 is ready)
+    uint32_t m;             // active heads per tile
+    uint32_t par0;          // D buffer of head k of a tile = (k + par0) & 1
+};
+
 template <int MODE, int C, int L, bool SAVE>
 __global__ void __launch_bounds__(256, 1)
 deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restrict__ camp, float time_arg, int use_cam_time,
@@ -202,7 +243,9 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
     float* sBias = reinterpret_cast<float*>(smem + Ls.bias);     // b0[128] | b1[5][128] | b2[64]
     float4* sW2s = reinterpret_cast<float4*>(smem + Ls.w2s);     // [4 small heads][128 hidden]: (W2[0][j], W2[1][j], W2[2][j], W2[3][j])
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Ls.bars);
-    uint64_t *bar_w0 = bars, *bar_w1 = bars + 1, *bar_l0 = bars + 3, *bar_l1 = bars + 4, *bar_l2 = bars + 5;
+    // bars: 0 w0 | 1,2 full[j] (W1 K-half j landed) | 3,4 hfree[j] (its MMAs retired) | 5,6 dfull[b] (head GEMM into D[b]
+    // complete) | 7 l0 | 8 l2
+    uint64_t *bar_w0 = bars, *bar_full = bars + 1, *bar_hfree = bars + 3, *bar_dfull = bars + 5, *bar_l0 = bars + 7, *bar_l2 = bars + 8;
     int b2off[G4D_NUM_HEADS];
     {
         int o = 0;
@@ -223,7 +266,7 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
     }
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, tc::kTmemCols);
     if (tid == 0) {
-        mbar_init(bar_w0, 1); mbar_init(bar_w1, 1); mbar_init(bar_l0, 1); mbar_init(bar_l1, 1); mbar_init(bar_l2, 1);
+        for (int i = 0; i < 9; ++i) mbar_init(bars + i, 1);
         fence_barrier_init();
     }
     tc::fence_before_sync();
@@ -234,25 +277,73 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
     const uint32_t sW1 = tc::smem_addr(smem + Ls.w1), sW2 = tc::smem_addr(smem + Ls.w2), sW0 = tc::smem_addr(smem + Ls.w0);
     const bool hsh = d.head_mask & G4D_HEAD_SHS;
     const float t = use_cam_time ? cam.time : time_arg;
-    float amax[3], ascale[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) { amax[a] = __ldg(d.aabb + a); ascale[a] = 2.0f / (__ldg(d.aabb + 3 + a) - amax[a]); }
+    (void)t;
 
-    // ---- resident operands: W0 and (when active) the SH head's W2 image; first head's W1
+    // ---- the W1 stream of this CTA (issuer thread only uses it)
+    TcPump pp{};
+    pp.m = (uint32_t)__popc(d.head_mask & 31);
+    pp.par0 = hsh ? ((pp.m - 1u) & 1u) : 0u;
+    {
+        const int64_t my_tiles = (int64_t)blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+        pp.total = (uint32_t)my_tiles * pp.m;
+    }
+    pp.allow = -1;
+    // head id of the k-th active head
+    auto head_of = [&](uint32_t k) {
+        int h = 0, seen = -1;
+        for (; h < G4D_NUM_HEADS; ++h)
+            if (d.head_mask & (1 << h)) { if (++seen == (int)k) break; }
+        return h;
+    };
+    // issue whatever the stream allows right now; never blocks
+    auto pump = [&]() {
+        bool progress = true;
+        while (progress) {
+            progress = false;
+            {   // next W1 K-half copy: its buffer must have been consumed by the previous GEMM
+                const uint32_t q = pp.th >> 1, j = pp.th & 1u;
+                if (q < pp.total && (q == 0 || mbar_test(bar_hfree + j, (q - 1u) & 1u))) {
+                    const int h = head_of(q % pp.m);
+                    mbar_expect_tx(bar_full + j, 65536u);
+                    tma_bulk_g2s(smem + Ls.w1 + j * 65536u, tw.w1[h] + j * 16384u, 65536u, bar_full + j);
+                    ++pp.th;
+                    progress = true;
+                }
+            }
+            {   // next GEMM K-half: its weights must have landed, its D buffer must be free, A1 must be ready
+                const uint32_t q = pp.mh >> 1, j = pp.mh & 1u;
+                if (q < pp.total && (int32_t)q <= pp.allow && mbar_test(bar_full + j, q & 1u)) {
+                    const uint32_t b = ((q % pp.m) + pp.par0) & 1u;
+                    tc::fence_after_sync();
+                    tc::gemm_3xtf32<64>(tbase + (b ? kColD1 : kColD), tbase + kColA1Hi + j * 64u, tbase + kColA1Lo + j * 64u,
+                                        sW1 + j * 65536u, sW1 + j * 65536u + 32768u, 128, 64, 0, j != 0);
+                    tc::umma_commit(bar_hfree + j);
+                    if (j) tc::umma_commit(bar_dfull + b);
+                    ++pp.mh;
+                    progress = true;
+                }
+            }
+        }
+    };
+    // wait for an mbarrier phase; the issuer keeps the stream moving meanwhile
+    auto wait_pumping = [&](uint64_t* bar, uint32_t parity) {
+        if (issuer) {
+            while (!mbar_test(bar, parity)) pump();
+        } else {
+            mbar_wait(bar, parity);
+        }
+    };
+
+    // ---- resident operands: W0 and (when active) the SH head's W2 image; the first two W1 K-halves
     if (issuer) {
         const uint32_t w2b = hsh ? 2u * 48 * 128 * 4 : 0u;
         mbar_expect_tx(bar_w0, 2u * 128 * F * 4 + w2b);
         tma_bulk_g2s(smem + Ls.w0, tw.w0, 2u * 128 * F * 4, bar_w0);
         if (hsh) tma_bulk_g2s(smem + Ls.w2, tw.w2[4], w2b, bar_w0);
-        if (d.head_mask) {
-            const int h0 = __ffs(d.head_mask) - 1;
-            mbar_expect_tx(bar_w1, 2u * 65536);
-            tma_bulk_g2s(smem + Ls.w1, tw.w1[h0], 65536, bar_w1);
-            tma_bulk_g2s(smem + Ls.w1 + 65536, tw.w1[h0] + 16384, 65536, bar_w1);
-        }
+        pump();
     }
     if (is_m) mbar_wait(bar_w0, 0);
-    uint32_t ph_w1 = 0, ph_l0 = 0, ph_l1 = 0, ph_l2 = 0;
+    uint32_t ph_l0 = 0, ph_l2 = 0, ph_d0 = 0, ph_d1 = 0;
     // column chunks (16 hidden units each) of every epilogue are split between the two thread groups
     const int ch_lo = is_m ? 4 : 0, ch_hi = is_m ? 8 : 4;        // full-width epilogues (8 chunks)
     const int hc_lo = is_m ? 2 : 0, hc_hi = is_m ? 4 : 2;        // half-width epilogues of the SH head (4 chunks)
@@ -294,7 +385,8 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
 #define G4D_CYC(i) do { if (tw.dbg && issuer) { const long long tn_ = clock64(); cyc[i] += tn_ - tprev; tprev = tn_; } } while (0)
     bool first = true;
     int hseq = 0;   // running small-head counter -> sAcc buffer
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
+    uint32_t tile_q0 = 0;   // GEMM index of this tile's first head
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false, tile_q0 += pp.m) {
         const int64_t gi = tile * 128 + row;
         const bool valid = gi < n;
         const bool has_next = tile + gridDim.x < ntiles;
@@ -307,7 +399,7 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
             if (io.opacity) ol = io.opacity[gi];
         }
         G4D_CYC(0);   // input loads
-        // ---- layer 0: D = feat * W0^T   (features were put into X by the G group)
+        // ---- layer 0: D0 = feat * W0^T   (features were put into X by the G group)
         if (is_m) {
             bar_sync(kBarFeat, 256);
             G4D_CYC(1);   // wait for the features
@@ -317,18 +409,19 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                 tc::umma_commit(bar_l0);
             }
         }
-        mbar_wait(bar_l0, ph_l0); ph_l0 ^= 1u;
+        wait_pumping(bar_l0, ph_l0); ph_l0 ^= 1u;
         tc::fence_after_sync();
         G4D_CYC(2);   // layer-0 MMA
         if (is_m && !first) { bar_sync(kBarScratchFree, 256); tc::fence_after_sync(); }   // G has read the previous tile's scratch (A1 region)
         G4D_CYC(3);   // wait scratch free
-        // ---- epilogue 0: a1 = relu(D + b0) -> A1 (hi | lo); ReLU sign bits saved for the backward
+        // ---- epilogue 0: a1 = relu(D0 + b0) -> A1 (hi | lo); ReLU sign bits saved for the backward
         uint32_t rb[4] = {0u, 0u, 0u, 0u};   // my chunks' sign bits: 2 chunks per word
 #pragma unroll 1
         for (int ch = ch_lo; ch < ch_hi; ++ch) {
             const uint32_t c0 = (uint32_t)(ch * 16);
             uint32_t v[16], hi[16], lo[16];
             tc::tmem_ld16(lane_base + kColD + c0, v);
+            if (issuer) pump();
             tc::wait_ld();
             float bb[16];
 #pragma unroll
@@ -351,6 +444,8 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
         tc::wait_st();
         tc::fence_before_sync();
         bar_sync(kBarE, 256);
+        // A1 is complete and both accumulators are free: the first TWO head GEMMs of this tile may start
+        if (issuer) { pp.allow = (int32_t)min(tile_q0 + 1u, tile_q0 + pp.m - 1u); pump(); }
         G4D_CYC(4);   // epilogue 0
 
         float dl[11];
@@ -360,35 +455,19 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
 #pragma unroll
         for (int j = 0; j < 48; ++j) dsh[j] = 0.f;
 
+        uint32_t kact = 0;   // index of the head among the active ones
 #pragma unroll 1
         for (int h = 0; h < G4D_NUM_HEADS; ++h) {
             if (!(d.head_mask & (1 << h))) continue;
             const float* b1 = sBias + 128 + h * 128;
             const float* b2 = sBias + 128 + G4D_NUM_HEADS * 128 + b2off_of(d.head_mask, h);
-            int nh = -1;   // next head whose W1 goes into the buffer once this head has released it
-            {
-                const int later = d.head_mask >> (h + 1);
-                if (later) nh = h + 1 + (__ffs(later) - 1);
-                else if (has_next) nh = __ffs(d.head_mask) - 1;
-            }
-            // ---- layer 1: D = a1 * W1^T
-            if (is_m) {
-                mbar_wait(bar_w1, ph_w1); ph_w1 ^= 1u;
-                G4D_CYC(5);   // wait W1
-                if (issuer) {
-                    tc::fence_after_sync();
-                    tc::gemm_3xtf32<128>(tbase + kColD, tbase + kColA1Hi, tbase + kColA1Lo, sW1, sW1 + 65536u, 128, 128, 0, false);
-                    tc::umma_commit(bar_l1);
-                }
-            }
-            mbar_wait(bar_l1, ph_l1); ph_l1 ^= 1u;
+            const uint32_t db = (kact + pp.par0) & 1u;                  // accumulator of this head
+            const uint32_t dcol = db ? kColD1 : kColD;
+            // ---- layer 1 (issued ahead by the pump): wait for D[db] = a1 * W1^T
+            wait_pumping(bar_dfull + db, db ? ph_d1 : ph_d0);
+            if (db) ph_d1 ^= 1u; else ph_d0 ^= 1u;
             tc::fence_after_sync();
-            G4D_CYC(6);   // layer-1 MMA
-            if (issuer && nh >= 0) {   // W1 buffer is free: stream the next W1
-                mbar_expect_tx(bar_w1, 2u * 65536);
-                tma_bulk_g2s(smem + Ls.w1, tw.w1[nh], 65536, bar_w1);
-                tma_bulk_g2s(smem + Ls.w1 + 65536, tw.w1[nh] + 16384, 65536, bar_w1);
-            }
+            G4D_CYC(6);   // layer-1 MMA not hidden behind the previous epilogue
             rb[0] = rb[1] = rb[2] = rb[3] = 0u;
             if (h < 4) {
                 // ---- small head: layer 2 (k <= 4 outputs) fused into the epilogue in exact fp32 -- cheaper than two
@@ -398,7 +477,8 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
 #pragma unroll 1
                 for (int ch = ch_lo; ch < ch_hi; ++ch) {
                     uint32_t v[16];
-                    tc::tmem_ld16(lane_base + kColD + ch * 16, v);
+                    tc::tmem_ld16(lane_base + dcol + ch * 16, v);
+                    if (issuer) pump();
                     tc::wait_ld();
                     float bb[16];
 #pragma unroll
@@ -422,7 +502,8 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                 float4* slot = sAcc + (hseq & 1) * 128 + row;
                 if (!is_m) *slot = acc;
                 tc::fence_before_sync();
-                bar_sync(kBarE, 256);   // partial sums visible; D may be overwritten by the next layer-1 GEMM
+                bar_sync(kBarE, 256);   // partial sums visible; D[db] may be overwritten by the GEMM of head kact + 2
+                if (issuer) { pp.allow = (int32_t)min(tile_q0 + kact + 2u, tile_q0 + pp.m - 1u); pump(); }
                 if (is_m) {
                     // fixed summation order: (G's hidden units 0..63) + (M's hidden units 64..127)
                     const float4 ga = *slot;
@@ -435,15 +516,17 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                 ++hseq;
                 G4D_CYC(8);   // small-head epilogue + fp32 layer 2
             } else {
+                // the SH head is the last one and owns D0; D1 (= X) was drained by the previous head's epilogue
 #pragma unroll 1
                 for (int hh = 0; hh < 2; ++hh) {
-                    // hidden half hh: a2 = relu(D[:, 64hh : 64hh+64] + b1) -> X (hi | lo)
+                    // hidden half hh: a2 = relu(D0[:, 64hh : 64hh+64] + b1) -> X (hi | lo)
 #pragma unroll 1
                     for (int ch = hc_lo; ch < hc_hi; ++ch) {
                         const uint32_t cl = (uint32_t)(ch * 16);
                         const uint32_t cg = (uint32_t)(hh * 64) + cl;
                         uint32_t v[16], hi[16], lo[16];
                         tc::tmem_ld16(lane_base + kColD + cg, v);
+                        if (issuer) pump();
                         tc::wait_ld();
                         float bb[16];
 #pragma unroll
@@ -466,14 +549,14 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                     tc::fence_before_sync();
                     bar_sync(kBarE, 256);
                     G4D_CYC(8);   // hidden-half epilogue
-                    // ---- layer 2 partial: D2 (+)= a2_half * W2[:, 64hh : 64hh+64]^T   (D2 = D columns [0, 48))
+                    // ---- layer 2 partial: D2 (+)= a2_half * W2[:, 64hh : 64hh+64]^T   (D2 = D0 columns [0, 48))
                     if (issuer) {
                         tc::fence_after_sync();
                         tc::gemm_3xtf32<64>(tbase + kColD, tbase + kColX, tbase + kColXLo, sW2, sW2 + 48u * 128 * 4, 48, 128,
                                             (uint32_t)(hh * 16), hh == 1);
                         tc::umma_commit(bar_l2);
                     }
-                    mbar_wait(bar_l2, ph_l2); ph_l2 ^= 1u;
+                    wait_pumping(bar_l2, ph_l2); ph_l2 ^= 1u;
                     tc::fence_after_sync();
                     G4D_CYC(9);   // layer-2 partial MMA
                 }
@@ -492,13 +575,14 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                         for (int j = 0; j < 16; ++j) dsh[ch * 16 + j] = __uint_as_float(v[j]) + b2[ch * 16 + j];
                     }
                     tc::fence_before_sync();
-                    bar_sync(kBarM, 128);   // D may be overwritten by the next layer-1 / layer-0 GEMM
+                    bar_sync(kBarM, 128);   // D0 may be overwritten by the next tile's layer-0 GEMM
                 }
             }
+            ++kact;
             G4D_CYC(10);  // head output / hand-over
         }
         if (is_m) {
-            if (has_next) bar_arrive(kBarXFree, 256);   // every MMA reading X has completed: G may store the next tile's features
+            if (has_next) bar_arrive(kBarXFree, 256);   // every MMA reading X / writing D1 has completed: G may store the next tile's features
             p.x += dl[0]; p.y += dl[1]; p.z += dl[2];
             // ---- hand the deformed position and the SH deltas to the G thread of this lane (A1 is dead now)
             {
@@ -517,6 +601,7 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                 tc::fence_before_sync();
                 bar_arrive(kBarScratch, 256);
             }
+            if (issuer) pump();   // (prefetch of the next tile's first W1 halves once the last GEMM has retired)
             // ---- finish the geometric half of my Gaussian
             if (valid) {
                 sl[0] += dl[3]; sl[1] += dl[4]; sl[2] += dl[5];
@@ -531,6 +616,7 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                     fused_finish_geometry(cam, io, gi, p, sl, q, ol);
                 }
             }
+            if (issuer) pump();
             G4D_CYC(11);  // scratch hand-off + geometry tail
         } else {
             // ---- G tail: next tile's features, then the SH colour of my Gaussian once M has published p and the SH deltas

@@ -36,27 +36,26 @@ struct BinSortArgs {
     uint32_t* S;                   // [chunks] tiles_touched sums of equal-count slices
     uint32_t* chunk_start;         // [chunks + 1] positions in perm
     uint32_t* M;                   // [chunks][tiles] instance counts, then exclusive prefix over the chunks
-    uint32_t* tile_total;          // [tiles]
-    uint32_t* tile_start;          // [tiles] exclusive scan of tile_total (unclamped)
-    uint2* ranges;                 // [tiles] clamped to the capacity
+    uint32_t* tile_total;          // [tiles] instances per tile
     BinCtl* ctl;
     int grid_x, grid_y, num_tiles, count_band_rows;
-    uint32_t capacity; int tight;
+    int tight;
 };
 struct BinPlaceArgs {
     const uint32_t* perm; const uint2* rect; const float4* rec0; const float4* rec1;
-    const uint32_t* chunk_start; const uint32_t* M; const uint32_t* tile_start;
+    const uint32_t* chunk_start; const uint32_t* M; const uint32_t* tile_total;
+    uint2* ranges;                 // [tiles] (start, end) clamped to the capacity; empty tiles (0, 0)
     uint32_t* ids; uint32_t capacity;
     int grid_x, grid_y, num_tiles, band_rows, tight;
 };
-struct BinLayout { uint32_t* chunk_start; uint32_t* M; uint32_t* tile_start; BinCtl* ctl; int chunks; };
+struct BinLayout { uint32_t* chunk_start; uint32_t* M; uint32_t* tile_total; BinCtl* ctl; int chunks; };
 size_t bin_aux_bytes(int64_t n, int num_tiles, int sm_count);
-// depth sort + chunking + per-(chunk, tile) counts + scans: ranges, tile_start, ctl->R.  One cooperative launch.
-cudaError_t launch_bin_sort(int64_t n, int grid_x, int grid_y, const GeomBuffers& g, void* aux, uint2* ranges, uint32_t capacity,
-                            int tight, int sm_count, BinLayout* out, cudaStream_t st);
-// stable counting placement of every instance into its tile segment
-cudaError_t launch_bin_place(int grid_x, int grid_y, const GeomBuffers& g, const BinLayout& lay, uint32_t* ids, uint32_t capacity,
-                             int tight, cudaStream_t st);
+// depth sort + chunking + per-(tile, chunk) counts + scan over the chunks: M, tile_total, ctl->R.  One cooperative launch.
+cudaError_t launch_bin_sort(int64_t n, int grid_x, int grid_y, const GeomBuffers& g, void* aux, int tight, int sm_count,
+                            BinLayout* out, cudaStream_t st);
+// tile ranges + stable counting placement of every instance into its tile segment
+cudaError_t launch_bin_place(int grid_x, int grid_y, const GeomBuffers& g, const BinLayout& lay, uint32_t* ids, uint2* ranges,
+                             uint32_t capacity, int tight, cudaStream_t st);
 
 struct ImageBuffers {
     float* final_T;      // [H*W]

@@ -79,8 +79,8 @@ class FlatState:
     def __init__(self, groups: Sequence, device):
         self.groups = [(n, list(ps)) for n, ps in groups]
         self.device = device
-        total = sum(p.numel() for _, ps in self.groups for p in ps)
-        self.numel = (total + 3) // 4 * 4
+        # every tensor starts on a 16-byte boundary: the kernels read rotations / SH rows / planes with 128-bit loads
+        self.numel = sum((p.numel() + 3) // 4 * 4 for _, ps in self.groups for p in ps)
         self.param = torch.zeros(self.numel, device=device)
         self.grad = torch.zeros(self.numel, device=device)
         self.exp_avg = torch.zeros(self.numel, device=device)
@@ -106,7 +106,7 @@ class FlatState:
                 gv = view(self.grad)
                 p.grad = gv
                 self._views.append((p, pv, gv, off, n))
-                off += n
+                off += (n + 3) // 4 * 4
             self.segments[name] = (begin, off)
         self.step_count = 0
 
@@ -127,22 +127,35 @@ class FlatState:
     def zero_grad(self):
         self.grad.zero_()
 
-    def adam_step(self, lrs: Dict[str, float], grad_scale: float = 1.0, betas=(0.9, 0.999), eps=1e-15, only=None):
-        """``only``: restrict the update to these groups (the rest is left untouched, moments included)."""
+    def adam_step(self, lrs: Dict[str, float], grad_scale: float = 1.0, betas=(0.9, 0.999), eps=1e-15, only=None,
+                  span=None, count_step: bool = True):
+        """``only``: restrict the update to these groups (the rest is left untouched, moments included).
+        ``span`` = (begin, end), multiples of 4: update only that slice of the flat buffers (chunked all-reduce pipeline)."""
         if not self.attached():
             raise RuntimeError("FlatState: a parameter's .data / .grad is no longer a view of the flat buffers (zero_grad("
                                "set_to_none=True) or a parameter swap); use zero_grad() of this object and rebuild after densify")
-        self.step_count += 1
-        names = [n for n, _ in self.groups if only is None or n in only]
-        segs = (_lib.AdamSegment * len(names))()
-        for i, n in enumerate(names):
-            segs[i].begin, segs[i].end, segs[i].lr = self.segments[n][0], self.segments[n][1], float(lrs[n])
+        if count_step:
+            self.step_count += 1
+        b0, e0 = (0, self.numel) if span is None else span
+        clipped = []
+        for n, _ in self.groups:
+            if only is not None and n not in only:
+                continue
+            sb, se = max(self.segments[n][0], b0), min(self.segments[n][1], e0)
+            if se > sb:
+                clipped.append((sb - b0, se - b0, float(lrs[n])))
+        if not clipped:
+            return
+        segs = (_lib.AdamSegment * len(clipped))()
+        for i, (sb, se, lr) in enumerate(clipped):
+            segs[i].begin, segs[i].end, segs[i].lr = sb, se, lr
         dev = self.device
+        off = 4 * b0
         with torch.cuda.device(dev):
             ws = _lib.Workspace.get(dev.index if dev.index is not None else torch.cuda.current_device())
-            _lib.check(_lib.load().g4d_adam_step(ws.handle, self.param.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
-                                                 self.exp_avg_sq.data_ptr(), self.numel, segs, len(names), betas[0], betas[1], eps,
-                                                 self.step_count, float(grad_scale),
+            _lib.check(_lib.load().g4d_adam_step(ws.handle, self.param.data_ptr() + off, self.grad.data_ptr() + off,
+                                                 self.exp_avg.data_ptr() + off, self.exp_avg_sq.data_ptr() + off, e0 - b0, segs,
+                                                 len(clipped), betas[0], betas[1], eps, self.step_count, float(grad_scale),
                                                  int(torch.cuda.current_stream(dev).cuda_stream)), "g4d_adam_step")
 
 
@@ -263,23 +276,50 @@ class DPTrainer:
             w = float(self.world)
             losses.accumulate_regulation(g._deformation, o.time_smoothness_weight * w, o.l1_time_planes * w, o.plane_tv_weight * w,
                                          loss_accum=None)
-        # ---- ONE collective over every gradient of the step; densification statistics ride along
+        # ---- the step's ONE exchange: the flat gradient buffer, reduced in `comm_chunks` back-to-back slices so that Adam on
+        #      slice i overlaps the reduction of slice i + 1 (the collective runs on the backend's own stream)
+        works = None
         if self.dist is not None and self.world > 1:
-            self.dist.all_reduce(self.state.grad, op=self.dist.ReduceOp.SUM)
+            works = self._launch_allreduce()
         if it < o.densify_until_iter:
             g.max_radii2D[vis_any] = torch.maximum(g.max_radii2D[vis_any], radii_max[vis_any])
             g.xyz_gradient_accum[vis_any] += torch.norm(m2d_grad[vis_any, :2], dim=-1, keepdim=True)
             g.denom[vis_any] += 1
             if it % o.densification_interval == 0 or it % o.pruning_interval == 0:
+                if works is not None:                  # a rebuild copies the reduced network gradients: finish the exchange first
+                    for _, _, w in works:
+                        w.wait()
                 self._densify_and_prune(it, stage)
             if it % o.opacity_reset_interval == 0:
                 self.reset_opacity()
         # after a densify / prune the per-Gaussian tensors are new Parameters without gradients: like the reference's
         # optimizer.step() (which skips grad-less parameters, train.py:290), this step only updates the network
         only = ("grid", "deformation") if self._rebuilt_this_step else None
+        lrs = self.learning_rates(it)
+        if works is None or self._rebuilt_this_step:
+            if works is not None:
+                for _, _, w in works:
+                    w.wait()
+            self.state.adam_step(lrs, grad_scale=1.0 / self.world, only=only)
+        else:
+            for i, (b, e, w) in enumerate(works):
+                w.wait()                                   # the current stream waits for slice i only
+                self.state.adam_step(lrs, grad_scale=1.0 / self.world, span=(b, e), count_step=(i == 0))
         self._rebuilt_this_step = False
-        self.state.adam_step(self.learning_rates(it), grad_scale=1.0 / self.world, only=only)
         return self.loss_accum
+
+    comm_chunks = 4
+
+    def _launch_allreduce(self):
+        st = self.state
+        k = max(1, int(self.comm_chunks))
+        step = (st.numel // k + 3) // 4 * 4
+        works, b = [], 0
+        while b < st.numel:
+            e = min(st.numel, b + step)
+            works.append((b, e, self.dist.all_reduce(st.grad[b:e], op=self.dist.ReduceOp.SUM, async_op=True)))
+            b = e
+        return works
 
     def _global_stats(self):
         """(sum of ||grad means2D||, visible count, max radii) over ALL ranks.  The per-rank accumulators stay local (they

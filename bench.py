@@ -536,14 +536,13 @@ def gpu_eager_baseline(g4d, synth, w, scene, mod, dev):
 
 
 def run_train_steps(g4d, synth, lib, w, scene, mod, dev, dist, world, rank, steps, warmup, flush):
-    """Full train step per rank: B=2 views (cook_spinach batch size) fused fwd + bwd, L1 loss against a resident target,
-    ONE flat-bucket NCCL all-reduce of all gradients, fused Adam.  Returns ms per step (max over ranks)."""
-    dp = importlib.import_module("4dgaussians_b200.dp")
-    pc = synth.SyntheticGaussianModel(scene, mod, device=dev, sh_degree=3, requires_grad=True)
-    params = pc.gaussian_parameters() + [p for p in mod.flat_parameters()]
-    bucket = dp.FlatGradBucket(params)
-    mod.fused_grad_accumulation = True      # backward kernels add straight into the bucket views (deformation.py)
-    opt = torch.optim.Adam([{"params": params, "lr": 1e-4}], eps=1e-15, fused=True)
+    """Full train step per rank through the data-parallel harness (4dgaussians_b200/train_dp.py, the shape of
+    train.py:180-226,259-292): B=2 views (cook_spinach batch size) fused fwd + bwd, fused L1 loss kernel against a resident
+    target, HexPlane regulariser kernel, densification statistics, the flat gradient buffer all-reduced in 4 slices
+    pipelined with ONE-launch Adam slices.  Returns ms per step (max over ranks)."""
+    td = importlib.import_module("4dgaussians_b200.train_dp")
+    gs = td.GaussianSet(scene, mod, device=dev, sh_degree=3)
+    tr = td.DPTrainer(gs, td.default_opt(), dist=dist, world_size=world, rank=rank, cameras_extent=2.6, seed=0)
     B = 2
     cams = synth.orbit_cameras(64, w["width"], w["height"], radius=w["radius"], focal=w["focal"], timestamps=300)
     bg = torch.tensor(w["bg"], dtype=torch.float32, device=dev)
@@ -557,14 +556,8 @@ def run_train_steps(g4d, synth, lib, w, scene, mod, dev, dist, world, rank, step
             if dist is not None:
                 dist.barrier()
         a.record()
-        bucket.zero_()
-        for v in range(B):
-            cam = cams[((it * B + v) * world + rank) % len(cams)]
-            out = g4d.render(cam, pc, Pipe, bg)
-            loss = torch.nn.functional.l1_loss(out["render"], target) / B       # = utils/loss_utils.py:l1_loss
-            loss.backward()
-        bucket.allreduce_mean(dist, world)
-        opt.step()
+        mine = [cams[((it * B + v) * world + rank) % len(cams)] for v in range(B)]
+        tr.step(mine, [target] * B, bg, Pipe)
         b.record()
         if it >= warmup:
             evs.append((a, b))
@@ -572,14 +565,17 @@ def run_train_steps(g4d, synth, lib, w, scene, mod, dev, dist, world, rank, step
     ms = _max_over_ranks(dist, dev, sum(x.elapsed_time(y) for x, y in evs) / len(evs))
     ctx = lib.Workspace.get(dev.index)._free_contexts
     st = ctx[-1].stage_times() if ctx else {}
+    numel = tr.state.numel
     mod.fused_grad_accumulation = False
-    for p in params:
+    for p in mod.parameters():
         p.grad = None
     return {"ms_per_step": ms, "step_ms": [round(x.elapsed_time(y), 3) for x, y in evs],
             "views_per_step_per_gpu": B, "global_batch": B * world,
             "arithmetic": "forward MLP 3xTF32 (fp32-accurate); backward MLP BF16 hi+lo, 3 products (~16 mantissa bits) vs the "
                           "reference's fp32 SGEMM; everything else fp32",
-            "includes": "2x fused fwd+bwd (network gradients accumulated straight into the flat bucket), L1 loss, one flat-bucket all-reduce (%d floats), fused Adam" % bucket.numel,
+            "includes": "DPTrainer.step: 2x fused fwd+bwd (network gradients accumulated straight into the flat buffer), fused L1 "
+                        "loss + gradient kernels, HexPlane regulariser kernel, densification statistics, all-reduce of the flat "
+                        "gradient buffer (%d floats, 4 pipelined slices), one-launch Adam per slice" % numel,
             "last_view_stage_ms": st}
 
 

@@ -28,6 +28,7 @@ def test_flat_state_views_and_segments():
     assert names == ["xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation", "grid", "deformation"]
     b, e = st.segments["xyz"]
     assert (b, e) == (0, 400 * 3) and st.segments["f_dc"] == (1200, 2400)
+    assert all(off % 4 == 0 for _, _, _, off, _ in st._views)         # 16-byte aligned starts (vector loads in the kernels)
     g._xyz.data[5, 1] = 42.0
     assert float(st.param[5 * 3 + 1]) == 42.0                        # .data is a view of the flat buffer
     plane = g._deformation.deformation_net.grid.grids[0][0]
