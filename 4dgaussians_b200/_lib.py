@@ -22,7 +22,7 @@ OPT_SYNC_MODE, OPT_INSTANCE_CAPACITY, OPT_TIGHT_CULL, OPT_STAGE_TIMING, OPT_TENS
 STAGES = ("prep", "geom", "scan", "emit", "sort", "ranges", "blend", "blend_bwd", "geom_bwd", "deform_bwd")
 
 BUF = dict(depth=1, rect=2, tiles_touched=3, xy=4, conic_opacity=5, rgb=6, sorted_keys=7, sorted_ids=8, ranges=9,
-           final_T=10, n_contrib=11, clamped=12, deformed=13, deformed_shs=14)
+           final_T=10, n_contrib=11, clamped=12, deformed=13, deformed_shs=14, bin_phases=15)
 
 # every symbol include/g4d.h declares (tests/test_abi.py checks the .so exports all of them)
 ABI_SYMBOLS = [
@@ -233,7 +233,8 @@ class Context:
             "xy": (np.float32, (-1, 2)), "conic_opacity": (np.float32, (-1, 4)), "rgb": (np.float32, (-1, 3)),
             "sorted_keys": (np.uint64, (-1,)), "sorted_ids": (np.uint32, (-1,)), "ranges": (np.uint32, (-1, 2)),
             "final_T": (np.float32, (-1,)), "n_contrib": (np.uint32, (-1,)), "clamped": (np.uint8, (-1, 3)),
-            "deformed": (np.float32, (-1, 11)), "deformed_shs": (np.float32, (-1, 16, 3))}[name]
+            "deformed": (np.float32, (-1, 11)), "deformed_shs": (np.float32, (-1, 16, 3)),
+            "bin_phases": (np.int64, (-1,))}[name]
         return raw.view(dt).reshape(shape)
 
     def __del__(self):

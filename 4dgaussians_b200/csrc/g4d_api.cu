@@ -86,6 +86,7 @@ struct G4DContext {
     int64_t n = 0;
     int H = 0, W = 0, grid_x = 0, grid_y = 0;
     int64_t R = 0, capacity = 0;
+    const void* bin_ctl = nullptr;    // device BinCtl of the last forward
     bool learned = false;             // R of an earlier exact forward is known (no-sync mode needs a learnt capacity)
     bool has_forward = false, is_fused = false, fused_sh = false, deformed = false;
     GeomBuffers g{};
@@ -157,9 +158,10 @@ int ensure_image(G4DContext* c, int H, int W) {
 int ensure_bin(G4DContext* c, int64_t r) {
     const size_t R = (size_t)(r > 0 ? r : 1);
     if ((int64_t)R <= c->capacity && c->bin.p) return G4D_OK;
-    G4D_CUDA(c->bin.ensure(R * 4));          // DevBuf grows by 1.5x: the one growth factor of the instance list
+    G4D_CUDA(c->bin.ensure(R * 8));          // DevBuf grows by 1.5x: the one growth factor of the instance list
+    c->capacity = (int64_t)(c->bin.cap / 8);
     c->b.ids_sorted = c->bin.as<uint32_t>();
-    c->capacity = (int64_t)(c->bin.cap / 4);
+    c->b.kbuf = c->bin.as<uint32_t>() + c->capacity;
     return G4D_OK;
 }
 
@@ -347,6 +349,7 @@ int bin_and_blend(G4DContext* c, const G4DCamera* cam, int64_t n, float* out_col
             StageTimer tm(c, G4D_STAGE_SCAN, st);
             G4D_CUDA(launch_bin_sort(n, c->grid_x, c->grid_y, c->g, c->binaux.p, ws->tight_cull, ws->sm_count, &lay, st));
         }
+        c->bin_ctl = lay.ctl;
         if (!nosync) {
             G4D_CUDA(cudaMemcpyAsync(ws->h_pinned, &lay.ctl->R, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             G4D_CUDA(cudaStreamSynchronize(st));   // exact mode: the one host sync of the path (as in the reference, A.2)
@@ -367,7 +370,7 @@ int bin_and_blend(G4DContext* c, const G4DCamera* cam, int64_t n, float* out_col
         {
             StageTimer tm(c, G4D_STAGE_EMIT, st);
             const uint32_t cap_place = (uint32_t)(c->capacity < (int64_t)kNoCap ? c->capacity : (int64_t)kNoCap);
-            G4D_CUDA(launch_bin_place(c->grid_x, c->grid_y, c->g, lay, c->b.ids_sorted, c->b.ranges, cap_place, ws->tight_cull, st));
+            G4D_CUDA(launch_bin_place(c->grid_x, c->grid_y, c->g, lay, c->b.ids_sorted, c->b.kbuf, c->b.ranges, cap_place, ws->tight_cull, st));
         }
     } else {
         c->R = 0;
@@ -667,6 +670,10 @@ int64_t g4d_context_read(G4DContext* c, int which, void* host_dst, int64_t bytes
         case G4D_BUF_DEFORMED_SHS: {
             if (!c->is_fused || !c->fused_sh || !c->fo.shs) return fail(G4D_ERR_STATE, "G4D_BUF_DEFORMED_SHS needs a fused forward with the SHS head active");
             ok = pull(c->fo.shs, N * 192); outv = tmp; outv.resize(N * 192);
+        } break;
+        case G4D_BUF_BIN_PHASES: {
+            if (!c->bin_ctl) return fail(G4D_ERR_STATE, "no binning has run on this context");
+            ok = pull(reinterpret_cast<const char*>(c->bin_ctl) + 16, 16 * 8); outv = tmp; outv.resize(16 * 8);
         } break;
         default: return fail(G4D_ERR_ARG, "unknown buffer id");
     }

@@ -165,83 +165,65 @@ __device__ __forceinline__ uint32_t radix_pass(const BinSortArgs& a, cg::grid_gr
     return total;
 }
 
-// ---- pair-parallel walk ------------------------------------------------------------------------------------------------
-// Visits the (Gaussian, tile) pairs of perm[ks, ke) restricted to the tile rows [y0, y1), in list order, 32 pairs per step:
-// f(active, tile index inside the band, Gaussian id) is called by all 32 lanes (inactive lanes pad the last step).
+// ---- unordered walk over the (Gaussian, tile) pairs of perm[ks, ke) restricted to the tile rows [y0, y1) ------------------
+// f(tile index inside the band, position k of the Gaussian in perm).  No order is promised inside the range: small rects
+// (< 32 tiles) are walked by ONE LANE each (a far chunk holds thousands of 1-4 tile Gaussians: 32 of them advance per
+// iteration), large ones by the whole warp (32 tiles per step).
 template <class F>
-__device__ __forceinline__ void walk_pairs(const uint32_t* __restrict__ perm, const uint2* __restrict__ rect,
-                                           const float4* __restrict__ rec0, const float4* __restrict__ rec1, int tight, uint32_t ks,
-                                           uint32_t ke, int y0, int y1, int grid_x, F&& f) {
+__device__ __forceinline__ void walk_unordered(const uint32_t* __restrict__ perm, const uint2* __restrict__ rect,
+                                               const float4* __restrict__ rec0, const float4* __restrict__ rec1, int tight, uint32_t ks,
+                                               uint32_t ke, int y0, int y1, int grid_x, F&& f) {
     const int lane = threadIdx.x & 31;
-    // two-deep register prefetch: perm two groups ahead, rect one group ahead (both are L2 round trips; a far chunk holds
-    // thousands of 1-4 tile Gaussians, so the walk would otherwise be a chain of dependent gathers)
-    uint32_t gi_n = ks + lane < ke ? perm[ks + lane] : 0u;
-    uint32_t gi_nn = ks + 32u + lane < ke ? perm[ks + 32u + lane] : 0u;
-    uint2 rc_n = ks + lane < ke ? rect[gi_n] : make_uint2(0u, 0u);
     for (uint32_t k0 = ks; k0 < ke; k0 += 32u) {
         const uint32_t k = k0 + lane;
-        const uint32_t gi = gi_n;
-        const uint2 rc = rc_n;
-        gi_n = gi_nn;
-        rc_n = k + 32u < ke ? rect[gi_n] : make_uint2(0u, 0u);
-        gi_nn = k + 64u < ke ? perm[k + 64u] : 0u;
-        uint32_t xy = 0, w = 1, nt = 0;
+        int minx = 0, miny = 0, w = 0, h = 0;
         float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
         if (k < ke) {
-            const int minx = (int)(rc.x & 0xFFFFu), maxx = (int)(rc.y & 0xFFFFu);
-            const int miny = max((int)(rc.x >> 16), y0), maxy = min((int)(rc.y >> 16), y1);
-            w = (uint32_t)max(maxx - minx, 1);
-            nt = maxy > miny ? (uint32_t)((maxx - minx) * (maxy - miny)) : 0u;
-            xy = (uint32_t)minx | ((uint32_t)miny << 16);
+            const uint32_t gi = perm[k];
+            const uint2 rc = rect[gi];
+            minx = (int)(rc.x & 0xFFFFu);
+            w = (int)(rc.y & 0xFFFFu) - minx;
+            miny = max((int)(rc.x >> 16), y0);
+            h = min((int)(rc.y >> 16), y1) - miny;
+            if (h < 0) h = 0;
             if (tight) { r0 = rec0[gi]; r1 = rec1[gi]; }
         }
-        uint32_t incl = nt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += y;
+        const int nt = w * h;
+        const bool big = nt >= 32;
+        if (!big) {
+            int x = 0, y = 0;
+            for (int i = 0; i < nt; ++i) {
+                if (!tight || tile_contributes(r0, r1, minx + x, miny + y)) f((miny + y - y0) * grid_x + minx + x, k);
+                if (++x == w) { x = 0; ++y; }
+            }
         }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        const uint32_t excl = incl - nt;
-        const float rw = __frcp_rn((float)w);
-        for (uint32_t b = 0; b < total; b += 32u) {
-            const uint32_t flat = b + lane;
-            const bool active = flat < total;
-            int g = 0;                       // owner = number of Gaussians whose inclusive prefix is <= flat
-#pragma unroll
-            for (int sft = 16; sft > 0; sft >>= 1) {
-                const uint32_t v = __shfl_sync(0xffffffffu, incl, (g + sft - 1) & 31);
-                if (v <= flat) g += sft;
-            }
-            g &= 31;
-            const uint32_t oxy = __shfl_sync(0xffffffffu, xy, g), ow = __shfl_sync(0xffffffffu, w, g);
-            const uint32_t oex = __shfl_sync(0xffffffffu, excl, g), oid = __shfl_sync(0xffffffffu, gi, g);
-            const float orw = __shfl_sync(0xffffffffu, rw, g);
-            const uint32_t t = active ? flat - oex : 0u;
-            // t / ow without the integer-division sequence: t < 2^24 (tile rects), one correction step makes it exact
-            uint32_t ty = (uint32_t)((float)t * orw);
-            if (ty * ow > t) --ty;
-            else if ((ty + 1u) * ow <= t) ++ty;
-            const uint32_t tx = t - ty * ow;
-            const int x = (int)(oxy & 0xFFFFu) + (int)tx, y = (int)(oxy >> 16) + (int)ty;
-            bool on = active;
+        uint32_t todo = __ballot_sync(0xffffffffu, big);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int bx = __shfl_sync(0xffffffffu, minx, src), by = __shfl_sync(0xffffffffu, miny, src);
+            const int bw = __shfl_sync(0xffffffffu, w, src), bn = __shfl_sync(0xffffffffu, nt, src);
+            const uint32_t bk = __shfl_sync(0xffffffffu, k, src);
+            float4 q0 = r0, q1 = r1;
             if (tight) {
-                float4 q0, q1;
-                q0.x = __shfl_sync(0xffffffffu, r0.x, g); q0.y = __shfl_sync(0xffffffffu, r0.y, g);
-                q0.z = __shfl_sync(0xffffffffu, r0.z, g); q0.w = __shfl_sync(0xffffffffu, r0.w, g);
-                q1.x = __shfl_sync(0xffffffffu, r1.x, g); q1.y = __shfl_sync(0xffffffffu, r1.y, g);
-                q1.z = 0.f; q1.w = 0.f;
-                on = on && tile_contributes(q0, q1, x, y);
+                q0.x = __shfl_sync(0xffffffffu, r0.x, src); q0.y = __shfl_sync(0xffffffffu, r0.y, src);
+                q0.z = __shfl_sync(0xffffffffu, r0.z, src); q0.w = __shfl_sync(0xffffffffu, r0.w, src);
+                q1.x = __shfl_sync(0xffffffffu, r1.x, src); q1.y = __shfl_sync(0xffffffffu, r1.y, src);
             }
-            f(on, (y - y0) * grid_x + x, oid);
+            for (int t = lane; t < bn; t += 32) {
+                const int ty = t / bw, tx = t - ty * bw;
+                if (!tight || tile_contributes(q0, q1, bx + tx, by + ty)) f((by + ty - y0) * grid_x + bx + tx, bk);
+            }
         }
     }
 }
 
 // walk cost of a Gaussian in units of tile instances: its pairs plus a fixed per-Gaussian share of the group overhead
-__device__ __forceinline__ uint32_t chunk_weight(uint32_t tiles_touched) { return tiles_touched + 12u; }
+__device__ __forceinline__ uint32_t chunk_weight(uint32_t tiles_touched) { return tiles_touched + 4u; }
 
 }  // namespace
+
+#define G4D_BIN_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) a.ctl->phase_clk[i] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(kBinThreads, 1) bin_sort_kernel(BinSortArgs a) {
     cg::grid_group grid = cg::this_grid();
@@ -251,6 +233,7 @@ __global__ void __launch_bounds__(kBinThreads, 1) bin_sort_kernel(BinSortArgs a)
     const uint32_t G = gridDim.x, c = blockIdx.x;
     const uint32_t N = (uint32_t)a.n;
 
+    G4D_BIN_MARK(0);
     // ---- 0. range of the visible depth bits
     {
         const uint32_t per = (N + G - 1) / G;
@@ -281,6 +264,7 @@ __global__ void __launch_bounds__(kBinThreads, 1) bin_sort_kernel(BinSortArgs a)
     }
     // (S is reused by phase 2, several grid-wide syncs later)
 
+    G4D_BIN_MARK(1);
     // ---- 1. depth order of the visible Gaussians: ceil(kbits / 9) stable passes (uniform over the grid)
     const int passes = (int)((kbits + kDigitBits - 1) / kDigitBits);
     uint32_t nvis;
@@ -297,6 +281,7 @@ __global__ void __launch_bounds__(kBinThreads, 1) bin_sort_kernel(BinSortArgs a)
         radix_pass<false, true>(a, grid, s, dyn, (passes - 1) * kDigitBits, 0u, nvis, ki, vi, nullptr, a.perm);
     }
 
+    G4D_BIN_MARK(2);
     // ---- 2. chunks of (nearly) equal walk cost (instances + a per-Gaussian constant) along the depth order
     const uint32_t per = (nvis + G - 1) / G;
     const uint32_t lo = min(c * per, nvis), hi = min(lo + per, nvis);
@@ -334,6 +319,7 @@ __global__ void __launch_bounds__(kBinThreads, 1) bin_sort_kernel(BinSortArgs a)
     }
     grid.sync();
 
+    G4D_BIN_MARK(3);
     // ---- 3. instances per (tile, chunk): shared-memory histogram of my chunk, band by band
     const uint32_t cs = __ldcg(a.chunk_start + c), ce = __ldcg(a.chunk_start + c + 1);
     {
@@ -344,10 +330,8 @@ __global__ void __launch_bounds__(kBinThreads, 1) bin_sort_kernel(BinSortArgs a)
             const int bn = (y1 - y0) * a.grid_x;
             for (int j = tid; j < bn; j += kBinThreads) dyn[j] = 0;
             __syncthreads();
-            walk_pairs(a.perm, a.rect, a.rec0, a.rec1, a.tight, ks, ke, y0, y1, a.grid_x, [&](bool on, int tile, uint32_t) {
-                const uint32_t peers = __match_any_sync(0xffffffffu, on ? (uint32_t)tile : (0x80000000u + (uint32_t)lane));
-                if (on && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&dyn[tile], (uint32_t)__popc(peers));
-            });
+            walk_unordered(a.perm, a.rect, a.rec0, a.rec1, a.tight, ks, ke, y0, y1, a.grid_x,
+                           [&](int tile, uint32_t) { atomicAdd(&dyn[tile], 1u); });
             __syncthreads();
             for (int j = tid; j < bn; j += kBinThreads) a.M[(size_t)(y0 * a.grid_x + j) * G + c] = dyn[j];
             __syncthreads();
@@ -355,6 +339,7 @@ __global__ void __launch_bounds__(kBinThreads, 1) bin_sort_kernel(BinSortArgs a)
     }
     grid.sync();
 
+    G4D_BIN_MARK(4);
     // ---- 4. per tile: exclusive scan over the chunks (one warp per tile) and the tile's total; R = sum of the totals.
     //         (the exclusive scan over the TILES -- tile_start, ranges -- is done by the placement kernel: one grid-wide sync
     //         less here, 5440 values re-scanned per CTA there)
@@ -384,119 +369,104 @@ __global__ void __launch_bounds__(kBinThreads, 1) bin_sort_kernel(BinSortArgs a)
             if (c == 0) a.ctl->n_visible = nvis;
         }
     }
+    G4D_BIN_MARK(5);
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.ctl->phase_clk[15] = (long long)kbits;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// stable counting placement: CTA = chunk, warp = contiguous share of the chunk, lane = one (Gaussian, tile) pair.
-// Shared memory per band of tile rows: base[tiles] u32 (slot of the chunk's first instance in every tile) and 17 rows of u16
-// counters [16 warps + 1 total][tiles].  A chunk longer than kSubMax Gaussians is walked in sub-chunks (u16 range).
-constexpr int kPlaceThreads = 512, kPlaceWarps = kPlaceThreads / 32;
-constexpr uint32_t kSubMax = 16u * 4000u;
-
-__global__ void __launch_bounds__(kPlaceThreads, 1) bin_place_kernel(BinPlaceArgs a) {
-    extern __shared__ __align__(16) uint8_t place_smem[];
+// Placement.  CTA c owns chunk c of the depth-ordered list; inside the segment of tile t the instances of chunk c occupy
+// the private sub-segment [tile_start[t] + M[t][c], tile_start[t] + M[t][c+1]).  The CTA keeps one cursor per tile in
+// shared memory and drops its (Gaussian, tile) pairs with shared-memory atomics in whatever order the lanes reach them --
+// the sub-segments are already in depth order with respect to each other, so only the few entries INSIDE a sub-segment
+// (4 on average) are left unordered.  What is stored is the Gaussian's position k in the depth order, not its index.
+__global__ void __launch_bounds__(kBinThreads, 1) bin_place_kernel(BinPlaceArgs a) {
+    extern __shared__ __align__(16) uint32_t cur[];     // [tiles of the band] next free slot of my sub-segment
     __shared__ uint32_t s_w[33];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const uint32_t c = blockIdx.x, G = gridDim.x;
     const uint32_t cs = a.chunk_start[c], ce = a.chunk_start[c + 1];
-    const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t T = (uint32_t)a.num_tiles;
-    // block-wide exclusive scan helper over kPlaceThreads threads (returns exclusive value, total)
-    auto block_excl = [&](uint32_t v, uint32_t& total) {
-        uint32_t x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        __syncthreads();
-        if (lane == 31) s_w[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t w = lane < kPlaceWarps ? s_w[lane] : 0u;
-            uint32_t ws = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += y; }
-            s_w[lane] = ws - w;
-            if (lane == 31) s_w[32] = ws;
-        }
-        __syncthreads();
-        total = s_w[32];
-        return s_w[warp] + x - v;
-    };
+    const uint32_t len = ce - cs, per = (len + 31) / 32;
+    const uint32_t ks = cs + min((uint32_t)warp * per, len), ke = cs + min((uint32_t)(warp + 1) * per, len);
     for (int y0 = 0; y0 < a.grid_y; y0 += a.band_rows) {
         const int y1 = min(a.grid_y, y0 + a.band_rows);
         const uint32_t bn = (uint32_t)((y1 - y0) * a.grid_x), t0 = (uint32_t)(y0 * a.grid_x);
-        uint32_t* base = reinterpret_cast<uint32_t*>(place_smem);
-        uint16_t* rows = reinterpret_cast<uint16_t*>(place_smem + (size_t)a.band_rows * a.grid_x * 4);
-        uint16_t* row = rows + (size_t)warp * bn;
-        // ---- exclusive scan of the tile totals: start slot of every tile of the band (+ ranges / overflow, written once)
+        // ---- exclusive scan of the tile totals: start slot of every tile of the band (+ ranges, written once)
         {
             uint32_t before = 0;
-            for (uint32_t t = tid; t < t0; t += kPlaceThreads) before += __ldg(a.tile_total + t);
+            for (uint32_t t = tid; t < t0; t += kBinThreads) before += __ldg(a.tile_total + t);
             uint32_t run;
-            block_excl(before, run);          // run = sum of every tile before the band
-            for (uint32_t b0 = 0; b0 < bn; b0 += kPlaceThreads) {
+            block_scan_incl(before, s_w, run);          // run = sum of every tile before the band
+            for (uint32_t b0 = 0; b0 < bn; b0 += kBinThreads) {
                 const uint32_t t = b0 + tid;
                 const uint32_t v = t < bn ? __ldg(a.tile_total + t0 + t) : 0u;
                 uint32_t tot;
-                const uint32_t start = run + block_excl(v, tot);
+                const uint32_t start = run + block_scan_incl(v, s_w, tot) - v;
                 if (t < bn) {
-                    base[t] = start + a.M[(size_t)(t0 + t) * G + c];
-                    // empty tiles keep (0, 0) like the reference's zero-initialised range array (identifyTileRanges, A.2)
-                    if (c == 0) a.ranges[t0 + t] = v ? make_uint2(min(start, a.capacity), min(start + v, a.capacity)) : make_uint2(0u, 0u);
+                    cur[t] = start + a.M[(size_t)(t0 + t) * G + c];
+                    if (c == 0) {
+                        a.tile_start[t0 + t] = start;
+                        // empty tiles keep (0, 0) like the reference's zero-initialised range array (identifyTileRanges, A.2)
+                        a.ranges[t0 + t] = v ? make_uint2(min(start, a.capacity), min(start + v, a.capacity)) : make_uint2(0u, 0u);
+                    }
                 }
                 run += tot;
             }
         }
         __syncthreads();
-        for (uint32_t sub = cs; sub < ce; sub += kSubMax) {
-            const uint32_t se = min(ce, sub + kSubMax), len = se - sub, per = (len + kPlaceWarps - 1) / kPlaceWarps;
-            const uint32_t ks = sub + min((uint32_t)warp * per, len), ke = sub + min((uint32_t)(warp + 1) * per, len);
-            for (uint32_t j = tid; j < (kPlaceWarps + 1) * bn / 2 + 1; j += kPlaceThreads)
-                if (2 * j < (kPlaceWarps + 1) * bn) reinterpret_cast<uint32_t*>(rows)[j] = 0u;
-            __syncthreads();
-            // (i) my warp's instance count per tile (plain read-modify-write: one writer per tile and step)
-            walk_pairs(a.perm, a.rect, a.rec0, a.rec1, a.tight, ks, ke, y0, y1, a.grid_x, [&](bool on, int tile, uint32_t) {
-                const uint32_t peers = __match_any_sync(0xffffffffu, on ? (uint32_t)tile : (0x80000000u + (uint32_t)lane));
-                if (on && (peers & lt) == 0) row[tile] = (uint16_t)(row[tile] + __popc(peers));
-                __syncwarp();
-            });
-            __syncthreads();
-            // (ii) exclusive prefix over the warps; the sub-chunk's total per tile goes to the extra row
-            for (uint32_t t = tid; t < bn; t += kPlaceThreads) {
-                uint32_t run = 0;
-#pragma unroll
-                for (int w = 0; w < kPlaceWarps; ++w) {
-                    const uint32_t v = rows[(size_t)w * bn + t];
-                    rows[(size_t)w * bn + t] = (uint16_t)run;
-                    run += v;
+        walk_unordered(a.perm, a.rect, a.rec0, a.rec1, a.tight, ks, ke, y0, y1, a.grid_x, [&](int tile, uint32_t k) {
+            const uint32_t slot = atomicAdd(&cur[tile], 1u);
+            if (slot < a.capacity) a.kbuf[slot] = k;
+        });
+        __syncthreads();
+    }
+}
+
+// Fix-up: order every (tile, chunk) sub-segment by depth rank and translate rank -> Gaussian index.  One warp per tile; a
+// round reads 32 sub-segment bounds (the M row of a tile is contiguous: coalesced), single entries are translated by their
+// lane, every longer sub-segment is broadcast and ranked by the whole warp, one entry per lane: keys are unique, so the
+// final position of an entry is the number of smaller keys in its sub-segment (n is ~4 on average).
+__global__ void __launch_bounds__(256) bin_fix_kernel(BinPlaceArgs a, int chunks) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= (uint32_t)a.num_tiles) return;
+    const uint32_t total = __ldg(a.tile_total + t);
+    if (total == 0) return;
+    const uint32_t start = a.tile_start[t];
+    const uint32_t* mrow = a.M + (size_t)t * chunks;
+    for (int c0 = 0; c0 < chunks; c0 += 32) {
+        const int c = c0 + lane;
+        uint32_t lo = 0, hi = 0;
+        if (c < chunks) {
+            lo = start + __ldg(mrow + c);
+            hi = start + (c + 1 < chunks ? __ldg(mrow + c + 1) : total);
+            lo = min(lo, a.capacity); hi = min(hi, a.capacity);
+        }
+        const uint32_t n = hi - lo;
+        if (n == 1) a.ids[lo] = a.perm[a.kbuf[lo]];
+        uint32_t todo = __ballot_sync(0xffffffffu, n > 1);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t blo = __shfl_sync(0xffffffffu, lo, src), bnn = __shfl_sync(0xffffffffu, n, src);
+            for (uint32_t i0 = 0; i0 < bnn; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                const uint32_t ki = i < bnn ? a.kbuf[blo + i] : 0xFFFFFFFFu;
+                uint32_t r = 0;
+                if (bnn <= 32) {                                   // the whole sub-segment sits in the lanes: rank by shuffle
+                    for (uint32_t j = 0; j < bnn; ++j) r += __shfl_sync(0xffffffffu, ki, (int)j) < ki ? 1u : 0u;
+                } else {
+                    for (uint32_t j = 0; j < bnn; ++j) r += a.kbuf[blo + j] < ki ? 1u : 0u;
                 }
-                rows[(size_t)kPlaceWarps * bn + t] = (uint16_t)run;
+                if (i < bnn) a.ids[blo + r] = a.perm[ki];
             }
-            __syncthreads();
-            // (iii) place: pairs of one step on the same tile take consecutive slots in lane (= depth) order
-            walk_pairs(a.perm, a.rect, a.rec0, a.rec1, a.tight, ks, ke, y0, y1, a.grid_x, [&](bool on, int tile, uint32_t id) {
-                const uint32_t peers = __match_any_sync(0xffffffffu, on ? (uint32_t)tile : (0x80000000u + (uint32_t)lane));
-                uint32_t slot = 0;
-                if (on) slot = base[tile] + row[tile] + (uint32_t)__popc(peers & lt);
-                __syncwarp();
-                if (on) {
-                    if ((peers & lt) == 0) row[tile] = (uint16_t)(row[tile] + __popc(peers));
-                    if (slot < a.capacity) a.ids[slot] = id;
-                }
-                __syncwarp();
-            });
-            __syncthreads();
-            if (se < ce)
-                for (uint32_t t = tid; t < bn; t += kPlaceThreads) base[t] += rows[(size_t)kPlaceWarps * bn + t];
-            __syncthreads();
         }
     }
-    (void)T;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 namespace {
 constexpr size_t kCountSmemBudget = 160 * 1024;
-constexpr size_t kPlaceSmemBudget = 224 * 1024;
+constexpr size_t kPlaceSmemBudget = 96 * 1024;
 size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 }  // namespace
 
@@ -519,6 +489,7 @@ cudaError_t launch_bin_sort(int64_t n, int grid_x, int grid_y, const GeomBuffers
     a.H = (uint32_t*)take(G * kRadix * 4); a.S = (uint32_t*)take(2 * G * 4); a.chunk_start = (uint32_t*)take((G + 1) * 4);
     a.M = (uint32_t*)take(G * (size_t)num_tiles * 4);
     a.tile_total = (uint32_t*)take((size_t)num_tiles * 4);
+    uint32_t* tile_start = (uint32_t*)take((size_t)num_tiles * 4);
     a.ctl = (BinCtl*)take(sizeof(BinCtl));
     a.grid_x = grid_x; a.grid_y = grid_y; a.num_tiles = num_tiles; a.tight = tight;
     int rows = (int)(kCountSmemBudget / ((size_t)grid_x * 4));
@@ -526,28 +497,30 @@ cudaError_t launch_bin_sort(int64_t n, int grid_x, int grid_y, const GeomBuffers
     a.count_band_rows = rows < grid_y ? rows : grid_y;
     size_t smem = (size_t)a.count_band_rows * grid_x * 4;
     if (smem < kSortSmemBytes) smem = kSortSmemBytes;
-    out->chunk_start = a.chunk_start; out->M = a.M; out->tile_total = a.tile_total; out->ctl = a.ctl; out->chunks = sm_count;
+    out->chunk_start = a.chunk_start; out->M = a.M; out->tile_total = a.tile_total; out->tile_start = tile_start; out->ctl = a.ctl;
+    out->chunks = sm_count;
     cudaError_t e = cudaFuncSetAttribute(bin_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     void* args[] = {&a};
     return cudaLaunchCooperativeKernel((const void*)bin_sort_kernel, dim3((unsigned)sm_count), dim3(kBinThreads), args, smem, st);
 }
 
-cudaError_t launch_bin_place(int grid_x, int grid_y, const GeomBuffers& g, const BinLayout& lay, uint32_t* ids, uint2* ranges,
-                             uint32_t capacity, int tight, cudaStream_t st) {
+cudaError_t launch_bin_place(int grid_x, int grid_y, const GeomBuffers& g, const BinLayout& lay, uint32_t* ids, uint32_t* kbuf,
+                             uint2* ranges, uint32_t capacity, int tight, cudaStream_t st) {
     const int num_tiles = grid_x * grid_y;
     BinPlaceArgs a{};
     a.perm = g.perm; a.rect = g.rect; a.rec0 = g.rec0; a.rec1 = g.rec1; a.chunk_start = lay.chunk_start; a.M = lay.M;
-    a.tile_total = lay.tile_total; a.ranges = ranges; a.ids = ids; a.capacity = capacity; a.grid_x = grid_x; a.grid_y = grid_y;
-    a.num_tiles = num_tiles; a.tight = tight;
-    const size_t per_tile = 4 + (kPlaceWarps + 1) * 2;                      // base u32 + 17 u16 counters
-    a.band_rows = (int)(kPlaceSmemBudget / (per_tile * (size_t)grid_x));
+    a.tile_total = lay.tile_total; a.tile_start = lay.tile_start; a.ranges = ranges; a.ids = ids; a.kbuf = kbuf;
+    a.capacity = capacity; a.grid_x = grid_x; a.grid_y = grid_y; a.num_tiles = num_tiles; a.tight = tight;
+    a.band_rows = (int)(kPlaceSmemBudget / (4 * (size_t)grid_x));
     if (a.band_rows < 1) return cudaErrorInvalidValue;
     if (a.band_rows > grid_y) a.band_rows = grid_y;
-    const size_t smem = per_tile * (size_t)a.band_rows * grid_x + 16;
+    const size_t smem = 4 * (size_t)a.band_rows * grid_x;
     cudaError_t e = cudaFuncSetAttribute(bin_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    bin_place_kernel<<<lay.chunks, kPlaceThreads, smem, st>>>(a);
+    bin_place_kernel<<<lay.chunks, kBinThreads, smem, st>>>(a);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    bin_fix_kernel<<<(num_tiles + 7) / 8, 256, 0, st>>>(a, lay.chunks);
     return cudaGetLastError();
 }
 

@@ -24,14 +24,21 @@
 // W1 streaming: the 128 KB (hi | lo) image of a head is split into two K-halves of 64 KB, each with its own "landed" and
 // "consumed" mbarrier: while the MMAs of K-half 1 of head k run, the TMA of K-half 0 of head k+1 is already in flight, so
 // the tensor pipe never waits for a whole-image copy (measured before: 960 cycles of exposed TMA wait per head + the whole
-// epilogue serialised behind every GEMM).  The issuer thread drives this as a small non-blocking state machine (`pump`)
-// polled between the chunks of its own epilogue work and inside its waits.
+// epilogue serialised behind every GEMM).
+// Roles (288 threads): warps 0-7 = the two epilogue groups (below); warp 8, one lane = the MMA issuer.  tcgen05.mma issue is
+// NOT free for the issuing thread -- it blocks while the pipe's queue is full (measured: an epilogue thread that also issued
+// the next head's 48 MMAs tripled every epilogue) -- so it gets its own warp and plain blocking waits on mbarriers:
+// features staged / A1 written / accumulator drained / hidden half written are signalled by the epilogue threads with
+// mbarrier.arrive, weights-landed by the TMA transaction count.  The TMA copies themselves are issued by thread 128, which
+// polls "K-half consumed" between the chunks of its own epilogue work (a copy is one non-blocking instruction).
 // Compiled with -fmad=false (it contains the projection, see g4d_math.cuh).
 #include "geom_finish.cuh"
 #include "tc_umma.cuh"
 
 namespace g4d {
 
+constexpr int kW1Parts = 4;                       // K-quarters of a head's W1 image: 4 x (hi 16 KB | lo 16 KB)
+constexpr uint32_t kW1PartBytes = 2u * 128u * (128u / kW1Parts) * 4u;
 constexpr uint32_t kColA1Hi = 0, kColA1Lo = 128, kColD = 256, kColD1 = 384, kColX = 384, kColXLo = 448;
 
 struct TcSmem { uint32_t w1, w2, w0, bias, w2s, bars, acc, total; };
@@ -45,7 +52,7 @@ inline TcSmem tc_smem_layout(int F, int max_kp16) {
     s.w0 = take(2u * 128 * F * 4);
     s.bias = take((128 + G4D_NUM_HEADS * 128 + 64) * 4);
     s.w2s = take(4 * 128 * 16);
-    s.bars = take(128);     // 9 mbarriers
+    s.bars = take(256);     // 18 mbarriers
     s.acc = take(2 * 128 * 16);
     s.total = off;
     return s;
@@ -56,7 +63,7 @@ struct TcPackDesc {
     const float* src[1 + 2 * G4D_NUM_HEADS];
     float* dst[1 + 2 * G4D_NUM_HEADS];
     int rows_src[1 + 2 * G4D_NUM_HEADS], rows_dst[1 + 2 * G4D_NUM_HEADS], K[1 + 2 * G4D_NUM_HEADS];
-    int khalves[1 + 2 * G4D_NUM_HEADS];   // 1: image = (hi_k0 | lo_k0 | hi_k1 | lo_k1), each K-half canonical with K / 2 columns
+    int khalves[1 + 2 * G4D_NUM_HEADS];   // P > 0: image = P K-parts (hi_k0 | lo_k0 | hi_k1 | lo_k1 | ...), each canonical with K / P columns
     int start[2 + 2 * G4D_NUM_HEADS];
     int count;
 };
@@ -73,7 +80,7 @@ __global__ void tc_pack_weights_kernel(TcPackDesc p) {
     uint32_t hi, lo;
     tc::tf32_split(v, hi, lo);
     if (p.khalves[m]) {
-        const uint32_t Kh = K >> 1, j = k / Kh, blk = p.rows_dst[m] * Kh;          // words per (part, K-half) block
+        const uint32_t Kh = K / p.khalves[m], j = k / Kh, blk = p.rows_dst[m] * Kh;   // words per (hi or lo, K-part) block
         const uint32_t off = tc::canon_off(n, k - j * Kh, Kh) >> 2;
         reinterpret_cast<uint32_t*>(p.dst[m])[(2 * j) * blk + off] = hi;
         reinterpret_cast<uint32_t*>(p.dst[m])[(2 * j + 1) * blk + off] = lo;
@@ -106,7 +113,7 @@ cudaError_t launch_tc_pack_weights(const G4DDeformParams& prm, float* blob, TcWe
         out->kp16[h] = h == 4 ? 48 : 16;
         out->w1[h] = nullptr; out->w2[h] = nullptr;
         if (!(prm.head_mask & (1 << h))) continue;
-        out->w1[h] = add(prm.w1[h], 128, 128, 128, 1);
+        out->w1[h] = add(prm.w1[h], 128, 128, 128, kW1Parts);
         out->w2[h] = add(prm.w2[h], head_out(h), out->kp16[h], 128);
     }
     p.start[m] = total; p.count = m;
@@ -133,7 +140,7 @@ __device__ __forceinline__ int b2off_of(int mask, int h) {
     return o;
 }
 
-constexpr int kBarFeat = 1, kBarXFree = 2, kBarScratch = 3, kBarScratchFree = 4, kBarM = 5, kBarE = 6;
+constexpr int kBarScratch = 3, kBarScratchFree = 4, kBarE = 6;   // named barriers between the two epilogue groups
 constexpr uint32_t kColScratch = kColA1Hi;   // p(3) + dsh(48) handed from M to G after the last head (A1 is dead then)
 
 // One channel vector (4 channels) of one level: product over the 6 planes of the bilinear samples.
@@ -209,18 +216,14 @@ __device__ __forceinline__ bool mbar_test(void* bar, uint32_t parity) {
     return done != 0;
 }
 
-// The issuer thread's view of the W1 stream.  Loads and GEMMs are numbered q = 0, 1, ... over (tile, active head) in
-// program order; each consists of two K-halves j.  th / mh = 2 q + j of the next TMA / MMA half to issue.
-struct TcPump {
-    uint32_t th, mh;        // next TMA half, next MMA half
-    uint32_t total;         // number of (tile, head) GEMMs of this CTA
-    int32_t allow;          // highest GEMM index that may START (its D buffer is free and A1 is ready)
-    uint32_t m;             // active heads per tile
-    uint32_t par0;          // D buffer of head k of a tile = (k + par0) & 1
-};
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kTcThreads = 288;   // 8 epilogue warps + the MMA warp
 
 template <int MODE, int C, int L, bool SAVE>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kTcThreads, 1)
 deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restrict__ camp, float time_arg, int use_cam_time,
                  int64_t n, DeformIO io) {
     constexpr int F = C * L;
@@ -230,43 +233,47 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int row = tid & 127;
-    for (int i = tid; i < (int)(sizeof(DeformDesc) / 4); i += 256)
+    for (int i = tid; i < (int)(sizeof(DeformDesc) / 4); i += kTcThreads)
         reinterpret_cast<uint32_t*>(&sd)[i] = reinterpret_cast<const uint32_t*>(&d)[i];
     // the hardware scheduler favours the higher warp ids of an SM sub-partition: the latency-critical M group takes them
-    const bool is_m = tid >= 128;
-    const bool issuer = tid == 128;
+    const bool is_mma_warp = warp == 8;
+    const bool is_m = tid >= 128 && !is_mma_warp;
+    const bool tma_thread = tid == 128;
     const int64_t ntiles = (n + 127) / 128;
     if (MODE == 1 || use_cam_time) {
-        for (int i = tid; i < (int)(sizeof(CameraDev) / 4); i += 256)
+        for (int i = tid; i < (int)(sizeof(CameraDev) / 4); i += kTcThreads)
             reinterpret_cast<uint32_t*>(&cam)[i] = reinterpret_cast<const uint32_t*>(camp)[i];
     }
     float* sBias = reinterpret_cast<float*>(smem + Ls.bias);     // b0[128] | b1[5][128] | b2[64]
     float4* sW2s = reinterpret_cast<float4*>(smem + Ls.w2s);     // [4 small heads][128 hidden]: (W2[0][j], W2[1][j], W2[2][j], W2[3][j])
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Ls.bars);
-    // bars: 0 w0 | 1,2 full[j] (W1 K-half j landed) | 3,4 hfree[j] (its MMAs retired) | 5,6 dfull[b] (head GEMM into D[b]
-    // complete) | 7 l0 | 8 l2
-    uint64_t *bar_w0 = bars, *bar_full = bars + 1, *bar_hfree = bars + 3, *bar_dfull = bars + 5, *bar_l0 = bars + 7, *bar_l2 = bars + 8;
+    // mbarriers: 0 w0 | 1-4 full[j] (W1 K-quarter j landed, tx count) | 5-8 hfree[j] (its MMAs retired) | 9,10 dfull[b] (head
+    // GEMM into D[b] complete) | 11 l0 | 12 l2 | 13 featready (128 G threads) | 14 a1ready (256) | 15,16 dfree[b] (256:
+    // accumulator drained by its epilogue) | 17 xready (256: SH hidden half written)
+    uint64_t *bar_w0 = bars, *bar_full = bars + 1, *bar_hfree = bars + 5, *bar_dfull = bars + 9, *bar_l0 = bars + 11, *bar_l2 = bars + 12;
+    uint64_t *bar_feat = bars + 13, *bar_a1 = bars + 14, *bar_dfree = bars + 15, *bar_x = bars + 17;
     int b2off[G4D_NUM_HEADS];
     {
         int o = 0;
 #pragma unroll
         for (int h = 0; h < G4D_NUM_HEADS; ++h) { b2off[h] = o; if (d.head_mask & (1 << h)) o += head_out(h); }
     }
-    for (int i = tid; i < 128; i += 256) sBias[i] = __ldg(d.b0 + i);
+    for (int i = tid; i < 128; i += kTcThreads) sBias[i] = __ldg(d.b0 + i);
     for (int h = 0; h < G4D_NUM_HEADS; ++h) {
         if (!(d.head_mask & (1 << h))) continue;
-        for (int i = tid; i < 128; i += 256) sBias[128 + h * 128 + i] = __ldg(d.b1[h] + i);
-        for (int i = tid; i < head_out(h); i += 256) sBias[128 + G4D_NUM_HEADS * 128 + b2off[h] + i] = __ldg(d.b2[h] + i);
+        for (int i = tid; i < 128; i += kTcThreads) sBias[128 + h * 128 + i] = __ldg(d.b1[h] + i);
+        for (int i = tid; i < head_out(h); i += kTcThreads) sBias[128 + G4D_NUM_HEADS * 128 + b2off[h] + i] = __ldg(d.b2[h] + i);
         if (h < 4) {
             const int ko = head_out(h);
-            for (int j = tid; j < 128; j += 256)
+            for (int j = tid; j < 128; j += kTcThreads)
                 sW2s[h * 128 + j] = make_float4(__ldg(d.w2[h] + j), ko > 1 ? __ldg(d.w2[h] + 128 + j) : 0.f,
                                                ko > 2 ? __ldg(d.w2[h] + 256 + j) : 0.f, ko > 3 ? __ldg(d.w2[h] + 384 + j) : 0.f);
         }
     }
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, tc::kTmemCols);
     if (tid == 0) {
-        for (int i = 0; i < 9; ++i) mbar_init(bars + i, 1);
+        for (int i = 0; i < 13; ++i) mbar_init(bars + i, 1);
+        mbar_init(bar_feat, 128); mbar_init(bar_a1, 256); mbar_init(bar_dfree, 256); mbar_init(bar_dfree + 1, 256); mbar_init(bar_x, 256);
         fence_barrier_init();
     }
     tc::fence_before_sync();
@@ -276,80 +283,116 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
     const uint32_t lane_base = tbase + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t sW1 = tc::smem_addr(smem + Ls.w1), sW2 = tc::smem_addr(smem + Ls.w2), sW0 = tc::smem_addr(smem + Ls.w0);
     const bool hsh = d.head_mask & G4D_HEAD_SHS;
-    const float t = use_cam_time ? cam.time : time_arg;
-    (void)t;
 
-    // ---- the W1 stream of this CTA (issuer thread only uses it)
-    TcPump pp{};
-    pp.m = (uint32_t)__popc(d.head_mask & 31);
-    pp.par0 = hsh ? ((pp.m - 1u) & 1u) : 0u;
+    // ---- the W1 stream of this CTA: loads / GEMMs are numbered q = 0, 1, ... over (tile, active head) in program order,
+    //      each made of two K-halves j
+    const uint32_t m_heads = (uint32_t)__popc(d.head_mask & 31);
+    const uint32_t par0 = hsh ? ((m_heads - 1u) & 1u) : 0u;      // accumulator of head k of a tile = (k + par0) & 1: SH gets D0
+    const int64_t my_tiles = (int64_t)blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const uint32_t total_q = (uint32_t)my_tiles * m_heads;
+    // head id of the k-th head this CTA processes: the small heads in an order ROTATED by the CTA index (at any moment the
+    // 148 CTAs then stream four different W1 images instead of hammering the L2 slices of one), the SH head always last
+    uint32_t hseq_pack = 0;               // 3 bits per position
     {
-        const int64_t my_tiles = (int64_t)blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-        pp.total = (uint32_t)my_tiles * pp.m;
+        const int ns = __popc(d.head_mask & 15);
+        const int rot = ns ? (int)(blockIdx.x % (unsigned)ns) : 0;
+        int pos = 0;
+        for (int h = 0; h < 4; ++h) {
+            if (!(d.head_mask & (1 << h))) continue;
+            const int k = pos >= rot ? pos - rot : pos - rot + ns;      // active small head #pos runs at position k
+            hseq_pack |= (uint32_t)h << (3 * k);
+            ++pos;
+        }
+        if (hsh) hseq_pack |= 4u << (3 * ns);
     }
-    pp.allow = -1;
-    // head id of the k-th active head
-    auto head_of = [&](uint32_t k) {
-        int h = 0, seen = -1;
-        for (; h < G4D_NUM_HEADS; ++h)
-            if (d.head_mask & (1 << h)) { if (++seen == (int)k) break; }
-        return h;
-    };
-    // issue whatever the stream allows right now; never blocks
-    auto pump = [&]() {
-        bool progress = true;
-        while (progress) {
-            progress = false;
-            {   // next W1 K-half copy: its buffer must have been consumed by the previous GEMM
-                const uint32_t q = pp.th >> 1, j = pp.th & 1u;
-                if (q < pp.total && (q == 0 || mbar_test(bar_hfree + j, (q - 1u) & 1u))) {
-                    const int h = head_of(q % pp.m);
-                    mbar_expect_tx(bar_full + j, 65536u);
-                    tma_bulk_g2s(smem + Ls.w1 + j * 65536u, tw.w1[h] + j * 16384u, 65536u, bar_full + j);
-                    ++pp.th;
-                    progress = true;
-                }
-            }
-            {   // next GEMM K-half: its weights must have landed, its D buffer must be free, A1 must be ready
-                const uint32_t q = pp.mh >> 1, j = pp.mh & 1u;
-                if (q < pp.total && (int32_t)q <= pp.allow && mbar_test(bar_full + j, q & 1u)) {
-                    const uint32_t b = ((q % pp.m) + pp.par0) & 1u;
-                    tc::fence_after_sync();
-                    tc::gemm_3xtf32<64>(tbase + (b ? kColD1 : kColD), tbase + kColA1Hi + j * 64u, tbase + kColA1Lo + j * 64u,
-                                        sW1 + j * 65536u, sW1 + j * 65536u + 32768u, 128, 64, 0, j != 0);
-                    tc::umma_commit(bar_hfree + j);
-                    if (j) tc::umma_commit(bar_dfull + b);
-                    ++pp.mh;
-                    progress = true;
+    auto head_at = [&](uint32_t k) { return (int)((hseq_pack >> (3u * k)) & 7u); };
+
+    // ================================================================================================================
+    // MMA warp: one lane issues every tcgen05.mma of the CTA, in order, with blocking waits
+    // ================================================================================================================
+    if (is_mma_warp) {
+        if ((tid & 31) == 0) {
+            mbar_wait(bar_w0, 0);
+            uint32_t used[2] = {0u, 0u}, seen[2] = {0u, 0u};       // GEMMs issued into / epilogues observed on D[b]
+            uint32_t ph_feat = 0, ph_a1 = 0, ph_x = 0, q = 0;
+            auto drain = [&](uint32_t b) {                          // every earlier user of D[b] has been read out
+                while (seen[b] < used[b]) { mbar_wait(bar_dfree + b, seen[b] & 1u); ++seen[b]; }
+            };
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                // ---- layer 0: D0 = feat * W0^T
+                mbar_wait(bar_feat, ph_feat); ph_feat ^= 1u;
+                drain(0); drain(1);
+                tc::fence_after_sync();
+                tc::gemm_3xtf32<F>(tbase + kColD, tbase + kColX, tbase + kColXLo, sW0, sW0 + 128u * F * 4, 128, F, 0, false);
+                tc::umma_commit(bar_l0);
+                mbar_wait(bar_a1, ph_a1); ph_a1 ^= 1u;              // epilogue 0 has written A1 and drained D0
+                for (uint32_t k = 0; k < m_heads; ++k, ++q) {
+                    const uint32_t b = (k + par0) & 1u;
+                    drain(b);
+#pragma unroll 1
+                    for (uint32_t j = 0; j < (uint32_t)kW1Parts; ++j) {
+                        constexpr uint32_t KP = 128 / kW1Parts;
+                        mbar_wait(bar_full + j, q & 1u);
+                        tc::fence_after_sync();
+                        tc::gemm_3xtf32<(int)KP>(tbase + (b ? kColD1 : kColD), tbase + kColA1Hi + j * KP, tbase + kColA1Lo + j * KP,
+                                                 sW1 + j * kW1PartBytes, sW1 + j * kW1PartBytes + kW1PartBytes / 2, 128, KP, 0, j != 0);
+                        tc::umma_commit(bar_hfree + j);
+                    }
+                    tc::umma_commit(bar_dfull + b);
+                    ++used[b];
+                    if (hsh && k + 1 == m_heads) {
+                        // SH head: two layer-2 partials D2 (+)= a2_half * W2[:, 64hh : 64hh+64]^T (D2 = D0 columns [0, 48))
+                        for (int hh = 0; hh < 2; ++hh) {
+                            mbar_wait(bar_x, ph_x); ph_x ^= 1u;
+                            tc::fence_after_sync();
+                            tc::gemm_3xtf32<64>(tbase + kColD, tbase + kColX, tbase + kColXLo, sW2, sW2 + 48u * 128 * 4, 48, 128,
+                                                (uint32_t)(hh * 16), hh == 1);
+                            tc::umma_commit(bar_l2);
+                        }
+                    }
                 }
             }
         }
+    } else {
+    // ================================================================================================================
+    // epilogue groups
+    // ================================================================================================================
+    // next W1 K-half copy (thread 128 only): its buffer must have been consumed by the previous GEMM; never blocks
+    uint32_t tq = 0, tj = 0, tk = 0;      // next copy: GEMM index, K-part, head position inside the tile
+    auto pump_tma = [&]() {
+        for (;;) {
+            if (tq >= total_q || (tq != 0 && !mbar_test(bar_hfree + tj, (tq - 1u) & 1u))) break;
+            const int h = head_at(tk);
+            mbar_expect_tx(bar_full + tj, kW1PartBytes);
+            tma_bulk_g2s(smem + Ls.w1 + tj * kW1PartBytes, tw.w1[h] + tj * (kW1PartBytes / 4u), kW1PartBytes, bar_full + tj);
+            if (++tj == (uint32_t)kW1Parts) { tj = 0; ++tq; if (++tk == m_heads) tk = 0; }
+        }
     };
-    // wait for an mbarrier phase; the issuer keeps the stream moving meanwhile
+    // wait for an mbarrier phase; thread 128 keeps the weight stream moving meanwhile
     auto wait_pumping = [&](uint64_t* bar, uint32_t parity) {
-        if (issuer) {
-            while (!mbar_test(bar, parity)) pump();
+        if (tma_thread) {
+            while (!mbar_test(bar, parity)) pump_tma();
         } else {
             mbar_wait(bar, parity);
         }
     };
 
     // ---- resident operands: W0 and (when active) the SH head's W2 image; the first two W1 K-halves
-    if (issuer) {
+    if (tma_thread) {
         const uint32_t w2b = hsh ? 2u * 48 * 128 * 4 : 0u;
         mbar_expect_tx(bar_w0, 2u * 128 * F * 4 + w2b);
         tma_bulk_g2s(smem + Ls.w0, tw.w0, 2u * 128 * F * 4, bar_w0);
         if (hsh) tma_bulk_g2s(smem + Ls.w2, tw.w2[4], w2b, bar_w0);
-        pump();
+        pump_tma();
     }
-    if (is_m) mbar_wait(bar_w0, 0);
     uint32_t ph_l0 = 0, ph_l2 = 0, ph_d0 = 0, ph_d1 = 0;
     // column chunks (16 hidden units each) of every epilogue are split between the two thread groups
     const int ch_lo = is_m ? 4 : 0, ch_hi = is_m ? 8 : 4;        // full-width epilogues (8 chunks)
     const int hc_lo = is_m ? 2 : 0, hc_hi = is_m ? 4 : 2;        // half-width epilogues of the SH head (4 chunks)
     float4* sAcc = reinterpret_cast<float4*>(smem + Ls.acc);     // [2][128]: G group's partial layer-2 sums of a small head
 
-    // features of a tile ([N][F] fp32, written by deform_features_kernel at full occupancy) -> A operand X (hi | lo)
+    // features of a tile ([N][F] fp32, written by deform_features_kernel at full occupancy) -> A operand X (hi | lo).
+    // X (= D1) is free here: every GEMM that wrote or read it has been waited for by this thread.
     auto stage_features = [&](int64_t tl) {
         const int64_t gs = tl * 128 + row;
         float feat[F];
@@ -364,7 +407,6 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
 #pragma unroll
             for (int c = 0; c < F; ++c) feat[c] = 0.f;
         }
-        if (tl != (int64_t)blockIdx.x) { bar_sync(kBarXFree, 256); tc::fence_after_sync(); }
 #pragma unroll
         for (int c0 = 0; c0 < F; c0 += 8) {
             uint32_t hi[8], lo[8];
@@ -375,18 +417,17 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
         }
         tc::wait_st();
         tc::fence_before_sync();
-        bar_arrive(kBarFeat, 256);
+        mbar_arrive(bar_feat);
     };
     if (!is_m && blockIdx.x < ntiles) stage_features(blockIdx.x);
 
-    // optional per-phase cycle accounting (issuer thread; G4D debug only)
+    // optional per-phase cycle accounting (thread 128; G4D debug only)
     long long cyc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = clock64();
-#define G4D_CYC(i) do { if (tw.dbg && issuer) { const long long tn_ = clock64(); cyc[i] += tn_ - tprev; tprev = tn_; } } while (0)
+#define G4D_CYC(i) do { if (tw.dbg && tma_thread) { const long long tn_ = clock64(); cyc[i] += tn_ - tprev; tprev = tn_; } } while (0)
     bool first = true;
     int hseq = 0;   // running small-head counter -> sAcc buffer
-    uint32_t tile_q0 = 0;   // GEMM index of this tile's first head
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false, tile_q0 += pp.m) {
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first = false) {
         const int64_t gi = tile * 128 + row;
         const bool valid = gi < n;
         const bool has_next = tile + gridDim.x < ntiles;
@@ -399,19 +440,10 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
             if (io.opacity) ol = io.opacity[gi];
         }
         G4D_CYC(0);   // input loads
-        // ---- layer 0: D0 = feat * W0^T   (features were put into X by the G group)
-        if (is_m) {
-            bar_sync(kBarFeat, 256);
-            G4D_CYC(1);   // wait for the features
-            if (issuer) {
-                tc::fence_after_sync();
-                tc::gemm_3xtf32<F>(tbase + kColD, tbase + kColX, tbase + kColXLo, sW0, sW0 + 128u * F * 4, 128, F, 0, false);
-                tc::umma_commit(bar_l0);
-            }
-        }
+        // ---- layer 0 (MMA warp): D0 = feat * W0^T
         wait_pumping(bar_l0, ph_l0); ph_l0 ^= 1u;
         tc::fence_after_sync();
-        G4D_CYC(2);   // layer-0 MMA
+        G4D_CYC(2);   // features + layer-0 MMA
         if (is_m && !first) { bar_sync(kBarScratchFree, 256); tc::fence_after_sync(); }   // G has read the previous tile's scratch (A1 region)
         G4D_CYC(3);   // wait scratch free
         // ---- epilogue 0: a1 = relu(D0 + b0) -> A1 (hi | lo); ReLU sign bits saved for the backward
@@ -421,7 +453,7 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
             const uint32_t c0 = (uint32_t)(ch * 16);
             uint32_t v[16], hi[16], lo[16];
             tc::tmem_ld16(lane_base + kColD + c0, v);
-            if (issuer) pump();
+            if (tma_thread) pump_tma();
             tc::wait_ld();
             float bb[16];
 #pragma unroll
@@ -443,9 +475,7 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
         if (SAVE && valid) store_relu_half(tw.relu_bits, 0, n, gi, is_m ? 2 : 0, rb[0], rb[1]);
         tc::wait_st();
         tc::fence_before_sync();
-        bar_sync(kBarE, 256);
-        // A1 is complete and both accumulators are free: the first TWO head GEMMs of this tile may start
-        if (issuer) { pp.allow = (int32_t)min(tile_q0 + 1u, tile_q0 + pp.m - 1u); pump(); }
+        mbar_arrive(bar_a1);          // A1 complete, D0 drained: the MMA warp may start the head GEMMs of this tile
         G4D_CYC(4);   // epilogue 0
 
         float dl[11];
@@ -455,15 +485,14 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
 #pragma unroll
         for (int j = 0; j < 48; ++j) dsh[j] = 0.f;
 
-        uint32_t kact = 0;   // index of the head among the active ones
 #pragma unroll 1
-        for (int h = 0; h < G4D_NUM_HEADS; ++h) {
-            if (!(d.head_mask & (1 << h))) continue;
+        for (uint32_t kact = 0; kact < m_heads; ++kact) {     // heads in this CTA's (rotated) order
+            const int h = head_at(kact);
             const float* b1 = sBias + 128 + h * 128;
             const float* b2 = sBias + 128 + G4D_NUM_HEADS * 128 + b2off_of(d.head_mask, h);
-            const uint32_t db = (kact + pp.par0) & 1u;                  // accumulator of this head
+            const uint32_t db = (kact + par0) & 1u;                     // accumulator of this head
             const uint32_t dcol = db ? kColD1 : kColD;
-            // ---- layer 1 (issued ahead by the pump): wait for D[db] = a1 * W1^T
+            // ---- layer 1 (issued ahead by the MMA warp): wait for D[db] = a1 * W1^T
             wait_pumping(bar_dfull + db, db ? ph_d1 : ph_d0);
             if (db) ph_d1 ^= 1u; else ph_d0 ^= 1u;
             tc::fence_after_sync();
@@ -478,7 +507,7 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                 for (int ch = ch_lo; ch < ch_hi; ++ch) {
                     uint32_t v[16];
                     tc::tmem_ld16(lane_base + dcol + ch * 16, v);
-                    if (issuer) pump();
+                    if (tma_thread) pump_tma();
                     tc::wait_ld();
                     float bb[16];
 #pragma unroll
@@ -498,12 +527,12 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                     }
                     if (SAVE) { const int k = ch - ch_lo; if (k < 2) rb[0] |= bits << (k * 16); else rb[1] |= bits << ((k - 2) * 16); }
                 }
+                tc::fence_before_sync();
+                mbar_arrive(bar_dfree + db);   // my part of D[db] is read: once all 256 have arrived the MMA warp may reuse it
                 if (SAVE && valid) store_relu_half(tw.relu_bits, 1 + h, n, gi, is_m ? 2 : 0, rb[0], rb[1]);
                 float4* slot = sAcc + (hseq & 1) * 128 + row;
                 if (!is_m) *slot = acc;
-                tc::fence_before_sync();
-                bar_sync(kBarE, 256);   // partial sums visible; D[db] may be overwritten by the GEMM of head kact + 2
-                if (issuer) { pp.allow = (int32_t)min(tile_q0 + kact + 2u, tile_q0 + pp.m - 1u); pump(); }
+                bar_sync(kBarE, 256);   // G's partial sums are visible to M
                 if (is_m) {
                     // fixed summation order: (G's hidden units 0..63) + (M's hidden units 64..127)
                     const float4 ga = *slot;
@@ -526,7 +555,7 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                         const uint32_t cg = (uint32_t)(hh * 64) + cl;
                         uint32_t v[16], hi[16], lo[16];
                         tc::tmem_ld16(lane_base + kColD + cg, v);
-                        if (issuer) pump();
+                        if (tma_thread) pump_tma();
                         tc::wait_ld();
                         float bb[16];
 #pragma unroll
@@ -547,15 +576,8 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                     }
                     tc::wait_st();
                     tc::fence_before_sync();
-                    bar_sync(kBarE, 256);
+                    mbar_arrive(bar_x);        // hidden half written: the MMA warp issues the layer-2 partial
                     G4D_CYC(8);   // hidden-half epilogue
-                    // ---- layer 2 partial: D2 (+)= a2_half * W2[:, 64hh : 64hh+64]^T   (D2 = D0 columns [0, 48))
-                    if (issuer) {
-                        tc::fence_after_sync();
-                        tc::gemm_3xtf32<64>(tbase + kColD, tbase + kColX, tbase + kColXLo, sW2, sW2 + 48u * 128 * 4, 48, 128,
-                                            (uint32_t)(hh * 16), hh == 1);
-                        tc::umma_commit(bar_l2);
-                    }
                     wait_pumping(bar_l2, ph_l2); ph_l2 ^= 1u;
                     tc::fence_after_sync();
                     G4D_CYC(9);   // layer-2 partial MMA
@@ -574,15 +596,13 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
 #pragma unroll
                         for (int j = 0; j < 16; ++j) dsh[ch * 16 + j] = __uint_as_float(v[j]) + b2[ch * 16 + j];
                     }
-                    tc::fence_before_sync();
-                    bar_sync(kBarM, 128);   // D0 may be overwritten by the next tile's layer-0 GEMM
                 }
+                tc::fence_before_sync();
+                mbar_arrive(bar_dfree + db);   // D0 (and D2 inside it) read out: the next tile's layer-0 GEMM may overwrite it
             }
-            ++kact;
             G4D_CYC(10);  // head output / hand-over
         }
         if (is_m) {
-            if (has_next) bar_arrive(kBarXFree, 256);   // every MMA reading X / writing D1 has completed: G may store the next tile's features
             p.x += dl[0]; p.y += dl[1]; p.z += dl[2];
             // ---- hand the deformed position and the SH deltas to the G thread of this lane (A1 is dead now)
             {
@@ -601,7 +621,7 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                 tc::fence_before_sync();
                 bar_arrive(kBarScratch, 256);
             }
-            if (issuer) pump();   // (prefetch of the next tile's first W1 halves once the last GEMM has retired)
+            if (tma_thread) pump_tma();   // (prefetch of the next tile's first W1 halves once the last GEMM has retired)
             // ---- finish the geometric half of my Gaussian
             if (valid) {
                 sl[0] += dl[3]; sl[1] += dl[4]; sl[2] += dl[5];
@@ -616,7 +636,7 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                     fused_finish_geometry(cam, io, gi, p, sl, q, ol);
                 }
             }
-            if (issuer) pump();
+            if (tma_thread) pump_tma();
             G4D_CYC(11);  // scratch hand-off + geometry tail
         } else {
             // ---- G tail: next tile's features, then the SH colour of my Gaussian once M has published p and the SH deltas
@@ -659,10 +679,11 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
         }
     }
     if (is_m && !first) { bar_sync(kBarScratchFree, 256); }   // pair the G group's last arrive
-    if (tw.dbg && issuer) {
+    if (tw.dbg && tma_thread) {
         for (int i = 0; i < 12; ++i) tw.dbg[blockIdx.x * 12 + i] = cyc[i];
     }
 #undef G4D_CYC
+    }   // epilogue groups
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tbase, tc::kTmemCols);
@@ -710,11 +731,11 @@ static cudaError_t launch_deform_tc_t(const DeformDesc& d, const TcWeights& tw, 
     if (tw.relu_bits) {
         e = cudaFuncSetAttribute(deform_tc_kernel<MODE, C, L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
-        deform_tc_kernel<MODE, C, L, true><<<grid, 256, bytes, st>>>(d, tw, Ls, cam, time, use_cam_time ? 1 : 0, n, io);
+        deform_tc_kernel<MODE, C, L, true><<<grid, kTcThreads, bytes, st>>>(d, tw, Ls, cam, time, use_cam_time ? 1 : 0, n, io);
     } else {
         e = cudaFuncSetAttribute(deform_tc_kernel<MODE, C, L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
-        deform_tc_kernel<MODE, C, L, false><<<grid, 256, bytes, st>>>(d, tw, Ls, cam, time, use_cam_time ? 1 : 0, n, io);
+        deform_tc_kernel<MODE, C, L, false><<<grid, kTcThreads, bytes, st>>>(d, tw, Ls, cam, time, use_cam_time ? 1 : 0, n, io);
     }
     return cudaGetLastError();
 }

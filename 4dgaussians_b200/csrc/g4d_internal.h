@@ -21,12 +21,13 @@ struct GeomBuffers {
 };
 
 struct BinBuffers {
+    uint32_t* kbuf;         // [capacity] placement scratch (depth ranks)
     uint32_t* ids_sorted;   // [capacity] Gaussian index of every (tile, Gaussian) instance, tile-major, depth-ordered per tile
     uint2* ranges;          // [tiles] (start, end) into ids_sorted
 };
 
 // ---- binning (g4d_bin.cu) ---------------------------------------------------------------------------------------
-struct BinCtl { uint32_t n_visible, R, overflow, pad; };   // device-resident results of one forward's binning
+struct BinCtl { uint32_t n_visible, R, overflow, pad; long long phase_clk[16]; };   // device-resident results of one forward's binning (+ CTA 0's clock at every phase boundary)
 struct BinSortArgs {
     int64_t n;
     const float2* rec2; const uint32_t* tiles_touched; const uint2* rect; const float4* rec0; const float4* rec1;
@@ -44,18 +45,21 @@ struct BinSortArgs {
 struct BinPlaceArgs {
     const uint32_t* perm; const uint2* rect; const float4* rec0; const float4* rec1;
     const uint32_t* chunk_start; const uint32_t* M; const uint32_t* tile_total;
+    uint32_t* tile_start;          // [tiles] exclusive scan of tile_total (written by placement CTA 0, read by the fix-up)
     uint2* ranges;                 // [tiles] (start, end) clamped to the capacity; empty tiles (0, 0)
-    uint32_t* ids; uint32_t capacity;
+    uint32_t* ids;                 // [capacity] final instance list (Gaussian indices)
+    uint32_t* kbuf;                // [capacity] depth ranks as placed (unordered inside a (tile, chunk) sub-segment)
+    uint32_t capacity;
     int grid_x, grid_y, num_tiles, band_rows, tight;
 };
-struct BinLayout { uint32_t* chunk_start; uint32_t* M; uint32_t* tile_total; BinCtl* ctl; int chunks; };
+struct BinLayout { uint32_t* chunk_start; uint32_t* M; uint32_t* tile_total; uint32_t* tile_start; BinCtl* ctl; int chunks; };
 size_t bin_aux_bytes(int64_t n, int num_tiles, int sm_count);
 // depth sort + chunking + per-(tile, chunk) counts + scan over the chunks: M, tile_total, ctl->R.  One cooperative launch.
 cudaError_t launch_bin_sort(int64_t n, int grid_x, int grid_y, const GeomBuffers& g, void* aux, int tight, int sm_count,
                             BinLayout* out, cudaStream_t st);
-// tile ranges + stable counting placement of every instance into its tile segment
-cudaError_t launch_bin_place(int grid_x, int grid_y, const GeomBuffers& g, const BinLayout& lay, uint32_t* ids, uint2* ranges,
-                             uint32_t capacity, int tight, cudaStream_t st);
+// tile ranges + placement of every instance into its (tile, chunk) sub-segment + per-sub-segment ordering (2 launches)
+cudaError_t launch_bin_place(int grid_x, int grid_y, const GeomBuffers& g, const BinLayout& lay, uint32_t* ids, uint32_t* kbuf,
+                             uint2* ranges, uint32_t capacity, int tight, cudaStream_t st);
 
 struct ImageBuffers {
     float* final_T;      // [H*W]

@@ -241,7 +241,10 @@ enum { G4D_BUF_DEPTH = 1,      /* float  [N]  view-space depth                  
        G4D_BUF_N_CONTRIB = 11, /* uint32 [H,W]                                    */
        G4D_BUF_CLAMPED = 12,   /* uint8  [N,3]                                    */
        G4D_BUF_DEFORMED = 13,  /* float  [N,11] (xyz, scale, rot, opacity) post-activation, fused path */
-       G4D_BUF_DEFORMED_SHS = 14 /* float [N,48] deformed SH coefficients (fused path with the SHS head active) */ };
+       G4D_BUF_DEFORMED_SHS = 14, /* float [N,48] deformed SH coefficients (fused path with the SHS head active) */
+       G4D_BUF_BIN_PHASES = 15 /* int64 [16] profiling: SM clock of CTA 0 at the phase boundaries of bin_sort (0 start,
+                                  1 after the key range, 2 after the depth sort, 3 after chunking, 4 after counting,
+                                  5 end), [15] = significant key bits */ };
 int64_t g4d_context_read(G4DContext *ctx, int which, void *host_dst, int64_t bytes);
 
 /* per-stage device time (ms) of the LAST forward / backward on this context, measured with CUDA events on the

@@ -592,9 +592,19 @@ def test_tensor_core_paths_corner_cases_vs_oracle(net, n):
 @pytest.mark.parametrize("net,n", [("small128", 700), ("dynerf", 21000), ("hypernerf", 40000)])
 def test_tensor_core_backward_matches_ffma_path(net, n):
     """BF16x2 tcgen05 backward (dgrad + wgrad kernels) against the FP32 FFMA backward: same gradients for every input
-    and every parameter.  n is chosen so that some CTAs own one tile and others two or three (persistent loop)."""
+    and every parameter.  n is chosen so that some CTAs own one tile and others two or three (persistent loop).
+    The two paths take their ReLU signs from different places (bits saved by the tensor-core forward vs the FFMA kernel's own
+    fp32 recomputation), so a Gaussian with a pre-activation within rounding of 0 may legitimately differ: the upstream
+    gradient of exactly those Gaussians (found in fp64 on the oracle, util_scene.kink_rows) is zeroed on both sides, and then
+    EVERYTHING must agree to BF16x2 accuracy -- no percentile, no 3x factor."""
     mod = make_module(net, seed=5)
+    cfg, prm = oracle_params_from_module(mod)
     ins, probes = _deform_inputs(n, 3)
+    kink = kink_rows(cfg, prm, ins[0], 0.27)
+    assert float(kink.float().mean()) <= 0.05
+    probes = [p.clone() for p in probes]
+    for p in probes:
+        p[kink] = 0
     ws = g4d._lib.Workspace.get(0)
     t = torch.tensor(0.27).repeat(n, 1).cuda()
     res = []
@@ -611,17 +621,12 @@ def test_tensor_core_backward_matches_ffma_path(net, n):
         ws.set_option(g4d._lib.OPT_TENSOR_CORES, 1)
     (gi_tc, gp_tc), (gi_ff, gp_ff) = res
     for a, b, nm in zip(gi_tc, gi_ff, ("xyz", "scales", "rot", "opacity", "shs")):
-        e, emax = rel_err_bulk(a.cpu().numpy(), b.cpu().numpy())
-        assert e <= 2e-4 and emax <= 5e-2, (nm, e, emax)
+        e = rel_err(a.cpu().numpy(), b.cpu().numpy())
+        assert e <= 2e-4, (nm, e)
     assert gp_tc.keys() == gp_ff.keys()
-    # the FFMA backward re-derives the ReLU signs from its own fp32 recomputation while the tensor-core backward uses the
-    # signs its forward saved: a unit whose pre-activation is within rounding of 0 may differ, which moves the norm-wise
-    # error by ~1/sqrt(n) per such unit; the element-wise bulk must agree to BF16x2 accuracy
     for k in gp_ff:
-        a, b = gp_tc[k].cpu().numpy(), gp_ff[k].cpu().numpy()
-        e = rel_err(a, b)
-        eb, _ = rel_err_bulk(a, b, q=90)        # one flipped unit touches one row of dW1 / one entry of db1: p90, not p99.9
-        assert e <= 3 * GRAD_TOL and eb <= 1e-4, (k, e, eb)
+        e = rel_err(gp_tc[k].cpu().numpy(), gp_ff[k].cpu().numpy())
+        assert e <= 2e-4, (k, e)
 
 
 def test_tight_cull_gives_bit_identical_images_with_fewer_instances():

@@ -70,6 +70,9 @@ def main():
             s = c.stats()
             print("iter", i, "R=%d visible=%d" % (s.num_rendered, s.num_visible),
                   {k: round(v, 4) for k, v in c.stage_times().items()}, flush=True)
+            ph = c.read("bin_phases")
+            names = ["key_range", "depth_sort", "chunking", "count", "scan"]
+            print("   bin_sort phase cycles (CTA 0):", {n_: int(ph[j + 1] - ph[j]) for j, n_ in enumerate(names)}, "key bits", int(ph[15]), flush=True)
 
 
 if __name__ == "__main__":
