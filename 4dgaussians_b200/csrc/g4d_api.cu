@@ -138,6 +138,7 @@ int ensure_geom(G4DContext* c, int64_t n) {
     c->g.radii = (int32_t*)(base + o3); c->g.rect = (uint2*)(base + o4); c->g.tiles_touched = (uint32_t*)(base + o5);
     c->g.clamped = (uint8_t*)(base + o7);
     c->g.perm = (uint32_t*)(base + o8);
+    c->g.depth_range = &c->cam.as<CameraDev>()->depth_min;
     return G4D_OK;
 }
 
@@ -158,10 +159,10 @@ int ensure_image(G4DContext* c, int H, int W) {
 int ensure_bin(G4DContext* c, int64_t r) {
     const size_t R = (size_t)(r > 0 ? r : 1);
     if ((int64_t)R <= c->capacity && c->bin.p) return G4D_OK;
-    G4D_CUDA(c->bin.ensure(R * 8));          // DevBuf grows by 1.5x: the one growth factor of the instance list
-    c->capacity = (int64_t)(c->bin.cap / 8);
-    c->b.ids_sorted = c->bin.as<uint32_t>();
-    c->b.kbuf = c->bin.as<uint32_t>() + c->capacity;
+    G4D_CUDA(c->bin.ensure(R * 12 + 16));    // DevBuf grows by 1.5x: the one growth factor of the instance list
+    c->capacity = (int64_t)((c->bin.cap - 16) / 12);
+    c->b.kbuf = c->bin.as<uint2>();          // (8-byte entries first: alignment)
+    c->b.ids_sorted = reinterpret_cast<uint32_t*>(c->b.kbuf + c->capacity);
     return G4D_OK;
 }
 

@@ -1,8 +1,8 @@
 // g4d_bin.cu -- tile binning as TWO hand-written launches, no library sort, no host round trip:
 //
 //   bin_sort_kernel  (cooperative, persistent, one 1024-thread CTA per SM, grid-wide syncs between phases)
-//       0. min / max of the visible Gaussians' depth bits -> the keys are sorted as (bits - min): 24-27 significant bits
-//          instead of 32, i.e. 3 radix passes instead of 4
+//       0. the keys are sorted as (depth bits - min) -- min / max of the visible Gaussians' depth bits are reduced by the
+//          projection stage -- 24-27 significant bits instead of 32, i.e. 3 radix passes instead of 4
 //       1. LSD radix sort (9-bit digits, stable) of the VISIBLE Gaussians by depth; the first pass compacts away the
 //          invisible ones while it scatters.  Ties keep Gaussian-index order.                            -> perm[n_visible]
 //       2. the depth-ordered list is cut into one chunk per CTA with equal numbers of tile instances (near Gaussians cover
@@ -169,18 +169,28 @@ __device__ __forceinline__ uint32_t radix_pass(const BinSortArgs& a, cg::grid_gr
 // f(tile index inside the band, position k of the Gaussian in perm).  No order is promised inside the range: small rects
 // (< 32 tiles) are walked by ONE LANE each (a far chunk holds thousands of 1-4 tile Gaussians: 32 of them advance per
 // iteration), large ones by the whole warp (32 tiles per step).
-template <class F>
+// f(tile index inside the band, position k of the Gaussian in perm, Gaussian index); f4(tiles[4] (-1 = none), k, index)
+// handles up to four pairs of one Gaussian at once
+template <class F, class F4>
 __device__ __forceinline__ void walk_unordered(const uint32_t* __restrict__ perm, const uint2* __restrict__ rect,
                                                const float4* __restrict__ rec0, const float4* __restrict__ rec1, int tight, uint32_t ks,
-                                               uint32_t ke, int y0, int y1, int grid_x, F&& f) {
+                                               uint32_t ke, int y0, int y1, int grid_x, F&& f, F4&& f4) {
     const int lane = threadIdx.x & 31;
+    // two-deep register prefetch (perm two groups ahead, rect one group ahead): both are L2 round trips, and a far chunk is a
+    // long chain of such groups with only a few tiles of work each
+    uint32_t gi_n = ks + lane < ke ? perm[ks + lane] : 0u;
+    uint32_t gi_nn = ks + 32u + lane < ke ? perm[ks + 32u + lane] : 0u;
+    uint2 rc_n = ks + lane < ke ? rect[gi_n] : make_uint2(0u, 0u);
     for (uint32_t k0 = ks; k0 < ke; k0 += 32u) {
         const uint32_t k = k0 + lane;
         int minx = 0, miny = 0, w = 0, h = 0;
+        const uint32_t gi = gi_n;
+        const uint2 rc = rc_n;
+        gi_n = gi_nn;
+        rc_n = k + 32u < ke ? rect[gi_n] : make_uint2(0u, 0u);
+        gi_nn = k + 64u < ke ? perm[k + 64u] : 0u;
         float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
         if (k < ke) {
-            const uint32_t gi = perm[k];
-            const uint2 rc = rect[gi];
             minx = (int)(rc.x & 0xFFFFu);
             w = (int)(rc.y & 0xFFFFu) - minx;
             miny = max((int)(rc.x >> 16), y0);
@@ -192,9 +202,17 @@ __device__ __forceinline__ void walk_unordered(const uint32_t* __restrict__ perm
         const bool big = nt >= 32;
         if (!big) {
             int x = 0, y = 0;
-            for (int i = 0; i < nt; ++i) {
-                if (!tight || tile_contributes(r0, r1, minx + x, miny + y)) f((miny + y - y0) * grid_x + minx + x, k);
-                if (++x == w) { x = 0; ++y; }
+            for (int i = 0; i < nt; i += 4) {          // four pairs per trip: their atomics overlap (see f4 below)
+                int tl[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    tl[u] = -1;
+                    if (i + u < nt) {
+                        if (!tight || tile_contributes(r0, r1, minx + x, miny + y)) tl[u] = (miny + y - y0) * grid_x + minx + x;
+                        if (++x == w) { x = 0; ++y; }
+                    }
+                }
+                f4(tl, k, gi);
             }
         }
         uint32_t todo = __ballot_sync(0xffffffffu, big);
@@ -203,7 +221,7 @@ __device__ __forceinline__ void walk_unordered(const uint32_t* __restrict__ perm
             todo &= todo - 1;
             const int bx = __shfl_sync(0xffffffffu, minx, src), by = __shfl_sync(0xffffffffu, miny, src);
             const int bw = __shfl_sync(0xffffffffu, w, src), bn = __shfl_sync(0xffffffffu, nt, src);
-            const uint32_t bk = __shfl_sync(0xffffffffu, k, src);
+            const uint32_t bk = __shfl_sync(0xffffffffu, k, src), bg = __shfl_sync(0xffffffffu, gi, src);
             float4 q0 = r0, q1 = r1;
             if (tight) {
                 q0.x = __shfl_sync(0xffffffffu, r0.x, src); q0.y = __shfl_sync(0xffffffffu, r0.y, src);
@@ -212,7 +230,7 @@ __device__ __forceinline__ void walk_unordered(const uint32_t* __restrict__ perm
             }
             for (int t = lane; t < bn; t += 32) {
                 const int ty = t / bw, tx = t - ty * bw;
-                if (!tight || tile_contributes(q0, q1, bx + tx, by + ty)) f((by + ty - y0) * grid_x + bx + tx, bk);
+                if (!tight || tile_contributes(q0, q1, bx + tx, by + ty)) f((by + ty - y0) * grid_x + bx + tx, bk, bg);
             }
         }
     }
@@ -234,30 +252,11 @@ __global__ void __launch_bounds__(kBinThreads, 1) bin_sort_kernel(BinSortArgs a)
     const uint32_t N = (uint32_t)a.n;
 
     G4D_BIN_MARK(0);
-    // ---- 0. range of the visible depth bits
-    {
-        const uint32_t per = (N + G - 1) / G;
-        const uint32_t lo = min(c * per, N), hi = min(lo + per, N);
-        uint32_t mn = 0xFFFFFFFFu, mx = 0u;
-        for (uint32_t i = lo + tid; i < hi; i += kBinThreads) {
-            if (a.tiles_touched[i] != 0) {
-                const uint32_t k = __float_as_uint(a.rec2[i].y);
-                mn = min(mn, k); mx = max(mx, k);
-            }
-        }
-        mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
-        if (tid == 0) { s.mm[0] = 0xFFFFFFFFu; s.mm[1] = 0u; }
-        __syncthreads();
-        if (lane == 0) { atomicMin(&s.mm[0], mn); atomicMax(&s.mm[1], mx); }
-        __syncthreads();
-        if (tid == 0) { a.S[c] = s.mm[0]; a.S[G + c] = s.mm[1]; if (c == 0) { a.ctl->R = 0u; a.ctl->overflow = 0u; } }
-    }
-    grid.sync();
+    // ---- 0. range of the visible depth bits: reduced by the projection stage (RED.MIN / RED.MAX into the context's CameraDev)
+    if (blockIdx.x == 0 && tid == 0) { a.ctl->R = 0u; a.ctl->overflow = 0u; }
     uint32_t kmin, kbits;
     {
-        uint32_t mn = 0xFFFFFFFFu, mx = 0u;
-        for (uint32_t j = lane; j < G; j += 32) { mn = min(mn, __ldcg(a.S + j)); mx = max(mx, __ldcg(a.S + G + j)); }
-        mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
+        const uint32_t mn = __ldcg(a.depth_range), mx = __ldcg(a.depth_range + 1);
         kmin = mn <= mx ? mn : 0u;
         const uint32_t span = mn <= mx ? mx - mn : 0u;
         kbits = span ? 32u - (uint32_t)__clz((int)span) : 1u;
@@ -331,7 +330,11 @@ __global__ void __launch_bounds__(kBinThreads, 1) bin_sort_kernel(BinSortArgs a)
             for (int j = tid; j < bn; j += kBinThreads) dyn[j] = 0;
             __syncthreads();
             walk_unordered(a.perm, a.rect, a.rec0, a.rec1, a.tight, ks, ke, y0, y1, a.grid_x,
-                           [&](int tile, uint32_t) { atomicAdd(&dyn[tile], 1u); });
+                           [&](int tile, uint32_t, uint32_t) { atomicAdd(&dyn[tile], 1u); },
+                           [&](const int (&tl)[4], uint32_t, uint32_t) {
+#pragma unroll
+                               for (int u = 0; u < 4; ++u) if (tl[u] >= 0) atomicAdd(&dyn[tl[u]], 1u);
+                           });
             __syncthreads();
             for (int j = tid; j < bn; j += kBinThreads) a.M[(size_t)(y0 * a.grid_x + j) * G + c] = dyn[j];
             __syncthreads();
@@ -413,28 +416,39 @@ __global__ void __launch_bounds__(kBinThreads, 1) bin_place_kernel(BinPlaceArgs 
             }
         }
         __syncthreads();
-        walk_unordered(a.perm, a.rect, a.rec0, a.rec1, a.tight, ks, ke, y0, y1, a.grid_x, [&](int tile, uint32_t k) {
-            const uint32_t slot = atomicAdd(&cur[tile], 1u);
-            if (slot < a.capacity) a.kbuf[slot] = k;
-        });
+        walk_unordered(a.perm, a.rect, a.rec0, a.rec1, a.tight, ks, ke, y0, y1, a.grid_x,
+                       [&](int tile, uint32_t k, uint32_t gi) {
+                           const uint32_t slot = atomicAdd(&cur[tile], 1u);
+                           if (slot < a.capacity) a.kbuf[slot] = make_uint2(k, gi);
+                       },
+                       [&](const int (&tl)[4], uint32_t k, uint32_t gi) {
+                           uint32_t slot[4];
+#pragma unroll
+                           for (int u = 0; u < 4; ++u) slot[u] = tl[u] >= 0 ? atomicAdd(&cur[tl[u]], 1u) : 0xFFFFFFFFu;
+#pragma unroll
+                           for (int u = 0; u < 4; ++u) if (slot[u] < a.capacity) a.kbuf[slot[u]] = make_uint2(k, gi);
+                       });
         __syncthreads();
     }
 }
 
-// Fix-up: order every (tile, chunk) sub-segment by depth rank and translate rank -> Gaussian index.  One warp per tile; a
-// round reads 32 sub-segment bounds (the M row of a tile is contiguous: coalesced), single entries are translated by their
-// lane, every longer sub-segment is broadcast and ranked by the whole warp, one entry per lane: keys are unique, so the
-// final position of an entry is the number of smaller keys in its sub-segment (n is ~4 on average).
+// Fix-up: order every (tile, chunk) sub-segment by depth rank.  One warp per (tile, 32 chunks); it reads 32 sub-segment bounds
+// (the M row of a tile is contiguous: coalesced) and every lane loads the first eight (rank, Gaussian) pairs of ITS
+// sub-segment at once -- one memory round trip per round, not one per entry; sub-segments of up to eight entries (the bulk:
+// the average is ~4) are ranked in registers by their lane, longer ones by the whole warp with shuffles.  Ranks are unique,
+// so the final position of an entry is the number of smaller ranks in its sub-segment.
 __global__ void __launch_bounds__(256) bin_fix_kernel(BinPlaceArgs a, int chunks) {
     const int lane = threadIdx.x & 31;
-    const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int rounds = (chunks + 31) / 32;
+    const uint32_t item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // (tile, round): a dense tile's rounds run
+    const uint32_t t = item / (uint32_t)rounds;                                   // on different warps
     if (t >= (uint32_t)a.num_tiles) return;
     const uint32_t total = __ldg(a.tile_total + t);
     if (total == 0) return;
     const uint32_t start = a.tile_start[t];
     const uint32_t* mrow = a.M + (size_t)t * chunks;
-    for (int c0 = 0; c0 < chunks; c0 += 32) {
-        const int c = c0 + lane;
+    {
+        const int c = (int)(item - t * (uint32_t)rounds) * 32 + lane;
         uint32_t lo = 0, hi = 0;
         if (c < chunks) {
             lo = start + __ldg(mrow + c);
@@ -442,22 +456,50 @@ __global__ void __launch_bounds__(256) bin_fix_kernel(BinPlaceArgs a, int chunks
             lo = min(lo, a.capacity); hi = min(hi, a.capacity);
         }
         const uint32_t n = hi - lo;
-        if (n == 1) a.ids[lo] = a.perm[a.kbuf[lo]];
-        uint32_t todo = __ballot_sync(0xffffffffu, n > 1);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const uint32_t blo = __shfl_sync(0xffffffffu, lo, src), bnn = __shfl_sync(0xffffffffu, n, src);
-            for (uint32_t i0 = 0; i0 < bnn; i0 += 32) {
-                const uint32_t i = i0 + lane;
-                const uint32_t ki = i < bnn ? a.kbuf[blo + i] : 0xFFFFFFFFu;
-                uint32_t r = 0;
-                if (bnn <= 32) {                                   // the whole sub-segment sits in the lanes: rank by shuffle
-                    for (uint32_t j = 0; j < bnn; ++j) r += __shfl_sync(0xffffffffu, ki, (int)j) < ki ? 1u : 0u;
-                } else {
-                    for (uint32_t j = 0; j < bnn; ++j) r += a.kbuf[blo + j] < ki ? 1u : 0u;
+        constexpr int E = 8;
+        uint2 e[E];
+#pragma unroll
+        for (int q = 0; q < E; ++q) e[q] = (uint32_t)q < n ? a.kbuf[lo + q] : make_uint2(0xFFFFFFFFu, 0u);
+        if (n <= E) {
+#pragma unroll
+            for (int q = 0; q < E; ++q) {
+                if ((uint32_t)q < n) {
+                    uint32_t r = 0;
+#pragma unroll
+                    for (int p = 0; p < E; ++p) r += e[p].x < e[q].x ? 1u : 0u;
+                    a.ids[lo + r] = e[q].y;
                 }
-                if (i < bnn) a.ids[blo + r] = a.perm[ki];
+            }
+        }
+        // longer sub-segments: the whole warp, one entry per lane; the next one's entries are loaded before the current is ranked
+        uint32_t todo = __ballot_sync(0xffffffffu, n > E);
+        uint32_t blo = 0, bnn = 0;
+        uint2 ei = make_uint2(0xFFFFFFFFu, 0u);
+        if (todo) {
+            const int src = __ffs(todo) - 1;
+            blo = __shfl_sync(0xffffffffu, lo, src); bnn = __shfl_sync(0xffffffffu, n, src);
+            if ((uint32_t)lane < bnn) ei = a.kbuf[blo + lane];
+        }
+        while (todo) {
+            todo &= todo - 1;
+            const uint32_t clo = blo, cnn = bnn;
+            const uint2 ce = ei;
+            if (todo) {                                             // prefetch the next long sub-segment
+                const int src = __ffs(todo) - 1;
+                blo = __shfl_sync(0xffffffffu, lo, src); bnn = __shfl_sync(0xffffffffu, n, src);
+                ei = (uint32_t)lane < bnn ? a.kbuf[blo + lane] : make_uint2(0xFFFFFFFFu, 0u);
+            }
+            if (cnn <= 32) {                                        // the whole sub-segment sits in the lanes: rank by shuffle
+                uint32_t r = 0;
+                for (uint32_t j = 0; j < cnn; ++j) r += __shfl_sync(0xffffffffu, ce.x, (int)j) < ce.x ? 1u : 0u;
+                if ((uint32_t)lane < cnn) a.ids[clo + r] = ce.y;
+            } else {
+                for (uint32_t i = lane; i < cnn; i += 32) {
+                    const uint2 x = a.kbuf[clo + i];
+                    uint32_t r = 0;
+                    for (uint32_t j = 0; j < cnn; ++j) r += a.kbuf[clo + j].x < x.x ? 1u : 0u;
+                    a.ids[clo + r] = x.y;
+                }
             }
         }
     }
@@ -484,6 +526,7 @@ cudaError_t launch_bin_sort(int64_t n, int grid_x, int grid_y, const GeomBuffers
     auto take = [&](size_t bytes) { char* r = p; p += align256(bytes); return r; };
     BinSortArgs a{};
     a.n = n; a.rec2 = g.rec2; a.tiles_touched = g.tiles_touched; a.rect = g.rect; a.rec0 = g.rec0; a.rec1 = g.rec1;
+    a.depth_range = g.depth_range;
     a.kA = (uint32_t*)take(N * 4); a.vA = (uint32_t*)take(N * 4); a.kB = (uint32_t*)take(N * 4); a.vB = (uint32_t*)take(N * 4);
     a.perm = g.perm;
     a.H = (uint32_t*)take(G * kRadix * 4); a.S = (uint32_t*)take(2 * G * 4); a.chunk_start = (uint32_t*)take((G + 1) * 4);
@@ -505,7 +548,7 @@ cudaError_t launch_bin_sort(int64_t n, int grid_x, int grid_y, const GeomBuffers
     return cudaLaunchCooperativeKernel((const void*)bin_sort_kernel, dim3((unsigned)sm_count), dim3(kBinThreads), args, smem, st);
 }
 
-cudaError_t launch_bin_place(int grid_x, int grid_y, const GeomBuffers& g, const BinLayout& lay, uint32_t* ids, uint32_t* kbuf,
+cudaError_t launch_bin_place(int grid_x, int grid_y, const GeomBuffers& g, const BinLayout& lay, uint32_t* ids, uint2* kbuf,
                              uint2* ranges, uint32_t capacity, int tight, cudaStream_t st) {
     const int num_tiles = grid_x * grid_y;
     BinPlaceArgs a{};
@@ -520,7 +563,8 @@ cudaError_t launch_bin_place(int grid_x, int grid_y, const GeomBuffers& g, const
     if (e != cudaSuccess) return e;
     bin_place_kernel<<<lay.chunks, kBinThreads, smem, st>>>(a);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    bin_fix_kernel<<<(num_tiles + 7) / 8, 256, 0, st>>>(a, lay.chunks);
+    const int rounds = (lay.chunks + 31) / 32;
+    bin_fix_kernel<<<(num_tiles * rounds + 7) / 8, 256, 0, st>>>(a, lay.chunks);
     return cudaGetLastError();
 }
 

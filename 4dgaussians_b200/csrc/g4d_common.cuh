@@ -50,7 +50,9 @@ constexpr float kSH1 = 0.4886025119029199f;
 // Device-resident camera, written once per forward by pack_camera_kernel and read (uniformly) by all stages.
 struct CameraDev {
     int32_t H, W, sh_degree, grid_x;
-    int32_t grid_y, num_tiles, pad0, pad1;
+    int32_t grid_y, num_tiles;
+    uint32_t depth_min, depth_max;   // bits of the smallest / largest view-space depth among the visible Gaussians of this
+                                     // forward (reset by pack_camera, RED.MIN / RED.MAX by the projection stage, read by bin_sort)
     float tanfovx, tanfovy, scale_modifier, time;
     float focal_x, focal_y, pad2, pad3;
     float view[16];

@@ -27,7 +27,7 @@ __global__ void pack_camera_kernel(G4DCamera c, CameraDev* dst) {
         dst->grid_x = (c.image_width + kTile - 1) / kTile;
         dst->grid_y = (c.image_height + kTile - 1) / kTile;
         dst->num_tiles = dst->grid_x * dst->grid_y;
-        dst->pad0 = dst->pad1 = 0;
+        dst->depth_min = 0xFFFFFFFFu; dst->depth_max = 0u;
         dst->tanfovx = c.tanfovx; dst->tanfovy = c.tanfovy; dst->scale_modifier = c.scale_modifier; dst->time = c.time;
         dst->focal_x = (float)c.image_width / (2.f * c.tanfovx);
         dst->focal_y = (float)c.image_height / (2.f * c.tanfovy);

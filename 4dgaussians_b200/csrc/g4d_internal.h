@@ -17,11 +17,12 @@ struct GeomBuffers {
     uint2* rect;         // x = minx | miny<<16, y = maxx | maxy<<16   (tile units)
     uint32_t* tiles_touched;
     uint32_t* perm;      // the VISIBLE Gaussians' indices sorted by (depth bits, index)   (bin_sort_kernel)
+    uint32_t* depth_range;   // -> CameraDev.depth_min / depth_max of this context
     uint8_t* clamped;    // bit ch set when the forward clamped colour channel ch at 0
 };
 
 struct BinBuffers {
-    uint32_t* kbuf;         // [capacity] placement scratch (depth ranks)
+    uint2* kbuf;            // [capacity] placement scratch: (depth rank, Gaussian index)
     uint32_t* ids_sorted;   // [capacity] Gaussian index of every (tile, Gaussian) instance, tile-major, depth-ordered per tile
     uint2* ranges;          // [tiles] (start, end) into ids_sorted
 };
@@ -31,6 +32,7 @@ struct BinCtl { uint32_t n_visible, R, overflow, pad; long long phase_clk[16]; }
 struct BinSortArgs {
     int64_t n;
     const float2* rec2; const uint32_t* tiles_touched; const uint2* rect; const float4* rec0; const float4* rec1;
+    const uint32_t* depth_range;   // [2] min / max depth bits of the visible Gaussians (written by the projection stage)
     uint32_t *kA, *vA, *kB, *vB;   // [N] ping-pong buffers of the depth sort
     uint32_t* perm;                // [N] out: visible Gaussians in depth order
     uint32_t* H;                   // [chunks][256] digit histograms of the current pass
@@ -48,7 +50,7 @@ struct BinPlaceArgs {
     uint32_t* tile_start;          // [tiles] exclusive scan of tile_total (written by placement CTA 0, read by the fix-up)
     uint2* ranges;                 // [tiles] (start, end) clamped to the capacity; empty tiles (0, 0)
     uint32_t* ids;                 // [capacity] final instance list (Gaussian indices)
-    uint32_t* kbuf;                // [capacity] depth ranks as placed (unordered inside a (tile, chunk) sub-segment)
+    uint2* kbuf;                   // [capacity] (depth rank, Gaussian index) as placed: unordered inside a (tile, chunk) sub-segment
     uint32_t capacity;
     int grid_x, grid_y, num_tiles, band_rows, tight;
 };
@@ -58,7 +60,7 @@ size_t bin_aux_bytes(int64_t n, int num_tiles, int sm_count);
 cudaError_t launch_bin_sort(int64_t n, int grid_x, int grid_y, const GeomBuffers& g, void* aux, int tight, int sm_count,
                             BinLayout* out, cudaStream_t st);
 // tile ranges + placement of every instance into its (tile, chunk) sub-segment + per-sub-segment ordering (2 launches)
-cudaError_t launch_bin_place(int grid_x, int grid_y, const GeomBuffers& g, const BinLayout& lay, uint32_t* ids, uint32_t* kbuf,
+cudaError_t launch_bin_place(int grid_x, int grid_y, const GeomBuffers& g, const BinLayout& lay, uint32_t* ids, uint2* kbuf,
                              uint2* ranges, uint32_t capacity, int tight, cudaStream_t st);
 
 struct ImageBuffers {

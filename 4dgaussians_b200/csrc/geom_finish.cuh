@@ -15,8 +15,18 @@ struct DeformIO {
     int32_t* out_radii;
 };
 
+// depth range of the visible Gaussians for the binning sort (keys are sorted as bits - min: fewer radix passes).  One RED
+// pair per warp: the lanes that reach this point reduce among themselves first.
+G4D_D void note_depth_range(const GeomBuffers& g, uint32_t tiles, float depth) {
+    const unsigned m = __activemask();
+    const uint32_t k = __float_as_uint(depth);
+    const uint32_t lo = __reduce_min_sync(m, tiles ? k : 0xFFFFFFFFu), hi = __reduce_max_sync(m, tiles ? k : 0u);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1) && lo <= hi) { atomicMin(g.depth_range, lo); atomicMax(g.depth_range + 1, hi); }
+}
+
 G4D_D void store_projected(const GeomBuffers& g, int64_t gi, bool ok, const Projected& pr, float opacity, const float rgb[3],
                            uint32_t bits, int32_t* out_radii) {
+    note_depth_range(g, pr.tiles, pr.depth);
     g.rec0[gi] = make_float4(pr.px, pr.py, pr.conx, pr.cony);
     g.rec1[gi] = make_float4(pr.conz, ok ? opacity : 0.f, rgb[0], rgb[1]);
     g.rec2[gi] = make_float2(rgb[2], pr.depth);
@@ -80,6 +90,7 @@ G4D_D void fused_finish_geometry(const CameraDev& cam, const DeformIO& io, int64
     if (io.out_radii) io.out_radii[gi] = pr.radius;
     g.rect[gi] = make_uint2((uint32_t)pr.rminx | ((uint32_t)pr.rminy << 16), (uint32_t)pr.rmaxx | ((uint32_t)pr.rmaxy << 16));
     g.tiles_touched[gi] = pr.tiles;
+    note_depth_range(g, pr.tiles, pr.depth);
     if (io.fo.means3D) {
         io.fo.means3D[3 * gi] = p.x; io.fo.means3D[3 * gi + 1] = p.y; io.fo.means3D[3 * gi + 2] = p.z;
         io.fo.scales[3 * gi] = sc.x; io.fo.scales[3 * gi + 1] = sc.y; io.fo.scales[3 * gi + 2] = sc.z;
