@@ -1,8 +1,8 @@
 """Build recipe for libg4d.so (hand-written sm_100a kernels behind the C-ABI of include/g4d.h).
 
 In-tree build with plain nvcc (no torch dependency): the .so travels to the GPU box with the snapshot.
-``g4d_geom.cu`` and ``g4d_deform_tc.cu`` -- the two translation units that contain the projection maths -- are compiled
-with -fmad=false (bit-exact index stages, see g4d_math.cuh); the others use the default FMA contraction.  The tcgen05
+``g4d_geom.cu``, ``g4d_deform_tc.cu`` and ``g4d_deform_f16.cu`` -- the translation units that contain the projection maths
+(and ``g4d_knn.cu``: exact distances) -- are compiled with -fmad=false (bit-exact index stages, see g4d_math.cuh); the others use the default FMA contraction.  The tcgen05
 building-block self test (``g4d_tc_selftest.cu``) goes into its own ``libg4d_selftest.so`` (tests / tools only).
 """
 from __future__ import annotations
@@ -32,6 +32,7 @@ UNITS = {
     "g4d_backward.cu": [],
     "g4d_api.cu": [],
     "g4d_deform_tc.cu": ["-fmad=false"],
+    "g4d_deform_f16.cu": ["-fmad=false"],
     "g4d_deform_tc_bwd.cu": [],
 }
 

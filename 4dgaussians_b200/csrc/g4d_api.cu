@@ -56,7 +56,7 @@ struct G4DWorkspace {
     int64_t min_capacity = 0;
     int tight_cull = 0;
     int stage_timing = 0;
-    int tensor_cores = 1;
+    int tensor_cores = 2;      // 0: FP32 FFMA kernels, 1: tcgen05 3xTF32, 2 (default): tcgen05 FP16x2, two tiles in flight
     int warp_cull = 1;
     DevBuf tc_packed;
     TcWeights tcw{};
@@ -207,11 +207,24 @@ int refresh_packed(G4DWorkspace* ws, const G4DDeformParams* p, cudaStream_t st) 
     return G4D_OK;
 }
 
+bool forward_on_tensor_cores(const G4DWorkspace* ws, const DeformDesc& d) {
+    return ws->tensor_cores == 2 ? f16_deform_supported(d) : (ws->tensor_cores == 1 && tc_deform_supported(d));
+}
+
 // tensor-core weight images, same caching rule as refresh_packed
 int refresh_tc(G4DWorkspace* ws, const G4DDeformParams* p, cudaStream_t st) {
-    if (ws->tc_version == p->version && ws->tc_key == (const void*)p->w0 && ws->tc_packed.p) return G4D_OK;
+    const int arith = ws->tensor_cores == 2 ? 2 : 1;
+    ws->tcw.status = ws->h_pinned + 8;
+    if (arith == 2 && ws->h_pinned[8]) {
+        ws->h_pinned[8] = 0;
+        return fail(G4D_ERR_OVERFLOW, "an earlier FP16x2 tensor-core launch met a value outside the f16 operand range (activation >= 8188, "
+                                      "feature >= 1023 or weight >= 255): its results were saturated; set G4D_OPT_TENSOR_CORES = 1 (3xTF32)");
+    }
+    if (ws->tc_version == p->version && ws->tc_key == (const void*)p->w0 && ws->tc_packed.p && ws->tcw.arith == arith) return G4D_OK;
     G4D_CUDA(ws->tc_packed.ensure(tc_packed_floats(*p) * 4));
-    G4D_CUDA(launch_tc_pack_weights(*p, ws->tc_packed.as<float>(), &ws->tcw, st));
+    if (arith == 2) G4D_CUDA(launch_f16_pack_weights(*p, ws->tc_packed.as<float>(), &ws->tcw, st));
+    else G4D_CUDA(launch_tc_pack_weights(*p, ws->tc_packed.as<float>(), &ws->tcw, st));
+    ws->tcw.arith = arith;
     ws->tc_version = p->version;
     ws->tc_key = (const void*)p->w0;
     return G4D_OK;
@@ -436,6 +449,7 @@ G4DWorkspace* g4d_workspace_create(int device) {
     cudaDeviceProp prop{};
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ws->sm_count = prop.multiProcessorCount;
     if (cudaMallocHost((void**)&ws->h_pinned, 64) != cudaSuccess) { delete ws; fail(G4D_ERR_NOMEM, "cudaMallocHost"); return nullptr; }
+    for (int i = 0; i < 16; ++i) ws->h_pinned[i] = 0;      // [0]: R read-back, [8]: FP16x2 range flag (written by the kernel)
     return ws;
 }
 
@@ -477,7 +491,7 @@ int g4d_workspace_set_option(G4DWorkspace* ws, int option, int64_t value) {
         case G4D_OPT_INSTANCE_CAPACITY: ws->min_capacity = value; return G4D_OK;
         case G4D_OPT_TIGHT_CULL: ws->tight_cull = value ? 1 : 0; return G4D_OK;
         case G4D_OPT_STAGE_TIMING: ws->stage_timing = value ? 1 : 0; return G4D_OK;
-        case G4D_OPT_TENSOR_CORES: ws->tensor_cores = value ? 1 : 0; return G4D_OK;
+        case G4D_OPT_TENSOR_CORES: ws->tensor_cores = value < 0 || value > 2 ? 2 : (int)value; return G4D_OK;
         case G4D_OPT_WARP_CULL: ws->warp_cull = value ? 1 : 0; return G4D_OK;
         case G4D_OPT_TC_DEBUG: ws->tc_debug = value ? 1 : 0; return G4D_OK;
         default: return fail(G4D_ERR_ARG, "unknown option");
@@ -527,7 +541,7 @@ int g4d_deform_forward(G4DWorkspace* ws, const G4DDeformParams* prm, int64_t n, 
     float* trow[G4D_MAX_LEVELS][3] = {};
     if ((rc = setup_trow(ws->trow, trow, prm)) != G4D_OK) return rc;
     G4D_CUDA(launch_collapse_time_rows(*prm, nullptr, time, false, trow, st));
-    const bool use_tc = ws->tensor_cores && tc_deform_supported(make_desc(ws, prm, trow));
+    const bool use_tc = forward_on_tensor_cores(ws, make_desc(ws, prm, trow));
     if (!use_tc && (rc = refresh_packed(ws, prm, st)) != G4D_OK) return rc;     // FP32 transposes: only the FFMA kernels read them
     const DeformDesc d = make_desc(ws, prm, trow);
     GeomBuffers g{};
@@ -740,7 +754,7 @@ int g4d_render_forward(G4DContext* c, const G4DCamera* cam, const G4DDeformParam
     StageTimer* geom_tm = new StageTimer(c, G4D_STAGE_GEOM, st);
     struct Del { StageTimer*& p; ~Del() { delete p; p = nullptr; } } del{geom_tm};
     if (prm) {
-        const bool use_tc = ws->tensor_cores && tc_deform_supported(make_desc(ws, prm, c->trow_ptr));
+        const bool use_tc = forward_on_tensor_cores(ws, make_desc(ws, prm, c->trow_ptr));
         if (!use_tc && (rc = refresh_packed(ws, prm, st)) != G4D_OK) return rc;
         const DeformDesc d = make_desc(ws, prm, c->trow_ptr);
         if (use_tc && (rc = refresh_tc(ws, prm, st)) != G4D_OK) return rc;

@@ -92,11 +92,16 @@ struct TcWeights {
     long long* dbg;                    // optional [grid][12] per-phase cycle counters (debug)
     float* feat;                       // [N][F] fp32 staging of the HexPlane features (deform_features_kernel)
     uint32_t* relu_bits;               // optional [6][N][4]: ReLU sign bits saved for the backward (G4D_RELU_BITS_WORDS)
+    int arith;                         // 1: 3xTF32 images / kernel (g4d_deform_tc.cu), 2: FP16x2 images / kernel (g4d_deform_f16.cu)
+    uint32_t* status;                  // host-mapped word: set to 1 by the FP16x2 kernel when a value left the f16 operand range
 };
 
 size_t tc_packed_floats(const G4DDeformParams& prm);
 cudaError_t launch_tc_pack_weights(const G4DDeformParams& prm, float* blob, TcWeights* out, cudaStream_t st);
 bool tc_deform_supported(const DeformDesc& d);
+// FP16x2 variant (g4d_deform_f16.cu): same blob, same TcWeights, byte images
+cudaError_t launch_f16_pack_weights(const G4DDeformParams& prm, float* blob, TcWeights* out, cudaStream_t st);
+bool f16_deform_supported(const DeformDesc& d);
 
 // tensor-core backward (g4d_deform_tc_bwd.cu): BF16 (hi | lo) weight images in the 8x8-core layout of tc_umma.cuh
 struct TcBwdWeights {

@@ -257,6 +257,220 @@ cudaError_t launch_umma16_selftest(const int cfg[8], const float* A, const float
     return cudaGetLastError();
 }
 
+
+// ---- dispatch-rate microbenchmark ------------------------------------------------------------------------------------------
+// One CTA per launch block: thread 256 issues `ndisp` identical tcgen05.mma (M = 128, N, one K step) back to back and waits
+// for their completion; meanwhile `readers` warps (0..8) hammer OTHER TMEM columns with tcgen05.ld (op 1) or tcgen05.st
+// (op 2).  Answers: what does a dispatch cost as a function of N and of where A lives, and do TMEM<->register transfers
+// share a port with the tensor pipe's operand reads?  Data are zeros; only clocks matter.
+struct RateCfg { int N, a_smem, kind_tf32, readers, reader_op, ndisp, d_cols_apart, pad; };
+
+__global__ void __launch_bounds__(288, 1) umma_rate_kernel(RateCfg c, long long* __restrict__ out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(8) uint64_t bar_mma;
+    __shared__ volatile int done_flag;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 16384 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0u;   // A (4 KB) | B (8 KB)
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, tc::kTmemCols);
+    if (tid == 0) { mbar_init(&bar_mma, 1); fence_barrier_init(); done_flag = 0; }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base_s, 0);    // warp-uniform for the compiler (UTCHMMA operands are uniform registers)
+    const uint32_t lane_base = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+    if (warp < 8) {   // zero the whole TMEM (no NaN patterns in the accumulators)
+        uint32_t z[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) z[j] = 0u;
+        for (uint32_t col = (uint32_t)(warp >> 2) * 256u; col < (uint32_t)(warp >> 2) * 256u + 256u; col += 16) tc::tmem_st16(lane_base + col, z);
+        tc::wait_st();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    long long iters = 0;
+    if (warp == 8) {
+        // converged warp, one elected issuer: operands in uniform registers, no waterfall loop around UTCHMMA
+        uint32_t leader_;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader_));
+        const bool leader = leader_ != 0;
+        {
+            const uint32_t N = (uint32_t)c.N;
+            const uint32_t idesc = c.kind_tf32 ? tc::make_idesc_tf32(128, N) : tc::make_idesc_bf16(128, N, false, false);
+            const uint32_t a_s = tc::smem_addr(smem_raw), b_s = tc::smem_addr(smem_raw + 4096);
+            // one K step: two 128-byte cores per 8-row group -> LBO 128, SBO 256
+            const uint64_t ad = tc::make_smem_desc(a_s, 128u, 256u), bd = tc::make_smem_desc(b_s, 128u, 256u);
+            const uint32_t d0 = tbase, d1 = tbase + (uint32_t)c.d_cols_apart, a_t = tbase + 496u;   // A operand: 8 columns at the very end
+            const long long t0 = clock64();
+            for (int i = 0; i < c.ndisp; ++i) {
+                const uint32_t dd = (i & 1) ? d1 : d0;
+                if (leader) {
+                    if (c.kind_tf32) {
+                        tc::umma_tf32_ts(dd, a_t, bd, idesc, true);
+                    } else if (c.a_smem) {
+                        tc::umma_bf16_ss(dd, ad, bd, idesc, true);
+                    } else {
+                        tc::umma_bf16_ts(dd, a_t, bd, idesc, true);
+                    }
+                }
+            }
+            const long long t1 = clock64();
+            if (leader) tc::umma_commit(&bar_mma);
+            mbar_wait(&bar_mma, 0);
+            const long long t2 = clock64();
+            if (leader) {
+                done_flag = 1;
+                out[blockIdx.x * 4 + 0] = t1 - t0;   // issue loop (blocks when the queue is full)
+                out[blockIdx.x * 4 + 1] = t2 - t0;   // until the last dispatch retired
+            }
+        }
+    } else if (warp < c.readers && c.reader_op) {
+        uint32_t v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;
+        const uint32_t col0 = 256u + (uint32_t)(warp >> 2) * 112u;   // columns [256, 480): never touched by the MMAs
+        while (!done_flag) {
+#pragma unroll 1
+            for (uint32_t k = 0; k < 7; ++k) {
+                if (c.reader_op == 1) { tc::tmem_ld16(lane_base + col0 + k * 16u, v); tc::wait_ld(); }
+                else { tc::tmem_st16(lane_base + col0 + k * 16u, v); tc::wait_st(); }
+                ++iters;
+            }
+        }
+        if ((tid & 31) == 0) atomicAdd(reinterpret_cast<unsigned long long*>(out + blockIdx.x * 4 + 2), (unsigned long long)iters + (v[3] & 1u));
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, tc::kTmemCols);
+}
+
+cudaError_t launch_umma_rate(const int cfg[8], long long* out, int blocks, cudaStream_t st) {
+    RateCfg c{cfg[0], cfg[1], cfg[2], cfg[3], cfg[4], cfg[5], cfg[6], 0};
+    if (c.N < 16 || c.N > 256 || (c.N % 16) || c.readers < 0 || c.readers > 8 || c.ndisp < 1) return cudaErrorInvalidValue;
+    if (c.d_cols_apart + c.N > 256 && c.d_cols_apart != 0) return cudaErrorInvalidValue;
+    const size_t smem = 200 * 1024;    // one CTA per SM
+    cudaError_t e = cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    umma_rate_kernel<<<blocks, 288, smem, st>>>(c, out);
+    return cudaGetLastError();
+}
+
+
+// ---- realistic variant: a stream of [128 x N x 128] GEMMs as the forward issues them ------------------------------------------
+// 3 products x (128 / Kstep) k-steps with the real operand walk: A (hi | lo) in TMEM columns [256, 512) (or in shared memory),
+// B (hi | lo) image [N][128] in the K-major core-matrix layout.  distinct = 0 repeats the first k-step's addresses instead.
+struct GemmRateCfg { int N, a_smem, kind_tf32, readers, reader_op, ngemm, distinct, n_split, swz; };
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {   // K-major SWIZZLE_128B: SBO = 1024 (8 rows x 128 B), LBO unused
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(288, 1) umma_gemm_rate_kernel(GemmRateCfg c, long long* __restrict__ out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(8) uint64_t bar_mma;
+    __shared__ volatile int done_flag;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 196608 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0u;
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, tc::kTmemCols);
+    if (tid == 0) { mbar_init(&bar_mma, 1); fence_barrier_init(); done_flag = 0; }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base_s, 0);
+    const uint32_t lane_base = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+    if (warp < 8) {
+        uint32_t z[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) z[j] = 0u;
+        for (uint32_t col = (uint32_t)(warp >> 2) * 256u; col < (uint32_t)(warp >> 2) * 256u + 256u; col += 16) tc::tmem_st16(lane_base + col, z);
+        tc::wait_st();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    long long iters = 0;
+    if (warp == 8) {
+        uint32_t leader_;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader_));
+        const bool leader = leader_ != 0;
+        {
+            const uint32_t N = (uint32_t)c.N, esz = c.kind_tf32 ? 4u : 2u, kstep = c.kind_tf32 ? 8u : 16u, nks = 128u / kstep;
+            const uint32_t nsplit = c.n_split > 1 ? (uint32_t)c.n_split : 1u, Nd = N / nsplit;       // dispatch width
+            const uint32_t idesc = c.kind_tf32 ? tc::make_idesc_tf32(128, Nd) : tc::make_idesc_bf16(128, Nd, false, false);
+            const uint32_t row_grp = (128u * esz / 16u) * 128u;                 // SBO: one 8-row group = 128 K elements
+            const uint32_t b_img = N * 128u * esz, a_img = 128u * 128u * esz;
+            const uint32_t b_s = tc::smem_addr(smem_raw), a_s = b_s + 2u * b_img;
+            const uint32_t a_cols = 128u * esz / 4u;                            // TMEM columns of one A part
+            const long long t0 = clock64();
+            for (int g = 0; g < c.ngemm; ++g) {
+                for (uint32_t h = 0; h < nsplit; ++h) {
+                    const uint32_t dcol = tbase + h * Nd;
+                    for (uint32_t p = 0; p < 3; ++p) {
+                        for (uint32_t ks = 0; ks < nks; ++ks) {
+                            const uint32_t kk = c.distinct ? ks : 0u;
+                            const uint32_t boff = (p == 1 ? b_img : 0u) + h * (Nd / 8u) * row_grp + kk * 256u;
+                            // SWIZZLE_128B: [N][128 B] K-blocks of 4 k-steps; a k-step advances the start address by 32 B
+                            const uint32_t boff_sw = (p == 1 ? b_img : 0u) + (kk >> 2) * (N * 128u) + h * (Nd / 8u) * 1024u + (kk & 3u) * 32u;
+                            const uint64_t bd = c.swz ? make_smem_desc_sw128(b_s + boff_sw) : tc::make_smem_desc(b_s + boff, 128u, row_grp);
+                            const bool acc = p > 0 || ks > 0;
+                            if (!leader) continue;
+                            if (c.kind_tf32) {
+                                tc::umma_tf32_ts(dcol, tbase + 256u + (p == 0 ? a_cols : 0u) + kk * 8u, bd, idesc, acc);
+                            } else if (c.a_smem) {
+                                const uint64_t ad = c.swz ? make_smem_desc_sw128(a_s + (p == 0 ? a_img : 0u) + (kk >> 2) * (128u * 128u) + (kk & 3u) * 32u)
+                                                          : tc::make_smem_desc(a_s + (p == 0 ? a_img : 0u) + kk * 256u, 128u, row_grp);
+                                tc::umma_bf16_ss(dcol, ad, bd, idesc, acc);
+                            } else {
+                                tc::umma_bf16_ts(dcol, tbase + 256u + (p == 0 ? a_cols : 0u) + kk * 8u, bd, idesc, acc);
+                            }
+                        }
+                    }
+                }
+            }
+            const long long t1 = clock64();
+            if (leader) tc::umma_commit(&bar_mma);
+            mbar_wait(&bar_mma, 0);
+            const long long t2 = clock64();
+            if (leader) {
+                done_flag = 1;
+                out[blockIdx.x * 4 + 0] = t1 - t0;
+                out[blockIdx.x * 4 + 1] = t2 - t0;
+            }
+        }
+    } else if (warp < c.readers && c.reader_op) {
+        uint32_t v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;
+        const uint32_t col0 = 128u + (uint32_t)(warp >> 2) * 48u;   // columns [128, 224): not touched by the MMAs (N <= 128)
+        while (!done_flag) {
+#pragma unroll 1
+            for (uint32_t k = 0; k < 3; ++k) {
+                if (c.reader_op == 1) { tc::tmem_ld16(lane_base + col0 + k * 16u, v); tc::wait_ld(); }
+                else { tc::tmem_st16(lane_base + col0 + k * 16u, v); tc::wait_st(); }
+                ++iters;
+            }
+        }
+        if ((tid & 31) == 0) atomicAdd(reinterpret_cast<unsigned long long*>(out + blockIdx.x * 4 + 2), (unsigned long long)iters + (v[3] & 1u));
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tbase, tc::kTmemCols);
+}
+
+cudaError_t launch_umma_gemm_rate(const int cfg[8], long long* out, int blocks, cudaStream_t st) {
+    GemmRateCfg c{cfg[0], cfg[1], cfg[2], cfg[3], cfg[4], cfg[5], cfg[6] & 1, cfg[7], (cfg[6] >> 1) & 1};
+    if ((c.N != 64 && c.N != 128) || c.readers < 0 || c.readers > 8 || c.ngemm < 1) return cudaErrorInvalidValue;
+    if (c.kind_tf32 && c.a_smem) return cudaErrorInvalidValue;
+    const size_t smem = 196608 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    umma_gemm_rate_kernel<<<blocks, 288, smem, st>>>(c, out);
+    return cudaGetLastError();
+}
+
 }  // namespace g4d
 
 // ---- C entry of the stand-alone self-test library (libg4d_selftest.so; NOT part of libg4d.so / include/g4d.h) -------------
@@ -268,4 +482,20 @@ extern "C" int g4d_selftest_umma(const int* cfg, const float* A, const float* B,
     static float* scratch = nullptr;
     if (!scratch && cudaMalloc(&scratch, (size_t)2 * 128 * 128 * 4 + 256) != cudaSuccess) return -3;
     return g4d::launch_umma_selftest(cfg, A, B, scratch, D, st) == cudaSuccess ? 0 : -1;
+}
+
+// cfg = {N, a_smem, kind_tf32, reader warps, reader op (0 none, 1 tcgen05.ld, 2 tcgen05.st), dispatches, column distance of the
+// two alternating accumulators (0: one accumulator), 0}; out[blocks][4] (device, zeroed by the caller):
+// issue cycles, total cycles, reader iterations (16 columns x 32 lanes each)
+extern "C" int g4d_selftest_umma_rate(const int* cfg, long long* out, int blocks, void* stream) {
+    if (!cfg || !out || blocks < 1) return -2;
+    return g4d::launch_umma_rate(cfg, out, blocks, (cudaStream_t)stream) == cudaSuccess ? 0 : -1;
+}
+
+// cfg = {N (64 | 128), a_smem, kind_tf32, reader warps, reader op, GEMMs, bit 0: distinct addresses (1 = the real operand walk) |
+// bit 1: SWIZZLE_128B operand images instead of the SWIZZLE_NONE core-matrix layout,
+// n_split (dispatch width N / n_split)}; out as above
+extern "C" int g4d_selftest_umma_gemm_rate(const int* cfg, long long* out, int blocks, void* stream) {
+    if (!cfg || !out || blocks < 1) return -2;
+    return g4d::launch_umma_gemm_rate(cfg, out, blocks, (cudaStream_t)stream) == cudaSuccess ? 0 : -1;
 }

@@ -543,21 +543,23 @@ def test_tcgen05_building_blocks_selftest():
         assert float((D.double() - ref).abs().max() / ref.abs().max()) <= 2e-6, (N, K)
 
 
-@pytest.mark.parametrize("net,n", [("small128", 1000), ("dynerf", 5000), ("hypernerf", 3000)])
-def test_tensor_core_mlp_matches_ffma_path(net, n):
-    """The tcgen05 (3xTF32) MLP and the FP32 FFMA MLP are two implementations of the same function."""
+@pytest.mark.parametrize("tcmode", [2, 1])
+@pytest.mark.parametrize("net,n", [("small128", 1000), ("dynerf", 5000), ("hypernerf", 3000), ("dynerf", 40000)])
+def test_tensor_core_mlp_matches_ffma_path(net, n, tcmode):
+    """The tcgen05 MLPs (2: FP16x2 operands, two tiles in flight per SM -- the default; 1: 3xTF32) and the FP32 FFMA MLP are
+    implementations of the same function.  40000 Gaussians = 313 tiles: CTAs with one pair, one and a half, and two pairs."""
     mod = make_module(net, seed=7)
     ins, _ = _deform_inputs(n, 9)
     ws = g4d._lib.Workspace.get(0)
     t = torch.tensor(0.42).repeat(n, 1).cuda()
     try:
         with torch.no_grad():
-            ws.set_option(g4d._lib.OPT_TENSOR_CORES, 1)
+            ws.set_option(g4d._lib.OPT_TENSOR_CORES, tcmode)
             a = [o.clone() for o in mod(*ins, t)]
             ws.set_option(g4d._lib.OPT_TENSOR_CORES, 0)
             b = [o.clone() for o in mod(*ins, t)]
     finally:
-        ws.set_option(g4d._lib.OPT_TENSOR_CORES, 1)
+        ws.set_option(g4d._lib.OPT_TENSOR_CORES, 2)
     for x, y, nm in zip(a, b, ("pts", "scales", "rot", "opacity", "shs")):
         assert float((x - y).abs().max()) <= 5e-6, (nm, float((x - y).abs().max()))
 
@@ -589,8 +591,9 @@ def test_tensor_core_paths_corner_cases_vs_oracle(net, n):
         assert e <= 3 * GRAD_TOL, (k, e)
 
 
+@pytest.mark.parametrize("tcmode", [2, 1])
 @pytest.mark.parametrize("net,n", [("small128", 700), ("dynerf", 21000), ("hypernerf", 40000)])
-def test_tensor_core_backward_matches_ffma_path(net, n):
+def test_tensor_core_backward_matches_ffma_path(net, n, tcmode):
     """BF16x2 tcgen05 backward (dgrad + wgrad kernels) against the FP32 FFMA backward: same gradients for every input
     and every parameter.  n is chosen so that some CTAs own one tile and others two or three (persistent loop).
     The two paths take their ReLU signs from different places (bits saved by the tensor-core forward vs the FFMA kernel's own
@@ -609,7 +612,7 @@ def test_tensor_core_backward_matches_ffma_path(net, n):
     t = torch.tensor(0.27).repeat(n, 1).cuda()
     res = []
     try:
-        for tc in (1, 0):
+        for tc in (tcmode, 0):
             ws.set_option(g4d._lib.OPT_TENSOR_CORES, tc)
             mod.zero_grad(set_to_none=True)
             dev_in = [x.clone().requires_grad_(True) for x in ins]
@@ -618,7 +621,7 @@ def test_tensor_core_backward_matches_ffma_path(net, n):
             res.append(([x.grad.clone() for x in dev_in],
                         {k: p.grad.clone() for k, p in mod.named_parameters() if p.grad is not None}))
     finally:
-        ws.set_option(g4d._lib.OPT_TENSOR_CORES, 1)
+        ws.set_option(g4d._lib.OPT_TENSOR_CORES, 2)
     (gi_tc, gp_tc), (gi_ff, gp_ff) = res
     for a, b, nm in zip(gi_tc, gi_ff, ("xyz", "scales", "rot", "opacity", "shs")):
         e = rel_err(a.cpu().numpy(), b.cpu().numpy())

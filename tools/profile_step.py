@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--stage-times", type=int, default=0)
     ap.add_argument("--tc-debug", type=int, default=0)
     ap.add_argument("--tight-cull", type=int, default=0)
+    ap.add_argument("--tc-mode", type=int, default=2, help="0 FFMA, 1 3xTF32, 2 FP16x2 two-slot (default)")
     a = ap.parse_args()
     g4d = importlib.import_module("4dgaussians_b200")
     synth = importlib.import_module("4dgaussians_b200.synth")
@@ -46,6 +47,7 @@ def main():
         ws.set_option(g4d._lib.OPT_TC_DEBUG, 1)
     if a.tight_cull:
         ws.set_option(g4d._lib.OPT_TIGHT_CULL, 1)
+    ws.set_option(g4d._lib.OPT_TENSOR_CORES, a.tc_mode)
     for i in range(a.iters):
         cam = cams[i % len(cams)]
         if a.backward:
@@ -61,6 +63,9 @@ def main():
             g4d._lib.load().g4d_debug_tc_cycles(ws.handle, arr)
             names = ["inputs", "wait_feat", "L0_mma", "wait_scratch_free", "epi0", "wait_W1", "L1_mma", "wait_W2", "epi_half",
                      "L2_mma", "head_out", "tail"]
+            if a.tc_mode == 2:   # g4d_deform_f16.cu: thread 0 (slot 0) phases, then the MMA thread's blocked / total cycles
+                names = ["E:wait_L0", "E:epi0", "E:wait_head", "E:small_head_epi", "E:sh_hidden_epi", "E:handover", "E:wait_L2+stage_feat",
+                         "F:wait_deltas", "F:sh_out", "F:tail", "mma_warp_blocked", "mma_warp_total"]
             if a.backward:   # the backward kernel ran last and overwrote the slots (g4d_deform_tc_bwd.cu)
                 ph = ["feat+L0", "epi0+dh", "dout", "head_epi", "wait_other", "mma+tail"]
                 names = ["M:" + x for x in ph] + ["G:" + x for x in ph]
