@@ -66,33 +66,6 @@ F16Smem f16_smem_layout(int F, bool sh) {
     return s;
 }
 
-__device__ __forceinline__ bool mbar_test_(void* bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return done != 0;
-}
-// one lane of a CONVERGED warp (elect.sync): the issuer of tcgen05.mma / TMA instructions
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ int b2off_of_(int mask, int h) {
-    int o = 0;
-    for (int i = 0; i < h; ++i)
-        if (mask & (1 << i)) o += head_out(i);
-    return o;
-}
 __device__ __forceinline__ void mbar_arrive_(void* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -359,7 +332,7 @@ deform_f16_kernel(DeformDesc d, TcWeights tw, F16Smem Ls, const CameraDev* __res
         // TMA producer.  The whole warp walks the loop CONVERGED and one elected lane issues: operands then live in uniform
         // registers (a single-lane divergent branch turns every issue into an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop)
         // ============================================================================================================
-        const bool leader = elect_one();
+        const bool leader = tc::elect_one_sync();
         const uint32_t w2b = hsh ? 2u * 48 * 128 * 2 : 0u;
         if (leader) {
             mbar_expect_tx(bars + kBarW0, 2u * 128 * F * 2 + w2b);
@@ -385,7 +358,7 @@ deform_f16_kernel(DeformDesc d, TcWeights tw, F16Smem Ls, const CameraDev* __res
         // MMA issuer (converged walk, one elected issuer).  Order per head: slot 0, slot 1 -- while one slot's GEMM is on the
         // tensor pipe the other slot's threads run the epilogue of theirs.
         // ============================================================================================================
-        const bool leader = elect_one();
+        const bool leader = tc::elect_one_sync();
         long long t_wait = 0, t0 = clock64();
         auto wait = [&](uint64_t* bar, uint32_t parity) {
             if (tw.dbg) { const long long a = clock64(); mbar_wait(bar, parity); t_wait += clock64() - a; }

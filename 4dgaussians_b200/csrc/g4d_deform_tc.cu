@@ -279,7 +279,7 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    const uint32_t tbase = tmem_base_s;
+    const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base_s, 0);    // warp-uniform for the compiler (MMA operands are uniform registers)
     const uint32_t lane_base = tbase + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t sW1 = tc::smem_addr(smem + Ls.w1), sW2 = tc::smem_addr(smem + Ls.w2), sW0 = tc::smem_addr(smem + Ls.w0);
     const bool hsh = d.head_mask & G4D_HEAD_SHS;
@@ -311,7 +311,9 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
     // MMA warp: one lane issues every tcgen05.mma of the CTA, in order, with blocking waits
     // ================================================================================================================
     if (is_mma_warp) {
-        if ((tid & 31) == 0) {
+        // the warp walks the loop converged, one elected lane issues (uniform-register operands, tc_umma.cuh)
+        const bool leader = tc::elect_one_sync();
+        {
             mbar_wait(bar_w0, 0);
             uint32_t used[2] = {0u, 0u}, seen[2] = {0u, 0u};       // GEMMs issued into / epilogues observed on D[b]
             uint32_t ph_feat = 0, ph_a1 = 0, ph_x = 0, q = 0;
@@ -323,8 +325,11 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                 mbar_wait(bar_feat, ph_feat); ph_feat ^= 1u;
                 drain(0); drain(1);
                 tc::fence_after_sync();
-                tc::gemm_3xtf32<F>(tbase + kColD, tbase + kColX, tbase + kColXLo, sW0, sW0 + 128u * F * 4, 128, F, 0, false);
-                tc::umma_commit(bar_l0);
+                if (leader) {
+                    tc::gemm_3xtf32<F>(tbase + kColD, tbase + kColX, tbase + kColXLo, sW0, sW0 + 128u * F * 4, 128, F, 0, false);
+                    tc::umma_commit(bar_l0);
+                }
+                __syncwarp();
                 mbar_wait(bar_a1, ph_a1); ph_a1 ^= 1u;              // epilogue 0 has written A1 and drained D0
                 for (uint32_t k = 0; k < m_heads; ++k, ++q) {
                     const uint32_t b = (k + par0) & 1u;
@@ -334,20 +339,27 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
                         constexpr uint32_t KP = 128 / kW1Parts;
                         mbar_wait(bar_full + j, q & 1u);
                         tc::fence_after_sync();
-                        tc::gemm_3xtf32<(int)KP>(tbase + (b ? kColD1 : kColD), tbase + kColA1Hi + j * KP, tbase + kColA1Lo + j * KP,
-                                                 sW1 + j * kW1PartBytes, sW1 + j * kW1PartBytes + kW1PartBytes / 2, 128, KP, 0, j != 0);
-                        tc::umma_commit(bar_hfree + j);
+                        if (leader) {
+                            tc::gemm_3xtf32<(int)KP>(tbase + (b ? kColD1 : kColD), tbase + kColA1Hi + j * KP, tbase + kColA1Lo + j * KP,
+                                                     sW1 + j * kW1PartBytes, sW1 + j * kW1PartBytes + kW1PartBytes / 2, 128, KP, 0, j != 0);
+                            tc::umma_commit(bar_hfree + j);
+                        }
+                        __syncwarp();
                     }
-                    tc::umma_commit(bar_dfull + b);
+                    if (leader) tc::umma_commit(bar_dfull + b);
+                    __syncwarp();
                     ++used[b];
                     if (hsh && k + 1 == m_heads) {
                         // SH head: two layer-2 partials D2 (+)= a2_half * W2[:, 64hh : 64hh+64]^T (D2 = D0 columns [0, 48))
                         for (int hh = 0; hh < 2; ++hh) {
                             mbar_wait(bar_x, ph_x); ph_x ^= 1u;
                             tc::fence_after_sync();
-                            tc::gemm_3xtf32<64>(tbase + kColD, tbase + kColX, tbase + kColXLo, sW2, sW2 + 48u * 128 * 4, 48, 128,
-                                                (uint32_t)(hh * 16), hh == 1);
-                            tc::umma_commit(bar_l2);
+                            if (leader) {
+                                tc::gemm_3xtf32<64>(tbase + kColD, tbase + kColX, tbase + kColXLo, sW2, sW2 + 48u * 128 * 4, 48, 128,
+                                                    (uint32_t)(hh * 16), hh == 1);
+                                tc::umma_commit(bar_l2);
+                            }
+                            __syncwarp();
                         }
                     }
                 }

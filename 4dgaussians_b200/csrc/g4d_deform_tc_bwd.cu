@@ -209,7 +209,8 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
     const int tid = threadIdx.x, warp = tid >> 5;
     const int row = tid & 127;
     const bool is_m = tid >= 128;
-    const bool issuer = tid == 128;
+    const bool issuer = tid == 128;          // TMA copies
+    const bool issue_warp = warp == 4;       // tcgen05.mma: the whole warp arrives converged, one elected lane issues (tc_umma.cuh)
     const int64_t ntiles = (n + 127) / 128;
     for (int i = tid; i < (int)(sizeof(DeformDesc) / 4); i += 256)
         reinterpret_cast<uint32_t*>(&sd)[i] = reinterpret_cast<const uint32_t*>(&d)[i];
@@ -240,7 +241,7 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    const uint32_t tbase = tmem_base_s;
+    const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base_s, 0);    // warp-uniform for the compiler (MMA operands are uniform registers)
     const uint32_t lane_base = tbase + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t sW0 = tc::smem_addr(smem + Ls.w0), sW1 = tc::smem_addr(smem + Ls.w1);
     float amax[3], ascale[3];
@@ -359,10 +360,14 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
         // ---- layer 0 recompute: D = feat W0^T
         if (is_m) {
             bar_sync(kBarFeat, 256);
-            if (issuer) {
+            if (issue_warp) {
+                const bool leader = tc::elect_one_sync();
                 tc::fence_after_sync();
-                gemm_bf16x2_ts<F>(tbase + kD, tbase + kDZ, tbase + kDZLo, sW0, sW0 + 128u * F * 2, 128, F, false, false);
-                tc::umma_commit(bar_l0);
+                if (leader) {
+                    gemm_bf16x2_ts<F>(tbase + kD, tbase + kDZ, tbase + kDZLo, sW0, sW0 + 128u * F * 2, 128, F, false, false);
+                    tc::umma_commit(bar_l0);
+                }
+                __syncwarp();
             }
         }
         mbar_wait(bar_l0, ph_l0); ph_l0 ^= 1u;
@@ -405,11 +410,15 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
             // ---- first layer-1 GEMM of the tile
             const int buf = (int)(seq & 1);
             if (buf == 0) { mbar_wait(bar_w1, ph_w1_0); ph_w1_0 ^= 1u; } else { mbar_wait(bar_w1 + 1, ph_w1_1); ph_w1_1 ^= 1u; }
-            if (issuer) {
+            if (issue_warp) {
+                const bool leader = tc::elect_one_sync();
                 tc::fence_after_sync();
                 const uint32_t w = sW1 + buf * 2u * kImg128;
-                gemm_bf16x2_ts<128>(tbase + kD, tbase + kA1, tbase + kA1Lo, w, w + kImg128, 128, 128, false, false);
-                tc::umma_commit(bar_l1);
+                if (leader) {
+                    gemm_bf16x2_ts<128>(tbase + kD, tbase + kA1, tbase + kA1Lo, w, w + kImg128, 128, 128, false, false);
+                    tc::umma_commit(bar_l1);
+                }
+                __syncwarp();
             }
         }
 
@@ -521,21 +530,29 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
             bar_sync(kBarE, 256);
             G4D_CYC(4);   // wait for the other group
             // ---- d(a1) += dz W1 (W1 image read MN-major), then the next head's layer 1 straight behind it
-            if (issuer) {
+            if (issue_warp) {
+                const bool leader = tc::elect_one_sync();
                 tc::fence_after_sync();
                 const uint32_t w = sW1 + buf * 2u * kImg128;
-                gemm_bf16x2_ts<128>(tbase + kDA1, tbase + kDZ, tbase + kDZLo, w, w + kImg128, 128, 128, true, da1_started);
-                tc::umma_commit(bar_da1);
+                if (leader) {
+                    gemm_bf16x2_ts<128>(tbase + kDA1, tbase + kDZ, tbase + kDZLo, w, w + kImg128, 128, 128, true, da1_started);
+                    tc::umma_commit(bar_da1);
+                }
+                __syncwarp();
             }
             da1_started = true;
             ++seq;
             if (next_h >= 0 && is_m) {
                 const int nbuf = (int)(seq & 1);
                 if (nbuf == 0) { mbar_wait(bar_w1, ph_w1_0); ph_w1_0 ^= 1u; } else { mbar_wait(bar_w1 + 1, ph_w1_1); ph_w1_1 ^= 1u; }
-                if (issuer) {
+                if (issue_warp) {
+                    const bool leader = tc::elect_one_sync();
                     const uint32_t w = sW1 + nbuf * 2u * kImg128;
-                    gemm_bf16x2_ts<128>(tbase + kD, tbase + kA1, tbase + kA1Lo, w, w + kImg128, 128, 128, false, false);
-                    tc::umma_commit(bar_l1);
+                    if (leader) {
+                        gemm_bf16x2_ts<128>(tbase + kD, tbase + kA1, tbase + kA1Lo, w, w + kImg128, 128, 128, false, false);
+                        tc::umma_commit(bar_l1);
+                    }
+                    __syncwarp();
                 }
             }
             // the dz W1 chain has retired: DZ may be overwritten, and W1 buffer `buf` takes the pair after next
@@ -572,10 +589,14 @@ deform_tc_bwd_dgrad_kernel(BwdADesc bd, BwdSmemA Ls, float time, int64_t n, cons
         }
         if (is_m) {
             // ---- d(feat) = dh W0  (W0 image read MN-major: rows = hidden j = K, cols = feature f = N) -> [N][F] fp32
-            if (issuer) {
+            if (issue_warp) {
+                const bool leader = tc::elect_one_sync();
                 tc::fence_after_sync();
-                gemm_bf16x2_ts<128>(tbase + kD, tbase + kDZ, tbase + kDZLo, sW0, sW0 + 128u * F * 2, F, F, true, false);
-                tc::umma_commit(bar_g6);
+                if (leader) {
+                    gemm_bf16x2_ts<128>(tbase + kD, tbase + kDZ, tbase + kDZLo, sW0, sW0 + 128u * F * 2, F, F, true, false);
+                    tc::umma_commit(bar_g6);
+                }
+                __syncwarp();
             }
             mbar_wait(bar_g6, ph_g6); ph_g6 ^= 1u;
             tc::fence_after_sync();
@@ -774,7 +795,7 @@ __global__ void __launch_bounds__(128, 1) deform_tc_bwd_wgrad_kernel(BwdBDesc b)
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    const uint32_t tbase = tmem_base_s;
+    const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base_s, 0);    // warp-uniform for the compiler
     const uint32_t lane_base = tbase + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t colW = 0, colW2 = 128, colB = 192;   // accumulators: dW (128 or F cols) | dW2^T (kp16) | bias (16)
     const int64_t per = (b.ntiles + nch - 1) / nch;
@@ -783,7 +804,9 @@ __global__ void __launch_bounds__(128, 1) deform_tc_bwd_wgrad_kernel(BwdBDesc b)
     const uint32_t dp = 128u * kp16 * 2u;                              // ... of DOUT
     const int64_t nwork = t1 > t0 ? 2 * (t1 - t0) : 0;
     bool started = false;
-    if (tid == 0 && nwork > 0) {
+    if (warp == 0 && nwork > 0) {
+        // warp 0 walks the work list converged; one elected lane issues the TMA copies and the MMAs (tc_umma.cuh)
+        const bool leader = tc::elect_one_sync();
         auto load = [&](int64_t w) {
             const int st = (int)(w & 1), hf = (int)(w & 1);             // work item w = 2 (t - t0) + hf uses stage w & 1
             const int64_t t = t0 + (w >> 1);
@@ -807,29 +830,35 @@ __global__ void __launch_bounds__(128, 1) deform_tc_bwd_wgrad_kernel(BwdBDesc b)
             }
         };
         uint32_t ph_ld[2] = {0u, 0u}, ph_mma[2] = {0u, 0u};
-        load(0);
+        if (leader) load(0);
+        __syncwarp();
         for (int64_t w = 0; w < nwork; ++w) {
             const int st = (int)(w & 1);
             if (w + 1 < nwork) {
                 const int ns = st ^ 1;
                 if (w >= 1) { mbar_wait(&bar_mma[ns], ph_mma[ns]); ph_mma[ns] ^= 1u; }   // MMAs of work item w-1 have released stage ns
-                load(w + 1);
+                if (leader) load(w + 1);
+                __syncwarp();
             }
             mbar_wait(&bar_ld[st], ph_ld[st]); ph_ld[st] ^= 1u;
             tc::fence_after_sync();
             const uint32_t base = tc::smem_addr(smem + st * kStage), ones = tc::smem_addr(sOnes);
             const uint32_t x = base, y = base + 2 * kHalf128, a2 = base + 4 * kHalf128, dd = base + 6 * kHalf128;
-            if (layer0) {
-                gemm_bf16x2_ss_mn<64>(tbase + colW, x, x + kHalf128, 128, y, y + yp / 2, (uint32_t)b.F, (uint32_t)b.F, started, false);
-            } else {
-                gemm_bf16x2_ss_mn<64>(tbase + colW, x, x + kHalf128, 128, y, y + kHalf128, 128, 128, started, false);
-                gemm_bf16x2_ss_mn<64>(tbase + colW2, a2, a2 + kHalf128, 128, dd, dd + dp / 2, (uint32_t)kp16, (uint32_t)kp16, started, false);
+            if (leader) {
+                if (layer0) {
+                    gemm_bf16x2_ss_mn<64>(tbase + colW, x, x + kHalf128, 128, y, y + yp / 2, (uint32_t)b.F, (uint32_t)b.F, started, false);
+                } else {
+                    gemm_bf16x2_ss_mn<64>(tbase + colW, x, x + kHalf128, 128, y, y + kHalf128, 128, 128, started, false);
+                    gemm_bf16x2_ss_mn<64>(tbase + colW2, a2, a2 + kHalf128, 128, dd, dd + dp / 2, (uint32_t)kp16, (uint32_t)kp16, started, false);
+                }
+                gemm_bf16x2_ss_mn<64>(tbase + colB, x, x + kHalf128, 128, ones, ones, 16, 16, started, true);
+                tc::umma_commit(&bar_mma[st]);
             }
-            gemm_bf16x2_ss_mn<64>(tbase + colB, x, x + kHalf128, 128, ones, ones, 16, 16, started, true);
-            tc::umma_commit(&bar_mma[st]);
+            __syncwarp();
             started = true;
         }
-        tc::umma_commit(&bar_done);        // covers every MMA issued above
+        if (leader) tc::umma_commit(&bar_done);        // covers every MMA issued above
+        __syncwarp();
         mbar_wait(&bar_done, 0);
     }
     started = nwork > 0;

@@ -55,6 +55,22 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
                  "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
 
+// ---- issuing tcgen05.mma ---------------------------------------------------------------------------------------------------
+// UTCHMMA takes every operand from UNIFORM registers.  Issued from a single-lane divergent branch (`if (tid == X)`) the compiler
+// wraps each instruction in a waterfall loop (ELECT / R2UR.BROADCAST / BRA.U.ANY, ~150 cycles per MMA, measured with
+// tools/umma_rate.py); issued by an elected lane of a CONVERGED warp the operands stay in uniform registers and the issue rate
+// is the tensor pipe's (64 cycles per 128x128x8 tf32, 76 per 128x128x16 f16 dispatch).  elect.sync with the full member mask
+// also tells the compiler that the warp is converged here.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- 3xTF32 split ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t tf32_rna(float x) {
     uint32_t r;
