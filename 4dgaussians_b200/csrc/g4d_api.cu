@@ -58,6 +58,7 @@ struct G4DWorkspace {
     int stage_timing = 0;
     int tensor_cores = 2;      // 0: FP32 FFMA kernels, 1: tcgen05 3xTF32, 2 (default): tcgen05 FP16x2, two tiles in flight
     int warp_cull = 1;
+    int keep_deformed = 0;
     DevBuf tc_packed;
     TcWeights tcw{};
     DevBuf tc_bwd_packed, tc_feat;
@@ -88,7 +89,7 @@ struct G4DContext {
     int64_t R = 0, capacity = 0;
     const void* bin_ctl = nullptr;    // device BinCtl of the last forward
     bool learned = false;             // R of an earlier exact forward is known (no-sync mode needs a learnt capacity)
-    bool has_forward = false, is_fused = false, fused_sh = false, deformed = false;
+    bool has_forward = false, is_fused = false, fused_sh = false, deformed = false, fo_valid = false;
     GeomBuffers g{};
     BinBuffers b{};
     ImageBuffers im{};
@@ -494,6 +495,7 @@ int g4d_workspace_set_option(G4DWorkspace* ws, int option, int64_t value) {
         case G4D_OPT_TENSOR_CORES: ws->tensor_cores = value < 0 || value > 2 ? 2 : (int)value; return G4D_OK;
         case G4D_OPT_WARP_CULL: ws->warp_cull = value ? 1 : 0; return G4D_OK;
         case G4D_OPT_TC_DEBUG: ws->tc_debug = value ? 1 : 0; return G4D_OK;
+        case G4D_OPT_KEEP_DEFORMED: ws->keep_deformed = value ? 1 : 0; return G4D_OK;
         default: return fail(G4D_ERR_ARG, "unknown option");
     }
 }
@@ -669,7 +671,7 @@ int64_t g4d_context_read(G4DContext* c, int which, void* host_dst, int64_t bytes
             for (size_t i = 0; i < N && ok; ++i) for (int ch = 0; ch < 3; ++ch) outv[i * 3 + ch] = (tmp[i] >> ch) & 1;
         } break;
         case G4D_BUF_DEFORMED: {
-            if (!c->is_fused) return fail(G4D_ERR_STATE, "G4D_BUF_DEFORMED needs a fused forward");
+            if (!c->is_fused || !c->fo_valid) return fail(G4D_ERR_STATE, "G4D_BUF_DEFORMED needs a fused forward that kept its tensors (grad-enabled, or G4D_OPT_KEEP_DEFORMED)");
             outv.resize(N * 44);
             std::vector<float> m(N * 3), s(N * 3), r(N * 4), o(N);
             ok = N == 0 || (cudaMemcpy(m.data(), c->fo.means3D, N * 12, cudaMemcpyDeviceToHost) == cudaSuccess &&
@@ -683,7 +685,7 @@ int64_t g4d_context_read(G4DContext* c, int which, void* host_dst, int64_t bytes
             }
         } break;
         case G4D_BUF_DEFORMED_SHS: {
-            if (!c->is_fused || !c->fused_sh || !c->fo.shs) return fail(G4D_ERR_STATE, "G4D_BUF_DEFORMED_SHS needs a fused forward with the SHS head active");
+            if (!c->is_fused || !c->fused_sh || !c->fo.shs || !c->fo_valid) return fail(G4D_ERR_STATE, "G4D_BUF_DEFORMED_SHS needs a fused forward with the SHS head active");
             ok = pull(c->fo.shs, N * 192); outv = tmp; outv.resize(N * 192);
         } break;
         case G4D_BUF_BIN_PHASES: {
@@ -743,6 +745,9 @@ int g4d_render_forward(G4DContext* c, const G4DCamera* cam, const G4DDeformParam
     reset_stage_flags(c, 0, G4D_STAGE_COUNT - 1);
     const float* shs = g->features_rest ? nullptr : g->features_dc;
     const float* dc = g->features_rest ? g->features_dc : nullptr;
+    // a no-grad render needs none of the saved tensors: skip their stores (48 B + 192 B of deformed SH per Gaussian)
+    c->fo_valid = !(cam->debug & G4D_CAM_NO_GRAD) || ws->keep_deformed;
+    const FusedOutputs fo_arg = c->fo_valid ? c->fo : FusedOutputs{};
     {
         StageTimer tm(c, G4D_STAGE_PREP, st);
         G4D_CUDA(launch_pack_camera(*cam, dcam, st));
@@ -767,11 +772,11 @@ int g4d_render_forward(G4DContext* c, const G4DCamera* cam, const G4DDeformParam
             ws->tcw.feat = c->feat.as<float>();
         }
         G4D_CUDA(launch_deform(d, 1, dcam, cam->time, false, n, g->xyz, g->scaling, g->rotation, g->opacity, shs, dc,
-                               g->features_rest, nullptr, nullptr, nullptr, nullptr, nullptr, c->g, c->fo, out_radii,
+                               g->features_rest, nullptr, nullptr, nullptr, nullptr, nullptr, c->g, fo_arg, out_radii,
                                ws->sm_count, st, use_tc ? &ws->tcw : nullptr));
     } else {
         G4D_CUDA(launch_activate_preprocess(dcam, n, g->xyz, g->scaling, g->rotation, g->opacity, shs, dc, g->features_rest,
-                                            c->g, c->fo, out_radii, st));
+                                            c->g, fo_arg, out_radii, st));
     }
     delete geom_tm; geom_tm = nullptr;
     if ((rc = debug_sync(cam, st, "deform+preprocess")) != G4D_OK) return rc;
@@ -785,6 +790,7 @@ int g4d_render_backward(G4DContext* c, const G4DCamera* cam, const G4DDeformPara
                         const G4DGaussians* g, const float* dL_dcolor, G4DGaussianGrads* gg, void* stream) {
     if (!c) return fail(G4D_ERR_ARG, "context is NULL");
     if (!c->has_forward || !c->is_fused || !g || c->n != g->n) return fail(G4D_ERR_STATE, "g4d_render_backward needs the matching g4d_render_forward on this context");
+    if (!c->fo_valid) return fail(G4D_ERR_STATE, "g4d_render_backward after a G4D_CAM_NO_GRAD forward: nothing was saved for it");
     if ((prm != nullptr) != c->deformed) return fail(G4D_ERR_STATE, "deform params differ from the forward's");
     int rc = check_camera(cam);
     if (rc != G4D_OK) return rc;

@@ -139,13 +139,9 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
         n = xyz.shape[0]
         time = torch.tensor(t, device=xyz.device, dtype=torch.float32).repeat(n, 1)
         m3, sc, rot, op, shs = module(xyz, pc._scaling, pc._rotation, pc._opacity, pc.get_features, time)
-        rasterizer = GaussianRasterizer(raster_settings=_cuda_settings(rs, xyz.device))
+        rasterizer = GaussianRasterizer(raster_settings=rs)
         rendered_image, radii, depth = rasterizer(means3D=m3, means2D=screenspace_points, shs=shs, colors_precomp=None,
                                                   opacities=pc.opacity_activation(op), scales=pc.scaling_activation(sc),
                                                   rotations=pc.rotation_activation(rot), cov3D_precomp=None)
     return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
             "radii": radii, "depth": depth}
-
-
-def _cuda_settings(rs: GaussianRasterizationSettings, device) -> GaussianRasterizationSettings:
-    return rs

@@ -222,6 +222,8 @@ enum { G4D_OPT_SYNC_MODE = 1,  /* 1 (default): size the instance buffer exactly 
        G4D_OPT_TENSOR_CORES = 5, /* 1 (default): run the deformation MLP on tcgen05 tensor cores (3xTF32) when the
                                    configuration allows (net_width 128, C in {16,32}, F <= 64); 0: FP32 FFMA kernels */
        G4D_OPT_TC_DEBUG = 6,     /* 1: the tensor-core kernel records per-phase cycle counters (g4d_debug_tc_cycles) */
+       G4D_OPT_KEEP_DEFORMED = 8, /* 1: a no-grad fused forward (G4D_CAM_NO_GRAD) still stores the deformed + activated tensors
+                                   * (G4D_BUF_DEFORMED / _SHS reads); default 0: it skips those 48-240 B / Gaussian of writes */
        G4D_OPT_WARP_CULL = 7     /* 1 (default): the blend kernels skip, per warp, instances that cannot reach alpha >= 1/255
                                   *    on any pixel of the warp's 16 x 4 strip (results unchanged); 0 = test every pixel */ };
 int g4d_workspace_set_option(G4DWorkspace *ws, int option, int64_t value);

@@ -185,9 +185,13 @@ def test_full_size_fused_forward_vs_oracle(wl):
     bg = torch.tensor(w["bg"], dtype=torch.float32, device="cuda")
     ws = g4d._lib.Workspace.get(0)
     ws._free_contexts.clear()
-    with torch.no_grad():
-        out = g4d.render(cam, pc, _Pipe(), bg)
-    torch.cuda.synchronize()
+    ws.set_option(g4d._lib.OPT_KEEP_DEFORMED, 1)                 # (a no-grad render skips the stores of these tensors by default)
+    try:
+        with torch.no_grad():
+            out = g4d.render(cam, pc, _Pipe(), bg)
+        torch.cuda.synchronize()
+    finally:
+        ws.set_option(g4d._lib.OPT_KEEP_DEFORMED, 0)
     ctx = ws._free_contexts[-1]
     dfm = ctx.read("deformed")                                   # [N,11] what the fused kernel handed to its projection stage
     has_sh = not mod.args.no_dshs

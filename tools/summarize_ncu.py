@@ -10,7 +10,7 @@ import sys
 
 WANT = ["Duration", "DRAM Throughput", "Memory Throughput", "L2 Cache Throughput", "Compute (SM) Throughput", "Registers Per Thread",
         "Achieved Occupancy", "Executed Ipc Active", "Issue Slots Busy", "Dynamic Shared Memory Per Block"]
-STAGE = {"deform_features_kernel": "geom", "deform_tc_kernel": "geom", "deform_kernel": "geom", "bin_sort_kernel": "binning",
+STAGE = {"deform_features_kernel": "geom", "deform_tc_kernel": "geom", "deform_f16_kernel": "geom", "deform_kernel": "geom", "bin_sort_kernel": "binning",
          "bin_place_kernel": "binning", "bin_fix_kernel": "binning", "blend_forward_kernel": "blend"}
 
 
