@@ -95,10 +95,14 @@ struct G4DContext {
     ImageBuffers im{};
     FusedOutputs fo{};
     float* trow_ptr[G4D_MAX_LEVELS][3] = {};
-    uint32_t* h_r = nullptr;          // pinned: instance count of the last forward (no-sync mode)
-    cudaEvent_t ev_r = nullptr;
-    bool pending = false;             // an asynchronous R read-back has not been checked yet
-    int64_t used_capacity = 0;        // capacity the pending forward ran with
+    // no-sync mode: the instance count of a forward is read back asynchronously into one of TWO slots (pinned word + event), used
+    // alternately: when forward v starts, the slot it is about to reuse holds forward v-2 (complete unless the host is two views
+    // ahead of the device -- then it waits, which bounds the run-ahead), the other one forward v-1 (looked at only if it is done)
+    uint32_t* h_r = nullptr;          // pinned: [slot] instance count
+    cudaEvent_t ev_r[2] = {nullptr, nullptr};
+    bool pending[2] = {false, false}; // the slot's read-back has not been checked yet
+    int64_t used_capacity[2] = {0, 0};   // capacity the slot's forward ran with
+    int slot = 0;                     // slot the NEXT no-sync forward uses
     cudaEvent_t ev[2 * G4D_STAGE_COUNT] = {};
     bool ev_used[G4D_STAGE_COUNT] = {};
     bool ev_created = false;
@@ -330,18 +334,27 @@ int debug_sync(const G4DCamera* cam, cudaStream_t st, const char* stage) {
 
 // no-sync mode: the previous forward's instance count arrives asynchronously; look at it before reusing the context
 int check_pending(G4DContext* c) {
-    if (!c->pending) return G4D_OK;
-    G4D_CUDA(cudaEventSynchronize(c->ev_r));
-    c->pending = false;
-    c->R = (int64_t)c->h_r[0];
-    if (c->R > c->used_capacity) {
-        const int64_t need = c->R + c->R / 2;
-        if (need > c->ws->min_capacity) c->ws->min_capacity = need;
-        c->has_forward = false;
-        char msg[160];
-        snprintf(msg, sizeof(msg), "%lld tile instances did not fit the capacity of %lld used by the previous no-sync forward; its image is incomplete",
-                 (long long)c->R, (long long)c->used_capacity);
-        return fail(G4D_ERR_OVERFLOW, "instance buffer overflow", msg);
+    for (int k = 0; k < 2; ++k) {
+        const int s = c->slot ^ k;          // k = 0: the slot about to be reused (must be resolved), k = 1: the newer one
+        if (!c->pending[s]) continue;
+        if (k == 0) {
+            G4D_CUDA(cudaEventSynchronize(c->ev_r[s]));
+        } else {
+            const cudaError_t q = cudaEventQuery(c->ev_r[s]);
+            if (q == cudaErrorNotReady) { (void)cudaGetLastError(); continue; }
+            G4D_CUDA(q);
+        }
+        c->pending[s] = false;
+        c->R = (int64_t)c->h_r[s];
+        if (c->R > c->used_capacity[s]) {
+            const int64_t need = c->R + c->R / 2;
+            if (need > c->ws->min_capacity) c->ws->min_capacity = need;
+            c->has_forward = false;
+            char msg[160];
+            snprintf(msg, sizeof(msg), "%lld tile instances did not fit the capacity of %lld used by an earlier no-sync forward; its image is incomplete",
+                     (long long)c->R, (long long)c->used_capacity[s]);
+            return fail(G4D_ERR_OVERFLOW, "instance buffer overflow", msg);
+        }
     }
     return G4D_OK;
 }
@@ -377,9 +390,11 @@ int bin_and_blend(G4DContext* c, const G4DCamera* cam, int64_t n, float* out_col
         } else {
             // capacity-bounded, no host round trip: the placement clamps to the capacity, R arrives asynchronously and an
             // overflow is reported by the next call on this context
-            G4D_CUDA(cudaMemcpyAsync(c->h_r, &lay.ctl->R, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            G4D_CUDA(cudaEventRecord(c->ev_r, st));
-            c->pending = true; c->used_capacity = c->capacity;
+            const int sl = c->slot;
+            c->slot ^= 1;
+            G4D_CUDA(cudaMemcpyAsync(c->h_r + sl, &lay.ctl->R, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            G4D_CUDA(cudaEventRecord(c->ev_r[sl], st));
+            c->pending[sl] = true; c->used_capacity[sl] = c->capacity;
         }
         if ((rc = debug_sync(cam, st, "bin_sort")) != G4D_OK) return rc;
         {
@@ -468,7 +483,8 @@ G4DContext* g4d_context_create(G4DWorkspace* ws) {
     G4DContext* c = new G4DContext();
     c->ws = ws;
     if (c->cam.ensure(sizeof(CameraDev)) != cudaSuccess) { delete c; fail(G4D_ERR_NOMEM, "camera buffer"); return nullptr; }
-    if (cudaMallocHost((void**)&c->h_r, 64) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_r, cudaEventDisableTiming) != cudaSuccess) {
+    if (cudaMallocHost((void**)&c->h_r, 64) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_r[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_r[1], cudaEventDisableTiming) != cudaSuccess) {
         delete c; fail(G4D_ERR_NOMEM, "pinned scalar / event"); return nullptr;
     }
     return c;
@@ -478,7 +494,7 @@ void g4d_context_destroy(G4DContext* c) {
     if (!c) return;
     cudaSetDevice(c->ws->device);
     if (c->ev_created) for (int i = 0; i < 2 * G4D_STAGE_COUNT; ++i) cudaEventDestroy(c->ev[i]);
-    if (c->ev_r) cudaEventDestroy(c->ev_r);
+    for (int i = 0; i < 2; ++i) if (c->ev_r[i]) cudaEventDestroy(c->ev_r[i]);
     if (c->h_r) cudaFreeHost(c->h_r);
     c->cam.release(); c->geom.release(); c->bin.release(); c->binaux.release(); c->img.release(); c->fused.release(); c->gscratch.release(); c->gdeform.release(); c->relu.release(); c->feat.release();
     c->trow.release();

@@ -54,7 +54,9 @@ struct CameraDev {
     uint32_t depth_min, depth_max;   // bits of the smallest / largest view-space depth among the visible Gaussians of this
                                      // forward (reset by pack_camera, RED.MIN / RED.MAX by the projection stage, read by bin_sort)
     float tanfovx, tanfovy, scale_modifier, time;
-    float focal_x, focal_y, pad2, pad3;
+    float focal_x, focal_y;
+    uint32_t grid_bar;               // arrival counter of bin_sort_kernel's grid-wide barriers (reset by pack_camera every forward)
+    uint32_t pad3;
     float view[16];
     float proj[16];
     float campos[4];

@@ -31,7 +31,7 @@ __global__ void pack_camera_kernel(G4DCamera c, CameraDev* dst) {
         dst->tanfovx = c.tanfovx; dst->tanfovy = c.tanfovy; dst->scale_modifier = c.scale_modifier; dst->time = c.time;
         dst->focal_x = (float)c.image_width / (2.f * c.tanfovx);
         dst->focal_y = (float)c.image_height / (2.f * c.tanfovy);
-        dst->pad2 = dst->pad3 = 0.f;
+        dst->grid_bar = 0u; dst->pad3 = 0u;
     }
 }
 

@@ -33,6 +33,7 @@ struct BinSortArgs {
     int64_t n;
     const float2* rec2; const uint32_t* tiles_touched; const uint2* rect; const float4* rec0; const float4* rec1;
     const uint32_t* depth_range;   // [2] min / max depth bits of the visible Gaussians (written by the projection stage)
+    uint32_t* grid_bar;            // arrival counter of the grid-wide barriers (CameraDev.grid_bar, zero at launch)
     uint32_t *kA, *vA, *kB, *vB;   // [N] ping-pong buffers of the depth sort
     uint32_t* perm;                // [N] out: visible Gaussians in depth order
     uint32_t* H;                   // [chunks][256] digit histograms of the current pass

@@ -125,6 +125,8 @@ class deform_network(nn.Module):
         self._version_seen = None
         self._param_version = 0
         self._dirty = False
+        self._flat_cache = None          # the Parameter objects in C-ABI order (nn.Module container indexing is slow: ~90 calls per render)
+        self._cparams_cache = None       # (key, struct, keep): the ctypes struct is rebuilt only when a pointer / the head mask changes
 
     # ---- reference surface -------------------------------------------------------------------------
     @property
@@ -161,14 +163,23 @@ class deform_network(nn.Module):
                 | (0 if a.no_do else _lib.HEAD_OPACITY) | (0 if a.no_dshs else _lib.HEAD_SHS))
 
     def flat_parameters(self) -> List[torch.Tensor]:
-        """planes (level-major), w0, b0, then (w1, b1, w2, b2) per head -- the order _DeformFunction uses."""
-        net = self.deformation_net
-        out = [p for lvl in net.grid.grids for p in lvl]
-        out += [net.feature_out[0].weight, net.feature_out[0].bias]
-        for name in _HEADS:
-            seq = getattr(net, name)
-            out += [seq[1].weight, seq[1].bias, seq[3].weight, seq[3].bias]
-        return out
+        """planes (level-major), w0, b0, then (w1, b1, w2, b2) per head -- the order _DeformFunction uses.
+        The list of Parameter OBJECTS is cached (they survive .to() / load_state_dict / optimizer steps, which all write in
+        place); ``invalidate_cache()`` drops it after module surgery."""
+        if self._flat_cache is None:
+            net = self.deformation_net
+            out = [p for lvl in net.grid.grids for p in lvl]
+            out += [net.feature_out[0].weight, net.feature_out[0].bias]
+            for name in _HEADS:
+                seq = getattr(net, name)
+                out += [seq[1].weight, seq[1].bias, seq[3].weight, seq[3].bias]
+            self._flat_cache = out
+        return list(self._flat_cache)
+
+    def _apply(self, fn, *a, **k):       # .cuda() / .float() / .to(): pointers change, and so may the Parameter objects
+        self._flat_cache = None
+        self._cparams_cache = None
+        return super()._apply(fn, *a, **k)
 
     def _ensure_layout(self):
         for lvl in self.deformation_net.grid.grids:
@@ -200,9 +211,27 @@ class deform_network(nn.Module):
         """Call after changing weights in a way autograd's version counters cannot see (``p.data.copy_``, a custom fused
         optimizer) while rendering under ``torch.no_grad()``; training forwards refresh the images on their own."""
         self._version_seen = None
+        self._flat_cache = None
+        self._cparams_cache = None
 
     def c_params(self, keep: list, fresh: bool = False) -> _lib.DeformParams:
         self._ensure_layout()
+        net = self.deformation_net
+        key = (self.head_mask(), net.grid.aabb.data_ptr()) + tuple(p.data_ptr() for p in self.flat_parameters())
+        if self._cparams_cache is not None and self._cparams_cache[0] == key:
+            _, prm0, keep0 = self._cparams_cache
+            prm = _lib.DeformParams.from_buffer_copy(prm0)       # callers keep their struct (its version) for the backward
+            keep.extend(keep0)
+            prm.version = self.param_version(fresh)
+            return prm
+        keep_local = []
+        prm = self._build_c_params(keep_local)
+        self._cparams_cache = (key, _lib.DeformParams.from_buffer_copy(prm), keep_local)
+        keep.extend(keep_local)
+        prm.version = self.param_version(fresh)
+        return prm
+
+    def _build_c_params(self, keep: list) -> _lib.DeformParams:
         net = self.deformation_net
         kc = net.grid.grid_config[0]
         prm = _lib.DeformParams()
@@ -231,7 +260,6 @@ class deform_network(nn.Module):
             seq = getattr(net, name)
             prm.w1[h], prm.b1[h] = seq[1].weight.data_ptr(), seq[1].bias.data_ptr()
             prm.w2[h], prm.b2[h] = seq[3].weight.data_ptr(), seq[3].bias.data_ptr()
-        prm.version = self.param_version(fresh)
         return prm
 
     def alloc_grads(self) -> List[torch.Tensor]:

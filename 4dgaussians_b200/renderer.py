@@ -38,38 +38,45 @@ def settings_from_camera(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=
     return rs, t
 
 
+def _fused_forward(module: Optional[deform_network], rs, t, needs_bwd, xyz, scaling, rotation, opacity, f_dc, f_rest):
+    """One g4d_render_forward call.  Shared by the autograd Function and by the no-grad fast path of render()."""
+    lib = _lib.load()
+    dev = xyz.device
+    n = xyz.shape[0]
+    x = _dev_f32(xyz, n * 3, "xyz"); s = _dev_f32(scaling, n * 3, "scaling"); r = _dev_f32(rotation, n * 4, "rotation")
+    o = _dev_f32(opacity, n, "opacity"); dc = _dev_f32(f_dc, n * 3, "features_dc"); rest = _dev_f32(f_rest, n * 45, "features_rest")
+    H, W = int(rs.image_height), int(rs.image_width)
+    color = torch.empty(3, H, W, device=dev, dtype=torch.float32)
+    depth = torch.empty(1, H, W, device=dev, dtype=torch.float32)
+    radii = torch.empty(n, device=dev, dtype=torch.int32)
+    keep = []
+    cam = camera_from_settings(rs, time=t, keep=keep)
+    if not needs_bwd:
+        cam.debug |= _lib.CAM_NO_GRAD      # torch.no_grad() rendering: nothing is saved for a backward
+    # training forwards rebuild the packed weight images (fused optimizers do not bump Tensor._version)
+    prm = module.c_params(keep, fresh=needs_bwd) if module is not None else None
+    g = _lib.Gaussians(n, x.data_ptr(), s.data_ptr(), r.data_ptr(), o.data_ptr(), dc.data_ptr(), rest.data_ptr())
+    with torch.cuda.device(dev):
+        lease = _ContextLease(_lib.Workspace.get(dev.index if dev.index is not None else torch.cuda.current_device()))
+        _lib.check(lib.g4d_render_forward(lease.ctx.handle, C.byref(cam), C.byref(prm) if prm is not None else None,
+                                          C.byref(g), color.data_ptr(), depth.data_ptr(), radii.data_ptr(),
+                                          _stream_ptr(dev)), "g4d_render_forward")
+    cstructs = (cam, prm, g, keep, int(prm.version) if prm is not None else None)
+    return color, radii, depth, lease, cstructs, (x, s, r, o, dc, rest)
+
+
 class _FusedRender(torch.autograd.Function):
     """inputs: xyz, scaling, rotation, opacity, features_dc, features_rest, means2D, *deform parameters"""
 
     @staticmethod
     def forward(ctx, module: Optional[deform_network], rs, t, grad_mode, xyz, scaling, rotation, opacity, f_dc, f_rest, means2D, *params):
-        lib = _lib.load()
-        dev = xyz.device
-        n = xyz.shape[0]
-        x = _dev_f32(xyz, n * 3, "xyz"); s = _dev_f32(scaling, n * 3, "scaling"); r = _dev_f32(rotation, n * 4, "rotation")
-        o = _dev_f32(opacity, n, "opacity"); dc = _dev_f32(f_dc, n * 3, "features_dc"); rest = _dev_f32(f_rest, n * 45, "features_rest")
-        H, W = int(rs.image_height), int(rs.image_width)
-        color = torch.empty(3, H, W, device=dev, dtype=torch.float32)
-        depth = torch.empty(1, H, W, device=dev, dtype=torch.float32)
-        radii = torch.empty(n, device=dev, dtype=torch.int32)
-        keep = []
-        cam = camera_from_settings(rs, time=t, keep=keep)
         needs_bwd = grad_mode and any(ctx.needs_input_grad)    # (grad mode is always off INSIDE Function.forward)
-        if not needs_bwd:
-            cam.debug |= _lib.CAM_NO_GRAD      # torch.no_grad() rendering: nothing is saved for a backward
-        # training forwards rebuild the packed weight images (fused optimizers do not bump Tensor._version)
-        prm = module.c_params(keep, fresh=needs_bwd) if module is not None else None
-        g = _lib.Gaussians(n, x.data_ptr(), s.data_ptr(), r.data_ptr(), o.data_ptr(), dc.data_ptr(), rest.data_ptr())
-        with torch.cuda.device(dev):
-            lease = _ContextLease(_lib.Workspace.get(dev.index if dev.index is not None else torch.cuda.current_device()))
-            _lib.check(lib.g4d_render_forward(lease.ctx.handle, C.byref(cam), C.byref(prm) if prm is not None else None,
-                                              C.byref(g), color.data_ptr(), depth.data_ptr(), radii.data_ptr(),
-                                              _stream_ptr(dev)), "g4d_render_forward")
-        ctx.module, ctx.rs, ctx.t, ctx.n, ctx.lease = module, rs, t, n, lease
+        color, radii, depth, lease, cstructs, saved = _fused_forward(module, rs, t, needs_bwd, xyz, scaling, rotation, opacity, f_dc, f_rest)
+        ctx.module, ctx.rs, ctx.t, ctx.n, ctx.lease = module, rs, t, xyz.shape[0], lease
         # the C-ABI structs (and the tensors whose pointers they carry) are kept for the backward: rebuilding them costs the
         # host ~0.3 ms per view, during which the GPU has nothing queued behind the forward's last kernel
-        ctx.cstructs = (cam, prm, g, keep, int(prm.version) if prm is not None else None)
-        ctx.save_for_backward(x, s, r, o, dc, rest)
+        ctx.cstructs = cstructs
+        ctx.save_for_backward(*saved)
         ctx.mark_non_differentiable(radii, depth)
         return color, radii, depth
 
@@ -118,11 +125,14 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
         raise NotImplementedError("override_color / convert_SHs_python / compute_cov3D_python are dead or broken paths in "
                                   "the reference (gaussian_renderer/__init__.py:74-78,105-116)")
     xyz = pc.get_xyz
-    screenspace_points = torch.zeros_like(xyz, dtype=xyz.dtype, requires_grad=True, device=xyz.device) + 0
-    try:
-        screenspace_points.retain_grad()
-    except Exception:
-        pass
+    if torch.is_grad_enabled():
+        screenspace_points = torch.zeros_like(xyz, dtype=xyz.dtype, requires_grad=True, device=xyz.device) + 0
+        try:
+            screenspace_points.retain_grad()
+        except Exception:
+            pass
+    else:       # nothing will ever flow into it: one memset instead of memset + add
+        screenspace_points = torch.zeros_like(xyz)
     rs, t = settings_from_camera(viewpoint_camera, pc, pipe, bg_color, scaling_modifier, cam_type)
     if "coarse" in stage:
         module = None
@@ -131,9 +141,15 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
     else:
         raise NotImplementedError
     if module is None or isinstance(module, deform_network):
-        params = tuple(module.flat_parameters()) if module is not None else ()
-        rendered_image, radii, depth = _FusedRender.apply(module, rs, t, torch.is_grad_enabled(), xyz, pc._scaling, pc._rotation, pc._opacity,
-                                                          pc._features_dc, pc._features_rest, screenspace_points, *params)
+        if not torch.is_grad_enabled():
+            # no autograd node to build: skip Function.apply and its per-input bookkeeping (40 inputs with the network's parameters)
+            rendered_image, radii, depth, lease, _, _ = _fused_forward(module, rs, t, False, xyz, pc._scaling, pc._rotation, pc._opacity,
+                                                                       pc._features_dc, pc._features_rest)
+            lease.release()
+        else:
+            params = tuple(module.flat_parameters()) if module is not None else ()
+            rendered_image, radii, depth = _FusedRender.apply(module, rs, t, True, xyz, pc._scaling, pc._rotation, pc._opacity,
+                                                              pc._features_dc, pc._features_rest, screenspace_points, *params)
     else:
         # a foreign (e.g. the reference's own PyTorch) deformation module: keep its semantics, still rasterize with g4d
         n = xyz.shape[0]

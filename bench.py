@@ -441,8 +441,10 @@ def run_ours(args):
                               else "FP32 FFMA (net_width 64)",
                        "parallelism": "scene replicated, views sharded (dp%d)" % world},
             "ms_per_view": ms_per_view,
-            "host_enqueue_ms_per_view": host_enqueue_ms, "host_enqueue_note": "wall time the Python render() calls of one step take to "
-            "ENQUEUE a view (no synchronisation) vs %.3f ms until the GPU has finished it" % host_total_ms,
+            "host_enqueue_ms_per_view": host_enqueue_ms, "host_enqueue_note": "wall time per view of ENQUEUEING one step (no "
+            "synchronisation) vs %.3f ms until the GPU has finished it; the asynchronous instance-count read-backs bound the host's "
+            "run-ahead to two views, so a GPU-bound loop shows the GPU's time here (the Python side itself costs ~0.25 ms per view: "
+            "tools/host_profile.py)" % host_total_ms,
             "step_ms_stats": {"mean": float(np.mean(step_ms)), "median": float(np.median(step_ms)), "min": srt[0], "max": srt[-1]},
             "step_ms": [round(x, 3) for x in step_ms],
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": cam_bytes * V, "d2h_bytes_per_step": 3 * H * Wd * 4 * V,

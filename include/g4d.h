@@ -46,7 +46,8 @@ enum {
     G4D_ERR_ARG = -2,       /* invalid argument / unsupported configuration */
     G4D_ERR_NOMEM = -3,     /* device allocation failed */
     G4D_ERR_STATE = -4,     /* backward without a matching forward, ... */
-    G4D_ERR_OVERFLOW = -5   /* tile-instance buffer overflowed in no-sync mode; re-run with sync */
+    G4D_ERR_OVERFLOW = -5   /* tile-instance buffer overflowed in no-sync mode (re-run with sync), or an FP16x2 tensor-core
+                             * launch met a value outside the f16 operand range (G4D_OPT_TENSOR_CORES) */
 };
 
 enum { /* bits of G4DDeformParams.head_mask: a set bit means the head is ACTIVE (not no_dx etc.) */
@@ -219,8 +220,11 @@ enum { G4D_OPT_SYNC_MODE = 1,  /* 1 (default): size the instance buffer exactly 
                                   provably contribute nothing (images identical, fewer instances) */
        G4D_OPT_STAGE_TIMING = 4, /* 1: bracket every stage with CUDA events on the launching stream
                                    (bench.py's live per-kernel durations); 0 (default): off */
-       G4D_OPT_TENSOR_CORES = 5, /* 1 (default): run the deformation MLP on tcgen05 tensor cores (3xTF32) when the
-                                   configuration allows (net_width 128, C in {16,32}, F <= 64); 0: FP32 FFMA kernels */
+       G4D_OPT_TENSOR_CORES = 5, /* the deformation MLP's forward when the configuration allows tensor cores (net_width 128,
+                                   C in {16,32}, F <= 64): 2 (default) tcgen05 with FP16x2 operands (hi + lo halves, 3 products,
+                                   fp32-accurate; operands must stay below 65504 after scaling -- activations < 8188, features
+                                   < 1023, weights < 255 -- else the NEXT call returns G4D_ERR_OVERFLOW), two tiles in flight per
+                                   SM; 1: tcgen05 3xTF32 (no range limit); 0: FP32 FFMA kernels */
        G4D_OPT_TC_DEBUG = 6,     /* 1: the tensor-core kernel records per-phase cycle counters (g4d_debug_tc_cycles) */
        G4D_OPT_KEEP_DEFORMED = 8, /* 1: a no-grad fused forward (G4D_CAM_NO_GRAD) still stores the deformed + activated tensors
                                    * (G4D_BUF_DEFORMED / _SHS reads); default 0: it skips those 48-240 B / Gaussian of writes */

@@ -591,6 +591,72 @@ def test_tensor_core_paths_corner_cases_vs_oracle(net, n):
         assert e <= 3 * GRAD_TOL, (k, e)
 
 
+def test_fp16x2_range_violation_is_reported_and_tf32_path_has_no_limit():
+    """The FP16x2 forward converts (scaled) activations to f16: a hidden activation above 65504 / 8 saturates.  The kernel raises
+    a flag in host-mapped memory and the NEXT tensor-core call returns G4D_ERR_OVERFLOW; the 3xTF32 kernel (option 1) and the
+    FFMA kernels compute the same network without a range limit."""
+    mod = make_module("small128", seed=11)
+    n = 600
+    ins, _ = _deform_inputs(n, 4)
+    t = torch.tensor(0.3).repeat(n, 1).cuda()
+    ws = g4d._lib.Workspace.get(0)
+    with torch.no_grad():
+        mod.deformation_net.feature_out[0].bias.fill_(2.0e4)           # hidden activations ~2e4 >> 8188
+    try:
+        with torch.no_grad():
+            ws.set_option(g4d._lib.OPT_TENSOR_CORES, 1)
+            a = [o.clone() for o in mod(*ins, t)]
+            ws.set_option(g4d._lib.OPT_TENSOR_CORES, 0)
+            b = [o.clone() for o in mod(*ins, t)]
+            for x, y in zip(a, b):
+                assert float((x - y).abs().max()) <= 1e-5 * max(1.0, float(y.abs().max()))
+            ws.set_option(g4d._lib.OPT_TENSOR_CORES, 2)
+            mod(*ins, t)                                                # saturates; flagged
+            torch.cuda.synchronize()
+            with pytest.raises(g4d._lib.G4DError, match="f16 operand range"):
+                mod(*ins, t)
+            mod.deformation_net.feature_out[0].bias.fill_(0.1)          # back in range: the flag was consumed, results are exact again
+            c = [o.clone() for o in mod(*ins, t)]
+            ws.set_option(g4d._lib.OPT_TENSOR_CORES, 0)
+            d = [o.clone() for o in mod(*ins, t)]
+            for x, y in zip(c, d):
+                assert float((x - y).abs().max()) <= 5e-6
+    finally:
+        ws.set_option(g4d._lib.OPT_TENSOR_CORES, 2)
+
+
+def test_no_grad_render_skips_saved_tensors_unless_asked():
+    """A torch.no_grad() render does not store the deformed tensors (they only serve a backward); G4D_OPT_KEEP_DEFORMED keeps
+    them for the debug reads; the image is the same either way."""
+    n, W, H = 3000, 160, 120
+    scene = synth.make_scene(n, seed=2, scale_mean=0.05)
+    mod = make_module("small128", seed=2, aabb=scene["aabb"])
+    pc = synth.SyntheticGaussianModel(scene, mod, sh_degree=3)
+    cam = synth.make_camera(20.0, W, H, time=0.6)
+    bg = torch.tensor([0.0, 0.0, 0.0], device="cuda")
+    ws = g4d._lib.Workspace.get(0)
+
+    class P:
+        convert_SHs_python = False; compute_cov3D_python = False; debug = False
+    ws._free_contexts.clear()
+    with torch.no_grad():
+        img0 = g4d.render(cam, pc, P, bg)["render"].clone()
+    torch.cuda.synchronize()
+    with pytest.raises(g4d._lib.G4DError, match="kept its tensors"):
+        ws._free_contexts[-1].read("deformed")
+    ws.set_option(g4d._lib.OPT_KEEP_DEFORMED, 1)
+    try:
+        ws._free_contexts.clear()
+        with torch.no_grad():
+            img1 = g4d.render(cam, pc, P, bg)["render"].clone()
+        torch.cuda.synchronize()
+        dfm = ws._free_contexts[-1].read("deformed")
+        assert dfm.shape == (n, 11) and np.isfinite(dfm).all()
+    finally:
+        ws.set_option(g4d._lib.OPT_KEEP_DEFORMED, 0)
+    assert torch.equal(img0, img1)
+
+
 @pytest.mark.parametrize("tcmode", [2, 1])
 @pytest.mark.parametrize("net,n", [("small128", 700), ("dynerf", 21000), ("hypernerf", 40000)])
 def test_tensor_core_backward_matches_ffma_path(net, n, tcmode):
@@ -689,7 +755,8 @@ def test_warp_strip_cull_changes_no_pixel_and_no_gradient():
 
 def test_no_sync_mode_matches_sync_mode_and_reports_overflow():
     """G4D_OPT_SYNC_MODE=0: capacity-bounded binning without the host round trip gives bit-identical images; a forward
-    that outgrows the capacity is reported by the next call on the context."""
+    that outgrows the capacity is reported by the first call on the context after its asynchronous count read-back has landed
+    (at the latest by the second: the read-backs alternate between two slots, so that the host may run one view ahead)."""
     ins = [t.float().cuda() for t in raster_inputs(30_000, 6, scale_mean=0.02)]
     ws = g4d._lib.Workspace.get(0)
 
@@ -714,6 +781,7 @@ def test_no_sync_mode_matches_sync_mode_and_reports_overflow():
         ws._free_contexts.clear()                 # fresh context => fresh capacity
         render(ws2_ctx_cam_far); render(ws2_ctx_cam_far)
         render(synth.make_camera(0.0, 640, 480, radius=1.6))     # several times the instances of the far views
+        torch.cuda.synchronize()                  # (the count is read back asynchronously: reported by the first call after it landed)
         with pytest.raises(g4d._lib.G4DError, match="overflow"):
             render(ws2_ctx_cam_far)
     finally:
