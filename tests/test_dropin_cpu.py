@@ -47,6 +47,24 @@ def test_state_dict_round_trips_with_reference_module(name):
     assert [p.shape for p in mine.get_grid_parameters()] == [p.shape for p in ref.get_grid_parameters()]
 
 
+def test_flat_parameter_cache_follows_the_module():
+    """flat_parameters() caches the Parameter OBJECTS in C-ABI order (nn.Module container indexing costs ~0.1 ms per render): the
+    cache must survive in-place updates (load_state_dict, optimizer steps) and be dropped by .to()/.float() and invalidate_cache()."""
+    mod = g4d.deform_network(synth.hidden_args("dynerf"))
+    a = mod.flat_parameters()
+    assert len(a) == 12 + 2 + 4 * 5
+    assert a[12] is mod.deformation_net.feature_out[0].weight and a[-1] is mod.deformation_net.shs_deform[3].bias
+    b = mod.flat_parameters()
+    assert all(x is y for x, y in zip(a, b)) and a is not b                 # same objects, a fresh list each call
+    mod.load_state_dict({k: v.clone() for k, v in mod.state_dict().items()})
+    assert all(x is y for x, y in zip(a, mod.flat_parameters()))
+    mod.double(); mod.float()                                                # _apply: the cache is rebuilt
+    c = mod.flat_parameters()
+    assert all(x is y for x, y in zip(c, [p for lvl in mod.deformation_net.grid.grids for p in lvl]))
+    mod.invalidate_cache()
+    assert mod._flat_cache is None and len(mod.flat_parameters()) == len(a)
+
+
 def test_scalar_time_quirks():
     d = importlib.import_module("4dgaussians_b200.deformation")
     assert d.scalar_time(0) == 0.0 and d.scalar_time(0.25) == 0.25
