@@ -1,6 +1,7 @@
 // g4d_api.cu -- the C-ABI of libg4d.so (include/g4d.h): workspace / context management and stage orchestration.
 // No torch types, no CPU fallback: every entry point either runs the CUDA path or returns an error code.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -107,6 +108,11 @@ struct G4DContext {
     bool ev_used[G4D_STAGE_COUNT] = {};
     bool ev_created = false;
 };
+
+namespace g4d {
+// programmatic dependent launch of the forward chain (g4d_common.cuh); G4D_OPT_PDL / env G4D_PDL=0 switch it off
+int g_pdl = []() { const char* e = getenv("G4D_PDL"); return e ? atoi(e) != 0 : 1; }();
+}  // namespace g4d
 
 namespace {
 
@@ -366,6 +372,7 @@ int bin_and_blend(G4DContext* c, const G4DCamera* cam, int64_t n, float* out_col
     int rc;
     const int num_tiles = c->grid_x * c->grid_y;
     const uint32_t kNoCap = 0xFFFFFFFFu;
+    const uint32_t* readback = nullptr;
     if (n > 0) {
         if (ws->sm_count > 1024) return fail(G4D_ERR_ARG, "more than 1024 SMs are not supported by the binning kernel");
         G4D_CUDA(c->binaux.ensure(bin_aux_bytes(n, num_tiles, ws->sm_count)));
@@ -390,11 +397,9 @@ int bin_and_blend(G4DContext* c, const G4DCamera* cam, int64_t n, float* out_col
         } else {
             // capacity-bounded, no host round trip: the placement clamps to the capacity, R arrives asynchronously and an
             // overflow is reported by the next call on this context
-            const int sl = c->slot;
-            c->slot ^= 1;
-            G4D_CUDA(cudaMemcpyAsync(c->h_r + sl, &lay.ctl->R, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            G4D_CUDA(cudaEventRecord(c->ev_r[sl], st));
-            c->pending[sl] = true; c->used_capacity[sl] = c->capacity;
+            // (the read-back itself is enqueued behind the blend kernel, below: a copy between bin_sort and the placement
+            //  would keep the programmatically dependent launches of the chain from queueing up behind one another)
+            readback = &lay.ctl->R;
         }
         if ((rc = debug_sync(cam, st, "bin_sort")) != G4D_OK) return rc;
         {
@@ -411,6 +416,13 @@ int bin_and_blend(G4DContext* c, const G4DCamera* cam, int64_t n, float* out_col
     {
         StageTimer tm(c, G4D_STAGE_BLEND, st);
         G4D_CUDA(launch_blend_forward(dcam, c->grid_x, c->grid_y, c->g, c->b, c->im, out_color, out_depth, ws->warp_cull, st));
+    }
+    if (readback) {
+        const int sl = c->slot;
+        c->slot ^= 1;
+        G4D_CUDA(cudaMemcpyAsync(c->h_r + sl, readback, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        G4D_CUDA(cudaEventRecord(c->ev_r[sl], st));
+        c->pending[sl] = true; c->used_capacity[sl] = c->capacity;
     }
     if ((rc = debug_sync(cam, st, "blend_forward")) != G4D_OK) return rc;
     c->n = n;
@@ -512,6 +524,7 @@ int g4d_workspace_set_option(G4DWorkspace* ws, int option, int64_t value) {
         case G4D_OPT_WARP_CULL: ws->warp_cull = value ? 1 : 0; return G4D_OK;
         case G4D_OPT_TC_DEBUG: ws->tc_debug = value ? 1 : 0; return G4D_OK;
         case G4D_OPT_KEEP_DEFORMED: ws->keep_deformed = value ? 1 : 0; return G4D_OK;
+        case G4D_OPT_PDL: g4d::g_pdl = value ? 1 : 0; return G4D_OK;
         default: return fail(G4D_ERR_ARG, "unknown option");
     }
 }

@@ -271,6 +271,7 @@ __global__ void __launch_bounds__(kBinThreads, 1) bin_sort_kernel(BinSortArgs a)
     const uint32_t G = gridDim.x, c = blockIdx.x;
     const uint32_t N = (uint32_t)a.n;
 
+    pdl_trigger();      // (ordinary cooperative launch; lets the placement kernel queue up behind this grid)
     G4D_BIN_MARK(0);
     // ---- 0. range of the visible depth bits: reduced by the projection stage (RED.MIN / RED.MAX into the context's CameraDev)
     if (blockIdx.x == 0 && tid == 0) { a.ctl->R = 0u; a.ctl->overflow = 0u; }
@@ -407,6 +408,8 @@ __global__ void __launch_bounds__(kBinThreads, 1) bin_place_kernel(BinPlaceArgs 
     __shared__ uint32_t s_w[33];
     const int tid = threadIdx.x, warp = tid >> 5;
     const uint32_t c = blockIdx.x, G = gridDim.x;
+    pdl_wait();
+    pdl_trigger();
     const uint32_t cs = a.chunk_start[c], ce = a.chunk_start[c + 1];
     const uint32_t len = ce - cs, per = (len + 31) / 32;
     const uint32_t ks = cs + min((uint32_t)warp * per, len), ke = cs + min((uint32_t)(warp + 1) * per, len);
@@ -460,6 +463,8 @@ __global__ void __launch_bounds__(kBinThreads, 1) bin_place_kernel(BinPlaceArgs 
 __global__ void __launch_bounds__(256, 4) bin_fix_kernel(BinPlaceArgs a, int chunks) {
     const int lane = threadIdx.x & 31;
     const int rounds = (chunks + 31) / 32;
+    pdl_wait();
+    pdl_trigger();
     const uint32_t item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // (tile, round): a dense tile's rounds run
     const uint32_t t = item / (uint32_t)rounds;                                   // on different warps
     if (t >= (uint32_t)a.num_tiles) return;
@@ -600,11 +605,9 @@ cudaError_t launch_bin_place(int grid_x, int grid_y, const GeomBuffers& g, const
     const size_t smem = 4 * (size_t)a.band_rows * grid_x;
     cudaError_t e = cudaFuncSetAttribute(bin_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    bin_place_kernel<<<lay.chunks, kBinThreads, smem, st>>>(a);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if ((e = launch_k(bin_place_kernel, dim3(lay.chunks), dim3(kBinThreads), smem, st, true, a)) != cudaSuccess) return e;
     const int rounds = (lay.chunks + 31) / 32;
-    bin_fix_kernel<<<(num_tiles * rounds + 7) / 8, 256, 0, st>>>(a, lay.chunks);
-    return cudaGetLastError();
+    return launch_k(bin_fix_kernel, dim3((num_tiles * rounds + 7) / 8), dim3(256), 0, st, true, a, lay.chunks);
 }
 
 }  // namespace g4d

@@ -78,4 +78,30 @@ G4D_CE int head_out(int h) { return h == 0 ? 3 : h == 1 ? 3 : h == 2 ? 4 : h == 
 G4D_CE int head_col(int h) { return h == 0 ? 0 : h == 1 ? 3 : h == 2 ? 6 : h == 3 ? 10 : 11; }
 constexpr int kDeltaCols = 59;
 
+#if defined(__CUDACC__)
+// ---- programmatic dependent launch (sm_90+): a kernel launched with the "programmatic stream serialization" attribute may
+// become resident while the previous kernel of the stream is still draining; it must not touch anything that kernel (or the
+// one before it) wrote, nor write anything they read, before pdl_wait().  Every kernel of the forward chain does
+// `pdl_wait(); pdl_trigger();` in that order: a dependent can then only start once ALL CTAs of its predecessor are past
+// their own wait, i.e. once the predecessor's predecessor has completed -- what a kernel does before its wait may therefore
+// read anything older than its direct predecessor (parameters, weight images), and only that.  Both are no-ops in a kernel
+// launched the ordinary way.
+G4D_D void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+G4D_D void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+extern int g_pdl;   // process-wide switch (G4D_OPT_PDL / env G4D_PDL; g4d_api.cu)
+
+// <<<grid, block, smem, st>>> with the programmatic-stream-serialization attribute when `pdl` is set
+template <class... KArgs, class... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = (pdl && g_pdl) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 }  // namespace g4d

@@ -258,10 +258,9 @@ deform_f16_kernel(DeformDesc d, TcWeights tw, F16Smem Ls, const CameraDev* __res
     const int tid = threadIdx.x, warp = tid >> 5;
     const int row = tid & 127;
     const int64_t ntiles = (n + 127) / 128;
-    if (use_cam) {
-        for (int i = tid; i < (int)(sizeof(CameraDev) / 4); i += kF16Threads)
-            reinterpret_cast<uint32_t*>(&cam)[i] = reinterpret_cast<const uint32_t*>(camp)[i];
-    }
+    // (programmatic dependent launch: everything up to pdl_wait() below reads only the network's own parameters -- written long
+    //  before the previous two kernels of the stream -- and sets up shared memory, TMEM and the barriers while the HexPlane
+    //  gather in front of this kernel drains)
     float* sBias = reinterpret_cast<float*>(smem + Ls.bias);     // b0 * kSA [128] | b1[5][128] (SH head * kSA) | b2s[4][4] | b2sh[48]
     float4* sW2p = reinterpret_cast<float4*>(smem + Ls.w2s);     // [4 small heads][64 unit pairs][2] (small_head)
     float* sOut = reinterpret_cast<float*>(smem + Ls.out);       // [2 slots][11 deltas][128 Gaussians]
@@ -297,6 +296,12 @@ deform_f16_kernel(DeformDesc d, TcWeights tw, F16Smem Ls, const CameraDev* __res
             mbar_init(b + 6, 128); mbar_init(b + 7, 128); mbar_init(b + 8, 128);
         }
         fence_barrier_init();
+    }
+    pdl_wait();           // from here on: the camera, the staged features, the weight images
+    pdl_trigger();
+    if (use_cam) {
+        for (int i = tid; i < (int)(sizeof(CameraDev) / 4); i += kF16Threads)
+            reinterpret_cast<uint32_t*>(&cam)[i] = reinterpret_cast<const uint32_t*>(camp)[i];
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -648,13 +653,12 @@ static cudaError_t launch_deform_f16_t(const DeformDesc& d, const TcWeights& tw,
     if (tw.relu_bits) {
         e = cudaFuncSetAttribute(deform_f16_kernel<MODE, C, L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
-        deform_f16_kernel<MODE, C, L, true><<<grid, kF16Threads, bytes, st>>>(d, tw, Ls, cam, use_cam ? 1 : 0, n, io);
+        return launch_k(deform_f16_kernel<MODE, C, L, true>, dim3(grid), dim3(kF16Threads), bytes, st, true, d, tw, Ls, cam, use_cam ? 1 : 0, n, io);
     } else {
         e = cudaFuncSetAttribute(deform_f16_kernel<MODE, C, L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
-        deform_f16_kernel<MODE, C, L, false><<<grid, kF16Threads, bytes, st>>>(d, tw, Ls, cam, use_cam ? 1 : 0, n, io);
+        return launch_k(deform_f16_kernel<MODE, C, L, false>, dim3(grid), dim3(kF16Threads), bytes, st, true, d, tw, Ls, cam, use_cam ? 1 : 0, n, io);
     }
-    return cudaGetLastError();
 }
 
 cudaError_t launch_deform_features(const DeformDesc& d, int64_t n, const float* xyz, float* feat, cudaStream_t st);

@@ -704,6 +704,8 @@ deform_tc_kernel(DeformDesc d, TcWeights tw, TcSmem Ls, const CameraDev* __restr
 // ---- HexPlane gather at full occupancy: C/4 threads per Gaussian, one channel vector each -> feat [N][F] fp32 -----------
 template <int C4>
 __global__ void __launch_bounds__(256) deform_features_kernel(DeformDesc d, int64_t n, const float* __restrict__ xyz, float* __restrict__ feat) {
+    pdl_wait();         // the collapsed time rows come from the previous kernel of the stream
+    pdl_trigger();
     const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
     const int64_t g = t / C4;
     const int v = (int)(t % C4);
@@ -722,10 +724,9 @@ cudaError_t launch_deform_features(const DeformDesc& d, int64_t n, const float* 
     if (n == 0) return cudaSuccess;
     const int C4 = d.C / 4;
     const unsigned grid = (unsigned)((n * C4 + 255) / 256);
-    if (C4 == 4) deform_features_kernel<4><<<grid, 256, 0, st>>>(d, n, xyz, feat);
-    else if (C4 == 8) deform_features_kernel<8><<<grid, 256, 0, st>>>(d, n, xyz, feat);
-    else return cudaErrorInvalidValue;
-    return cudaGetLastError();
+    if (C4 == 4) return launch_k(deform_features_kernel<4>, dim3(grid), dim3(256), 0, st, true, d, n, xyz, feat);
+    if (C4 == 8) return launch_k(deform_features_kernel<8>, dim3(grid), dim3(256), 0, st, true, d, n, xyz, feat);
+    return cudaErrorInvalidValue;
 }
 
 bool tc_deform_supported(const DeformDesc& d) {

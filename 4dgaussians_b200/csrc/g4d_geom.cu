@@ -13,6 +13,7 @@ namespace g4d {
 
 // ------------------------------------------------------------------------------------------------------
 __global__ void pack_camera_kernel(G4DCamera c, CameraDev* dst) {
+    pdl_trigger();      // (ordinary launch: everything before it in the stream has completed)
     const int t = threadIdx.x;
     if (t < 16) {
         dst->view[t] = c.d_viewmatrix ? c.d_viewmatrix[t] : c.viewmatrix[t];
@@ -86,6 +87,8 @@ struct CollapseDesc {
 // Every Gaussian of a view shares t, so the time-axis interpolation of the three time planes is done once:
 // row[x][c] = plane[y0][x][c]*(y1-y) + plane[y1][x][c]*(y-y0)  with t NOT normalised (hexplane.py:164).
 __global__ void collapse_time_rows_kernel(CollapseDesc d, const CameraDev* cam, float time_arg, int use_cam_time) {
+    pdl_wait();         // cam->time (pack_camera); the rows are read by the previous view's kernels until they complete
+    pdl_trigger();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int nseg = d.levels * 3;
     if (i >= d.start[nseg]) return;
@@ -114,8 +117,7 @@ cudaError_t launch_collapse_time_rows(const G4DDeformParams& p, const CameraDev*
         }
     }
     d.start[p.levels * 3] = total;
-    collapse_time_rows_kernel<<<(total + 255) / 256, 256, 0, st>>>(d, cam, time, use_cam_time ? 1 : 0);
-    return cudaGetLastError();
+    return launch_k(collapse_time_rows_kernel, dim3((total + 255) / 256), dim3(256), 0, st, true, d, cam, time, use_cam_time ? 1 : 0);
 }
 
 // ------------------------------------------------------------------------------------------------------

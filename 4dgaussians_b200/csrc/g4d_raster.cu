@@ -125,6 +125,8 @@ blend_forward_packed_kernel(const CameraDev* __restrict__ cam, GeomBuffers g, co
     __shared__ float4 s0[kTilePixels];
     __shared__ float4 s1[kTilePixels];
     __shared__ float2 s2[kTilePixels];
+    pdl_wait();
+    pdl_trigger();
     const int H = cam->H, W = cam->W;
     const int tile = blockIdx.y * gridDim.x + blockIdx.x;
     const uint2 range = ranges[tile];
@@ -221,9 +223,8 @@ cudaError_t launch_blend_forward(const CameraDev* cam, int grid_x, int grid_y, G
     static int ppt = []() { const char* e = getenv("G4D_BLEND_FWD_PPT"); const int v = e ? atoi(e) : 2; return (v == 1 || v == 4) ? v : 2; }();
     static int packed = []() { const char* e = getenv("G4D_BLEND_FWD_PACKED"); return e ? atoi(e) : 1; }();
     if (packed && ppt == 2) {
-        blend_forward_packed_kernel<<<dim3(grid_x, grid_y), kTilePixels / 2, 0, st>>>(cam, g, b.ids_sorted, b.ranges, im.final_T,
-                                                                                      im.n_contrib, out_color, out_depth, warp_cull);
-        return cudaGetLastError();
+        return launch_k(blend_forward_packed_kernel, dim3(grid_x, grid_y), dim3(kTilePixels / 2), 0, st, true, cam, g, b.ids_sorted,
+                        b.ranges, im.final_T, im.n_contrib, out_color, out_depth, warp_cull);
     }
 #define G4D_LAUNCH_BF(P)                                                                                                  \
     blend_forward_kernel<P><<<dim3(grid_x, grid_y), kTilePixels / P, 0, st>>>(cam, g, b.ids_sorted, b.ranges, im.final_T, \

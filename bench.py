@@ -261,7 +261,9 @@ def run_ours(args):
         return cams_all[((step * V + v) * world + rank) % len(cams_all)]
     bg = torch.tensor(w["bg"], dtype=torch.float32, device=dev)
     ws = lib.Workspace.get(local)
-    ws.set_option(lib.OPT_STAGE_TIMING, 1)
+    # per-stage CUDA events (ten cudaEventRecord per view, each a break in the programmatically dependent launch chain) are
+    # recorded for ONE view of every timed step (the last) and for the untimed per-stage pass below, not for every view
+    ws.set_option(lib.OPT_STAGE_TIMING, 0)
     ws.set_option(lib.OPT_SYNC_MODE, 1 if args.host_sync else 0)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     H, Wd = w["height"], w["width"]
@@ -277,7 +279,10 @@ def run_ours(args):
     def resident_step(step):
         out = None
         for v in range(V):
+            if v == V - 1:
+                ws.set_option(lib.OPT_STAGE_TIMING, 1)
             out = g4d.render(cam_of(step, v), pc, Pipe, bg)      # same binding in warm-up and timed steps
+        ws.set_option(lib.OPT_STAGE_TIMING, 0)
         return out
 
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -305,6 +310,8 @@ def run_ours(args):
         t_wall = time.perf_counter() - t_wall0
         gc.enable()
     step_ms = [a.elapsed_time(b) for a, b in ev]
+    # the stage events of the last view of the last timed step (same context: no-grad renders release it at once)
+    in_region_stage_ms = ws._free_contexts[-1].stage_times() if ws._free_contexts else {}
     total_ms = _max_over_ranks(dist, dev, sum(step_ms))
     value = world * K * V / (total_ms / 1e3)
 
@@ -321,6 +328,7 @@ def run_ours(args):
 
     # ------------------------------------------------------------------ per-stage device times, R, blend work (untimed pass)
     stage_acc, Rs, vis, pairs = {}, [], [], []
+    ws.set_option(lib.OPT_STAGE_TIMING, 1)
     with torch.no_grad():
         for i in range(min(V, 8)):
             g4d.render(cam_of(Wm, i), pc, Pipe, bg)
@@ -333,6 +341,8 @@ def run_ours(args):
                 Rs.append(int(s_.num_rendered)); vis.append(int(s_.num_visible))
                 if i < 2:
                     pairs.append(float(fn_ctx.read("n_contrib").astype(np.float64).sum()))
+
+    ws.set_option(lib.OPT_STAGE_TIMING, 0)
 
     # ------------------------------------------------------------------ e2e arm: host camera in, image out to pinned host
     pinned = [torch.empty(3, H, Wd, dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -439,6 +449,8 @@ def run_ours(args):
                                   "device-side R, capacity-bounded, no host sync (overflow-checked)",
                        "mlp": "tcgen05 FP16x2 forward (hi+lo operands, 3 products, fp32-accurate), BF16x2 tcgen05 backward" if NETS[w["net"]]["Wd"] == 128
                               else "FP32 FFMA (net_width 64)",
+                       "launch": "programmatic dependent launch between the kernels of a view" if os.environ.get("G4D_PDL", "1") != "0"
+                                 else "ordinary stream order (G4D_PDL=0)",
                        "parallelism": "scene replicated, views sharded (dp%d)" % world},
             "ms_per_view": ms_per_view,
             "host_enqueue_ms_per_view": host_enqueue_ms, "host_enqueue_note": "wall time per view of ENQUEUEING one step (no "
@@ -467,7 +479,10 @@ def run_ours(args):
                               "achieved": ab["total"] / (ms_per_view * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                               "frac": ab["total"] / (ms_per_view * 1e-3) / 1e9 / peak},
             "roofline_blend": _blend_roofline(float(np.mean(pairs)) if pairs else 0.0, fwd_stages.get("blend", 0.0), sm_count),
-            "stage_ms": stages, "binning_ms": bin_ms, "train_step": train, "wall_s_timed_region": t_wall,
+            "stage_ms": stages, "stage_ms_note": "CUDA events on the launching stream around every stage, mean over 8 views rendered right "
+            "after the timed region (one view per synchronize); `stage_ms_in_timed_region` = the same events for the last view of the "
+            "last timed step (events are recorded for one view per timed step only: they break the dependent-launch chain)",
+            "stage_ms_in_timed_region": in_region_stage_ms, "binning_ms": bin_ms, "train_step": train, "wall_s_timed_region": t_wall,
             "parity_check": parity, "gpu_eager_baseline": eager,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -587,6 +602,8 @@ def run_train_steps(g4d, synth, lib, w, scene, mod, dev, dist, world, rank, step
     bg = torch.tensor(w["bg"], dtype=torch.float32, device=dev)
     target = torch.rand(3, w["height"], w["width"], device=dev)
     evs = []
+    wsp = lib.Workspace.get(dev.index)
+    wsp.set_option(lib.OPT_STAGE_TIMING, 0)
     for it in range(steps + warmup):
         flush.fill_(it & 0xFF)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -602,7 +619,13 @@ def run_train_steps(g4d, synth, lib, w, scene, mod, dev, dist, world, rank, step
             evs.append((a, b))
     torch.cuda.synchronize(dev)
     ms = _max_over_ranks(dist, dev, sum(x.elapsed_time(y) for x, y in evs) / len(evs))
-    ctx = lib.Workspace.get(dev.index)._free_contexts
+    # one more (untimed) step with the per-stage events on: stage times of its last view
+    wsp.set_option(lib.OPT_STAGE_TIMING, 1)
+    it = steps + warmup
+    tr.step([cams[((it * B + v) * world + rank) % len(cams)] for v in range(B)], [target] * B, bg, Pipe)
+    torch.cuda.synchronize(dev)
+    wsp.set_option(lib.OPT_STAGE_TIMING, 0)
+    ctx = wsp._free_contexts
     st = ctx[-1].stage_times() if ctx else {}
     numel = tr.state.numel
     mod.fused_grad_accumulation = False

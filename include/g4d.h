@@ -228,8 +228,11 @@ enum { G4D_OPT_SYNC_MODE = 1,  /* 1 (default): size the instance buffer exactly 
        G4D_OPT_TC_DEBUG = 6,     /* 1: the tensor-core kernel records per-phase cycle counters (g4d_debug_tc_cycles) */
        G4D_OPT_KEEP_DEFORMED = 8, /* 1: a no-grad fused forward (G4D_CAM_NO_GRAD) still stores the deformed + activated tensors
                                    * (G4D_BUF_DEFORMED / _SHS reads); default 0: it skips those 48-240 B / Gaussian of writes */
-       G4D_OPT_WARP_CULL = 7     /* 1 (default): the blend kernels skip, per warp, instances that cannot reach alpha >= 1/255
-                                  *    on any pixel of the warp's 16 x 4 strip (results unchanged); 0 = test every pixel */ };
+       G4D_OPT_WARP_CULL = 7,    /* 1 (default): the blend kernels skip, per warp, instances that cannot reach alpha >= 1/255
+                                  *    on any pixel of the warp's 16 x 4 strip (results unchanged); 0 = test every pixel */
+       G4D_OPT_PDL = 9           /* 1 (default): the kernels of a forward are launched programmatically dependent on one another
+                                  *    (a kernel's set-up overlaps the tail of its predecessor; results unchanged); 0: ordinary
+                                  *    stream order.  PROCESS-wide, not per workspace (also: environment G4D_PDL=0) */ };
 int g4d_workspace_set_option(G4DWorkspace *ws, int option, int64_t value);
 
 /* copy an internal per-forward buffer to HOST memory (tests / debugging; synchronises).
