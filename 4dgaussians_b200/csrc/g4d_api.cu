@@ -96,13 +96,15 @@ struct G4DContext {
     ImageBuffers im{};
     FusedOutputs fo{};
     float* trow_ptr[G4D_MAX_LEVELS][3] = {};
-    // no-sync mode: the instance count of a forward is read back asynchronously into one of TWO slots (pinned word + event), used
-    // alternately: when forward v starts, the slot it is about to reuse holds forward v-2 (complete unless the host is two views
-    // ahead of the device -- then it waits, which bounds the run-ahead), the other one forward v-1 (looked at only if it is done)
+    // no-sync mode: the instance count of a forward is read back asynchronously (behind its blend kernel) into one of kSlots
+    // slots (pinned word + event) used round robin: when forward v starts, the slot it is about to reuse holds forward
+    // v - kSlots (complete unless the host is kSlots views ahead of the device -- then it waits, which bounds the run-ahead),
+    // the others the newer forwards (looked at only if they are done)
+    static constexpr int kSlots = 4;
     uint32_t* h_r = nullptr;          // pinned: [slot] instance count
-    cudaEvent_t ev_r[2] = {nullptr, nullptr};
-    bool pending[2] = {false, false}; // the slot's read-back has not been checked yet
-    int64_t used_capacity[2] = {0, 0};   // capacity the slot's forward ran with
+    cudaEvent_t ev_r[kSlots] = {};
+    bool pending[kSlots] = {};        // the slot's read-back has not been checked yet
+    int64_t used_capacity[kSlots] = {};  // capacity the slot's forward ran with
     int slot = 0;                     // slot the NEXT no-sync forward uses
     cudaEvent_t ev[2 * G4D_STAGE_COUNT] = {};
     bool ev_used[G4D_STAGE_COUNT] = {};
@@ -340,8 +342,8 @@ int debug_sync(const G4DCamera* cam, cudaStream_t st, const char* stage) {
 
 // no-sync mode: the previous forward's instance count arrives asynchronously; look at it before reusing the context
 int check_pending(G4DContext* c) {
-    for (int k = 0; k < 2; ++k) {
-        const int s = c->slot ^ k;          // k = 0: the slot about to be reused (must be resolved), k = 1: the newer one
+    for (int k = 0; k < G4DContext::kSlots; ++k) {
+        const int s = (c->slot + k) % G4DContext::kSlots;   // k = 0: the slot about to be reused (oldest forward: must be resolved), then the newer ones
         if (!c->pending[s]) continue;
         if (k == 0) {
             G4D_CUDA(cudaEventSynchronize(c->ev_r[s]));
@@ -419,7 +421,7 @@ int bin_and_blend(G4DContext* c, const G4DCamera* cam, int64_t n, float* out_col
     }
     if (readback) {
         const int sl = c->slot;
-        c->slot ^= 1;
+        c->slot = (c->slot + 1) % G4DContext::kSlots;
         G4D_CUDA(cudaMemcpyAsync(c->h_r + sl, readback, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         G4D_CUDA(cudaEventRecord(c->ev_r[sl], st));
         c->pending[sl] = true; c->used_capacity[sl] = c->capacity;
@@ -495,10 +497,9 @@ G4DContext* g4d_context_create(G4DWorkspace* ws) {
     G4DContext* c = new G4DContext();
     c->ws = ws;
     if (c->cam.ensure(sizeof(CameraDev)) != cudaSuccess) { delete c; fail(G4D_ERR_NOMEM, "camera buffer"); return nullptr; }
-    if (cudaMallocHost((void**)&c->h_r, 64) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_r[0], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_r[1], cudaEventDisableTiming) != cudaSuccess) {
-        delete c; fail(G4D_ERR_NOMEM, "pinned scalar / event"); return nullptr;
-    }
+    bool ok = cudaMallocHost((void**)&c->h_r, 64) == cudaSuccess;
+    for (int i = 0; ok && i < G4DContext::kSlots; ++i) ok = cudaEventCreateWithFlags(&c->ev_r[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { g4d_context_destroy(c); fail(G4D_ERR_NOMEM, "pinned scalar / event"); return nullptr; }
     return c;
 }
 
@@ -506,7 +507,7 @@ void g4d_context_destroy(G4DContext* c) {
     if (!c) return;
     cudaSetDevice(c->ws->device);
     if (c->ev_created) for (int i = 0; i < 2 * G4D_STAGE_COUNT; ++i) cudaEventDestroy(c->ev[i]);
-    for (int i = 0; i < 2; ++i) if (c->ev_r[i]) cudaEventDestroy(c->ev_r[i]);
+    for (int i = 0; i < G4DContext::kSlots; ++i) if (c->ev_r[i]) cudaEventDestroy(c->ev_r[i]);
     if (c->h_r) cudaFreeHost(c->h_r);
     c->cam.release(); c->geom.release(); c->bin.release(); c->binaux.release(); c->img.release(); c->fused.release(); c->gscratch.release(); c->gdeform.release(); c->relu.release(); c->feat.release();
     c->trow.release();

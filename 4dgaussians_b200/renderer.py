@@ -118,6 +118,21 @@ class _FusedRender(torch.autograd.Function):
         return (None, None, None, None, gx, gs, gr, go, gdc, grest, gm2) + tuple(pgrads)
 
 
+_ZERO_POINTS = {}
+
+
+def _zero_points(xyz: torch.Tensor) -> torch.Tensor:
+    """The ``viewspace_points`` of a no-grad render: all zeros, never written by anything (no gradient can flow into it), so
+    one read-only tensor per (device, N) is shared between calls instead of filling a new one per view."""
+    key = (xyz.device, xyz.shape[0], xyz.dtype)
+    z = _ZERO_POINTS.get(key)
+    if z is None:
+        if len(_ZERO_POINTS) > 8:
+            _ZERO_POINTS.clear()
+        z = _ZERO_POINTS[key] = torch.zeros_like(xyz)
+    return z
+
+
 def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None, stage="fine",
            cam_type=None):
     """Render the scene.  Background tensor (bg_color) must be on GPU (as in the reference)."""
@@ -131,8 +146,8 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
             screenspace_points.retain_grad()
         except Exception:
             pass
-    else:       # nothing will ever flow into it: one memset instead of memset + add
-        screenspace_points = torch.zeros_like(xyz)
+    else:       # nothing will ever flow into it: a cached all-zero tensor instead of a memset (+ add) launch per view
+        screenspace_points = _zero_points(xyz)
     rs, t = settings_from_camera(viewpoint_camera, pc, pipe, bg_color, scaling_modifier, cam_type)
     if "coarse" in stage:
         module = None

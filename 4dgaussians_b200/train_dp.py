@@ -282,9 +282,13 @@ class DPTrainer:
         if self.dist is not None and self.world > 1:
             works = self._launch_allreduce()
         if it < o.densify_until_iter:
-            g.max_radii2D[vis_any] = torch.maximum(g.max_radii2D[vis_any], radii_max[vis_any])
-            g.xyz_gradient_accum[vis_any] += torch.norm(m2d_grad[vis_any, :2], dim=-1, keepdim=True)
-            g.denom[vis_any] += 1
+            # train.py:252-255 / gaussian_model.py:636-638 without the boolean-mask indexing (each `x[mask]` is a nonzero() ->
+            # one host synchronisation per statement): the same values, masked arithmetically (radii and the statistics
+            # are >= 0; an invisible Gaussian's screen-space gradient is exactly zero)
+            vis_f = vis_any.unsqueeze(-1).to(g.denom.dtype)
+            torch.maximum(g.max_radii2D, radii_max * vis_f.squeeze(-1), out=g.max_radii2D)
+            g.xyz_gradient_accum.add_(torch.norm(m2d_grad[:, :2], dim=-1, keepdim=True) * vis_f)
+            g.denom.add_(vis_f)
             if it % o.densification_interval == 0 or it % o.pruning_interval == 0:
                 if works is not None:                  # a rebuild copies the reduced network gradients: finish the exchange first
                     for _, _, w in works:
