@@ -92,6 +92,9 @@ struct GridBar {
     }
 };
 
+#define G4D_BIN_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) a.ctl->phase_clk[i] = clock64(); } while (0)
+#define G4D_BIN_MARK1(i) do { if (FIRST) G4D_BIN_MARK(i); } while (0)   // inside the first radix pass only
+
 struct SortShared {
     uint32_t hist[kRadix];
     uint32_t part[4 * kRadix];   // [0,2): totals of one half of the CTAs per digit, [2,4): totals of the CTAs before mine
@@ -130,7 +133,9 @@ __device__ __forceinline__ uint32_t radix_pass(const BinSortArgs& a, GridBar& gr
     }
     __syncthreads();
     if (tid < kRadix) a.H[c * kRadix + tid] = s.hist[tid];
+    G4D_BIN_MARK1(6);
     grid.sync();
+    G4D_BIN_MARK1(7);
     // ---- (b) my output base per digit = (all smaller digits of every CTA) + (same digit of the CTAs before me)
     {
         const uint32_t d = tid & (kRadix - 1), q = tid >> kDigitBits;       // 2 halves of the CTA range
@@ -151,6 +156,7 @@ __device__ __forceinline__ uint32_t radix_pass(const BinSortArgs& a, GridBar& gr
     const uint32_t incl = block_scan_incl(tot, s.sw, total);
     if (tid < kRadix) s.base[tid] = incl - tot + bef;
     __syncthreads();
+    G4D_BIN_MARK1(8);
     // ---- (c) stable scatter, 1024 elements per round: rank inside the warp by match, then across the warps by a scan
     for (uint32_t b0 = lo; b0 < hi; b0 += kBinThreads) {
         for (int j = tid; j < 32 * kRadix; j += kBinThreads) wc[j] = 0;
@@ -181,7 +187,9 @@ __device__ __forceinline__ uint32_t radix_pass(const BinSortArgs& a, GridBar& gr
         }
         __syncthreads();
     }
+    G4D_BIN_MARK1(9);
     grid.sync();
+    G4D_BIN_MARK1(10);
     return total;
 }
 
@@ -261,7 +269,6 @@ __device__ __forceinline__ uint32_t chunk_weight(uint32_t tiles_touched) { retur
 
 }  // namespace
 
-#define G4D_BIN_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) a.ctl->phase_clk[i] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(kBinThreads, 1) bin_sort_kernel(BinSortArgs a) {
     GridBar grid{a.grid_bar, 0u, gridDim.x};
@@ -460,6 +467,57 @@ __global__ void __launch_bounds__(kBinThreads, 1) bin_place_kernel(BinPlaceArgs 
 // sub-segment at once -- one memory round trip per round, not one per entry; sub-segments of up to eight entries (the bulk:
 // the average is ~4) are ranked in registers by their lane, longer ones by the whole warp with shuffles.  Ranks are unique,
 // so the final position of an entry is the number of smaller ranks in its sub-segment.
+// one lane orders its sub-segment [lo, lo + n) (n <= T, else it is left to the caller): ranks are unique, so the final position of
+// an entry is the number of smaller ranks in the sub-segment
+template <int T>
+__device__ __forceinline__ void rank_tier(const BinPlaceArgs& a, uint32_t lo, uint32_t n) {
+    constexpr bool kKeepId = T <= 16;      // the big tiers re-read the Gaussian index at store time (L1 hits) instead of
+    const bool mine = n <= (uint32_t)T;    // holding 2 T registers
+    uint32_t key[T], id[kKeepId ? T : 1];
+#pragma unroll
+    for (int q = 0; q < T; ++q) {
+        key[q] = 0xFFFFFFFFu;
+        if (mine && (uint32_t)q < n) {
+            if (kKeepId) { const uint2 e = a.kbuf[lo + q]; key[q] = e.x; id[q] = e.y; }
+            else key[q] = a.kbuf[lo + q].x;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < T; ++q) {
+        uint32_t r = 0;
+#pragma unroll
+        for (int p = 0; p < T; ++p)
+            if (p != q) r += key[p] < key[q] ? 1u : 0u;
+        if (mine && (uint32_t)q < n) a.ids[lo + r] = kKeepId ? id[q] : a.kbuf[lo + q].y;
+    }
+}
+
+// the whole warp orders ONE sub-segment [lo, lo + n), 32 < n <= 32 S: lane l holds entries l, l + 32, ...
+template <int S>
+__device__ __forceinline__ void coop_rank(const BinPlaceArgs& a, uint32_t lo, uint32_t n, int lane) {
+    uint2 e[S];
+    uint32_t r[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const uint32_t i = (uint32_t)lane + 32u * s;
+        e[s] = i < n ? a.kbuf[lo + i] : make_uint2(0xFFFFFFFFu, 0u);
+        r[s] = 0u;
+    }
+#pragma unroll
+    for (int s2 = 0; s2 < S; ++s2) {
+        if (32u * s2 >= n) break;                     // warp-uniform
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) {
+            const uint32_t kj = __shfl_sync(0xffffffffu, e[s2].x, l);      // (padding keys are never smaller than anything)
+#pragma unroll
+            for (int s = 0; s < S; ++s) r[s] += kj < e[s].x ? 1u : 0u;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+        if ((uint32_t)lane + 32u * s < n) a.ids[lo + r[s]] = e[s].y;
+}
+
 __global__ void __launch_bounds__(256, 4) bin_fix_kernel(BinPlaceArgs a, int chunks) {
     const int lane = threadIdx.x & 31;
     const int rounds = (chunks + 31) / 32;
@@ -481,62 +539,31 @@ __global__ void __launch_bounds__(256, 4) bin_fix_kernel(BinPlaceArgs a, int chu
             lo = min(lo, a.capacity); hi = min(hi, a.capacity);
         }
         const uint32_t n = hi - lo;
-        constexpr int E = 8, E2 = 32;
+        // Every lane ranks ITS sub-segment in registers, all 32 sub-segments of the warp in parallel: one memory round trip for
+        // the whole round.  The register tier T is the smallest that holds the longest sub-segment of the warp (warp-uniform):
+        // T loads, T^2 compares, T stores per lane -- the fixed 8 / 32 tiers of the first version spent ~1100 instructions per
+        // warp (ncu: 29.5 M for the kernel, issue bound), most of them compares against padding.
         const uint32_t nmax = __reduce_max_sync(0xffffffffu, n);
-        uint32_t done_limit = E;            // sub-segments of up to this many entries are finished by the per-lane code below
-        if (nmax <= (uint32_t)E) {
-            uint2 e[E];
-#pragma unroll
-            for (int q = 0; q < E; ++q) e[q] = (uint32_t)q < n ? a.kbuf[lo + q] : make_uint2(0xFFFFFFFFu, 0u);
-#pragma unroll
-            for (int q = 0; q < E; ++q) {
-                if ((uint32_t)q < n) {
-                    uint32_t r = 0;
-#pragma unroll
-                    for (int p = 0; p < E; ++p) r += e[p].x < e[q].x ? 1u : 0u;
-                    a.ids[lo + r] = e[q].y;
-                }
-            }
-        } else {
-            // a dense tile: (nearly) every lane's sub-segment is long.  Each lane still ranks its own sub-segment in registers, up
-            // to 32 entries, all 32 sub-segments of the warp in parallel -- one memory round trip for the whole round instead of
-            // one per long sub-segment (measured at C4: placement + fix-up 1.38 ms, most of it serialised load latency here)
-            done_limit = E2;
-            uint32_t key[E2];             // (the Gaussian indices are re-read at store time: L1 hits, and 32 registers fewer)
-#pragma unroll
-            for (int q = 0; q < E2; ++q) key[q] = ((uint32_t)q < n && n <= (uint32_t)E2) ? a.kbuf[lo + q].x : 0xFFFFFFFFu;
-            const uint32_t nq = min(nmax, (uint32_t)E2);
-#pragma unroll
-            for (int q = 0; q < E2; ++q) {
-                if ((uint32_t)q >= nq) break;              // warp-uniform
-                uint32_t r = 0;
-#pragma unroll
-                for (int p = 0; p < E2; ++p) r += key[p] < key[q] ? 1u : 0u;
-                if ((uint32_t)q < n && n <= (uint32_t)E2) a.ids[lo + r] = a.kbuf[lo + q].y;
-            }
-        }
+        uint32_t done_limit;            // sub-segments of up to this many entries are finished by the per-lane code
+        if (nmax <= 4u) { rank_tier<4>(a, lo, n); done_limit = 4u; }
+        else if (nmax <= 8u) { rank_tier<8>(a, lo, n); done_limit = 8u; }
+        else if (nmax <= 12u) { rank_tier<12>(a, lo, n); done_limit = 12u; }
+        else if (nmax <= 16u) { rank_tier<16>(a, lo, n); done_limit = 16u; }
+        else if (nmax <= 24u) { rank_tier<24>(a, lo, n); done_limit = 24u; }
+        else { rank_tier<32>(a, lo, n); done_limit = 32u; }
+        // sub-segments longer than 32 entries (a tile under the few dozen nearest, screen-filling Gaussians of a chunk): the whole
+        // warp ranks one at a time, S entries per lane in registers, every key broadcast once by shuffle (n shuffles + n S
+        // compares for n entries).  The first version re-read the list from L1 once per entry: ~16 k cycles for n = 100, ten such
+        // sub-segments in one warp were the critical path of the kernel (74 .. 110 us depending on the camera).
         uint32_t todo = __ballot_sync(0xffffffffu, n > done_limit);
-        uint32_t blo = 0, bnn = 0;
-        uint2 ei = make_uint2(0xFFFFFFFFu, 0u);
-        if (todo) {
-            const int src = __ffs(todo) - 1;
-            blo = __shfl_sync(0xffffffffu, lo, src); bnn = __shfl_sync(0xffffffffu, n, src);
-            if ((uint32_t)lane < bnn) ei = a.kbuf[blo + lane];
-        }
         while (todo) {
+            const int src = __ffs(todo) - 1;
             todo &= todo - 1;
-            const uint32_t clo = blo, cnn = bnn;
-            const uint2 ce = ei;
-            if (todo) {                                             // prefetch the next long sub-segment
-                const int src = __ffs(todo) - 1;
-                blo = __shfl_sync(0xffffffffu, lo, src); bnn = __shfl_sync(0xffffffffu, n, src);
-                ei = (uint32_t)lane < bnn ? a.kbuf[blo + lane] : make_uint2(0xFFFFFFFFu, 0u);
-            }
-            if (cnn <= 32) {                                        // the whole sub-segment sits in the lanes: rank by shuffle
-                uint32_t r = 0;
-                for (uint32_t j = 0; j < cnn; ++j) r += __shfl_sync(0xffffffffu, ce.x, (int)j) < ce.x ? 1u : 0u;
-                if ((uint32_t)lane < cnn) a.ids[clo + r] = ce.y;
-            } else {
+            const uint32_t clo = __shfl_sync(0xffffffffu, lo, src), cnn = __shfl_sync(0xffffffffu, n, src);
+            if (cnn <= 64u) coop_rank<2>(a, clo, cnn, lane);
+            else if (cnn <= 128u) coop_rank<4>(a, clo, cnn, lane);
+            else if (cnn <= 256u) coop_rank<8>(a, clo, cnn, lane);
+            else {
                 for (uint32_t i = lane; i < cnn; i += 32) {
                     const uint2 x = a.kbuf[clo + i];
                     uint32_t r = 0;

@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from argparse import Namespace
 from typing import Dict, List, Optional, Sequence
 
@@ -316,6 +317,10 @@ class DPTrainer:
 
     def _launch_allreduce(self):
         st = self.state
+        if self.dist.get_backend() != "nccl":
+            # gloo stages CUDA tensors through pinned host memory on its own streams (the CPU-side test configuration): hand it
+            # a finished buffer.  NCCL (the production path) is stream-ordered and needs no host synchronisation.
+            torch.cuda.current_stream(st.device).synchronize()
         k = max(1, int(self.comm_chunks))
         step = (st.numel // k + 3) // 4 * 4
         works, b = [], 0

@@ -82,6 +82,53 @@ def test_rasterizer_forward_indices_bit_exact_and_image(ci):
     assert (ctx.read("n_contrib").reshape(cam.image_height, -1) != ref["n_contrib"]).mean() < 0.005
 
 
+@pytest.mark.parametrize("n", [8_000, 14_000, 25_000, 45_000])
+def test_binning_long_sub_segments_bit_exact(n):
+    """Every Gaussian covers (nearly) every tile of a 4 x 3 tile image: a (tile, chunk) sub-segment of the placement holds
+    ~n / 148 entries -- 54, 95, 169, 304 -- i.e. the warp-cooperative rank paths of bin_fix_kernel with 2, 4 and 8 entries per
+    lane and the > 256 fallback.  Sorted keys / ids / ranges stay bit-identical to the reference order."""
+    c = dict(n=n, seed=11, wh=(64, 48), theta=35.0, radius=3.0, deg=0, bg=(0.0, 0.0, 0.0), scale_mean=0.3)
+    cam, ins, rc = _raster_case(**c)
+    m3, sc, ro, op, sh = [t.cuda() for t in ins]
+    rast = g4d.GaussianRasterizer(_settings(cam, c["bg"], c["deg"]))
+    m2 = torch.zeros_like(m3, requires_grad=True)
+    color, radii, depth = rast(means3D=m3.clone().requires_grad_(True), means2D=m2, shs=sh, colors_precomp=None, opacities=op,
+                               scales=sc, rotations=ro, cov3D_precomp=None)
+    ctx = color.grad_fn.lease.ctx
+    ref = rr.rasterize_forward(rc, *[t.numpy() for t in ins[:5]])
+    bn = ref["bin"]
+    assert ctx.stats().num_rendered == bn.R and bn.R > 5 * n
+    assert np.array_equal(ctx.read("sorted_keys"), bn.keys)
+    assert np.array_equal(ctx.read("sorted_ids"), bn.ids)
+    assert np.array_equal(ctx.read("ranges"), bn.ranges)
+
+
+def test_programmatic_dependent_launch_changes_nothing():
+    """G4D_OPT_PDL: the kernels of a forward queue up behind one another (griddepcontrol); images, radii and the instance list are
+    bit-identical to ordinary stream order."""
+    scene = synth.make_scene(6000, seed=4, scale_mean=0.04)
+    mod = make_module("dynerf", seed=3, aabb=scene["aabb"]).cuda()
+    pc = synth.SyntheticGaussianModel(scene, mod, sh_degree=3, requires_grad=False)
+    bg = torch.tensor([0.2, 0.1, 0.3], device="cuda")
+    ws = g4d._lib.Workspace.get(0)
+    outs = []
+    try:
+        for pdl in (0, 1, 0, 1):
+            ws.set_option(g4d._lib.OPT_PDL, pdl)
+            frames = []
+            with torch.no_grad():
+                for i in range(3):
+                    o = g4d.render(synth.make_camera(40.0 * i, 320, 200, radius=3.0, time=0.2 * i), pc, _Pipe, bg)
+                    frames.append((o["render"].clone(), o["depth"].clone(), o["radii"].clone()))
+            torch.cuda.synchronize()
+            outs.append(frames)
+    finally:
+        ws.set_option(g4d._lib.OPT_PDL, 1)
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
 @pytest.mark.parametrize("ci", range(len(RASTER_CASES)))
 def test_rasterizer_backward(ci):
     c = RASTER_CASES[ci]

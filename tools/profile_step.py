@@ -77,7 +77,9 @@ def main():
                   {k: round(v, 4) for k, v in c.stage_times().items()}, flush=True)
             ph = c.read("bin_phases")
             names = ["key_range", "depth_sort", "chunking", "count", "scan"]
-            print("   bin_sort phase cycles (CTA 0):", {n_: int(ph[j + 1] - ph[j]) for j, n_ in enumerate(names)}, "key bits", int(ph[15]), flush=True)
+            print("   bin_sort phase cycles (CTA 0):", {n_: int(ph[j + 1] - ph[j]) for j, n_ in enumerate(names)}, "key bits", int(ph[15]),
+                  "| first radix pass:", {n_: int(ph[j + 1] - ph[j]) for j, n_ in zip(range(6, 10), ["hist->barrier", "barrier", "offsets", "scatter"])}
+                  | {"hist": int(ph[6] - ph[1]), "barrier2": int(ph[10] - ph[9])}, flush=True)
 
 
 if __name__ == "__main__":
