@@ -518,6 +518,37 @@ __device__ __forceinline__ void coop_rank(const BinPlaceArgs& a, uint32_t lo, ui
         if ((uint32_t)lane + 32u * s < n) a.ids[lo + r[s]] = e[s].y;
 }
 
+// any length: 256 entries at a time in registers (8 per lane), every key of the sub-segment streamed past them 32 at a time
+// (coalesced re-read, next block prefetched) and broadcast by shuffle -- n^2 / 256 shuffles instead of n^2 / 32 dependent loads
+__device__ __noinline__ void coop_rank_big(const BinPlaceArgs& a, uint32_t lo, uint32_t n, int lane) {
+    constexpr int S = 8;
+    for (uint32_t base = 0; base < n; base += 32u * S) {
+        uint2 e[S];
+        uint32_t r[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const uint32_t i = base + (uint32_t)lane + 32u * s;
+            e[s] = i < n ? a.kbuf[lo + i] : make_uint2(0xFFFFFFFFu, 0u);
+            r[s] = 0u;
+        }
+        uint32_t nxt = (uint32_t)lane < n ? a.kbuf[lo + lane].x : 0xFFFFFFFFu;
+        for (uint32_t j0 = 0; j0 < n; j0 += 32u) {
+            const uint32_t cur = nxt;
+            const uint32_t jn = j0 + 32u + (uint32_t)lane;
+            nxt = jn < n ? a.kbuf[lo + jn].x : 0xFFFFFFFFu;
+#pragma unroll 8
+            for (int l = 0; l < 32; ++l) {
+                const uint32_t kj = __shfl_sync(0xffffffffu, cur, l);
+#pragma unroll
+                for (int s = 0; s < S; ++s) r[s] += kj < e[s].x ? 1u : 0u;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+            if (base + (uint32_t)lane + 32u * s < n) a.ids[lo + r[s]] = e[s].y;
+    }
+}
+
 __global__ void __launch_bounds__(256, 4) bin_fix_kernel(BinPlaceArgs a, int chunks) {
     const int lane = threadIdx.x & 31;
     const int rounds = (chunks + 31) / 32;
@@ -526,16 +557,20 @@ __global__ void __launch_bounds__(256, 4) bin_fix_kernel(BinPlaceArgs a, int chu
     const uint32_t item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // (tile, round): a dense tile's rounds run
     const uint32_t t = item / (uint32_t)rounds;                                   // on different warps
     if (t >= (uint32_t)a.num_tiles) return;
-    const uint32_t total = __ldg(a.tile_total + t);
-    if (total == 0) return;
-    const uint32_t start = a.tile_start[t];
     const uint32_t* mrow = a.M + (size_t)t * chunks;
     {
+        // the four words that locate a lane's sub-segment are independent loads: ONE memory round trip in front of the
+        // entries' own, not three (total -> start -> M row); a warp's life is a handful of such round trips
         const int c = (int)(item - t * (uint32_t)rounds) * 32 + lane;
+        const uint32_t total = __ldg(a.tile_total + t);
+        const uint32_t start = __ldg(a.tile_start + t);
+        const uint32_t m0 = c < chunks ? __ldg(mrow + c) : 0u;
+        const uint32_t m1 = c + 1 < chunks ? __ldg(mrow + c + 1) : 0u;
+        if (total == 0) return;
         uint32_t lo = 0, hi = 0;
         if (c < chunks) {
-            lo = start + __ldg(mrow + c);
-            hi = start + (c + 1 < chunks ? __ldg(mrow + c + 1) : total);
+            lo = start + m0;
+            hi = start + (c + 1 < chunks ? m1 : total);
             lo = min(lo, a.capacity); hi = min(hi, a.capacity);
         }
         const uint32_t n = hi - lo;
@@ -563,14 +598,7 @@ __global__ void __launch_bounds__(256, 4) bin_fix_kernel(BinPlaceArgs a, int chu
             if (cnn <= 64u) coop_rank<2>(a, clo, cnn, lane);
             else if (cnn <= 128u) coop_rank<4>(a, clo, cnn, lane);
             else if (cnn <= 256u) coop_rank<8>(a, clo, cnn, lane);
-            else {
-                for (uint32_t i = lane; i < cnn; i += 32) {
-                    const uint2 x = a.kbuf[clo + i];
-                    uint32_t r = 0;
-                    for (uint32_t j = 0; j < cnn; ++j) r += a.kbuf[clo + j].x < x.x ? 1u : 0u;
-                    a.ids[clo + r] = x.y;
-                }
-            }
+            else coop_rank_big(a, clo, cnn, lane);
         }
     }
 }
