@@ -65,3 +65,27 @@ def test_sass_is_sm100a(lib):
     if out.returncode != 0:
         pytest.skip("cuobjdump unavailable")
     assert "sm_100a" in out.stdout
+
+
+def test_option_constants_match_header():
+    src = open(os.path.join(ROOT, "include", "g4d.h")).read()
+    enum = src[src.index("enum { G4D_OPT_SYNC_MODE"):]
+    enum = re.sub(r"/\*.*?\*/", "", enum[:enum.index("};")], flags=re.S)
+    found = dict(re.findall(r"G4D_OPT_([A-Z_]+)\s*=\s*(\d+)", enum))
+    assert len(found) >= 9 and len(set(found.values())) == len(found)
+    for name, value in found.items():
+        assert getattr(g4d_lib, "OPT_" + name) == int(value), name
+
+
+def test_forward_chain_kernels_carry_the_dependent_launch_instructions(lib):
+    """every kernel of the forward chain waits on / releases its programmatic dependents (SASS ACQBULK / PREEXIT)."""
+    chain = {"_ZN3g4d16bin_place_kernelENS_12BinPlaceArgsE": ("ACQBULK", "PREEXIT"),
+             "_ZN3g4d14bin_fix_kernelENS_12BinPlaceArgsEi": ("ACQBULK", "PREEXIT"),
+             "_ZN3g4d15bin_sort_kernelENS_11BinSortArgsE": ("PREEXIT",)}
+    for fn, needed in chain.items():
+        out = subprocess.run(["cuobjdump", "-sass", "-fun", fn, g4d_lib.LIB_PATH], capture_output=True, text=True)
+        if out.returncode != 0:
+            pytest.skip("cuobjdump unavailable")
+        assert "Function : " + fn in out.stdout, fn
+        for ins in needed:
+            assert ins in out.stdout, (fn, ins)

@@ -136,3 +136,56 @@ def test_strip_cull_predicate_is_conservative():
             culled += 1
             assert not reach, (mx, my, A, B, C, op)
     assert culled > 300 and kept > 300      # the sample exercises both outcomes
+
+
+def test_sub_segment_rank_fix_restores_the_depth_order():
+    """DESIGN 4.2 step 5 (bin_fix_kernel) restated in numpy: the placement leaves the entries of a (tile, chunk) sub-segment in
+    arbitrary order; the final position of an entry is lo + (number of smaller depth ranks in its sub-segment).  The three code
+    paths -- per-lane register tiers padded with 0xFFFFFFFF, whole-warp ranking with S entries per lane, streaming of the keys past
+    256 register-resident entries at a time -- give the depth-ordered list for every length."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    PAD = np.uint32(0xFFFFFFFF)
+
+    def rank_tier(keys, T):                          # one lane: T registers, padding never counts as smaller
+        reg = np.full(T, PAD, np.uint32); reg[:len(keys)] = keys
+        return [int(sum(reg[p] < reg[q] for p in range(T) if p != q)) for q in range(len(keys))]
+
+    def coop_rank(keys, S):                          # one warp: lane l holds entries l, l + 32, ...; every key broadcast once
+        n = len(keys)
+        reg = np.full((S, 32), PAD, np.uint32); reg.reshape(-1)[:n] = keys
+        r = np.zeros((S, 32), np.int64)
+        for s2 in range(S):
+            if 32 * s2 >= n:
+                break
+            for l in range(32):
+                r += reg[s2, l] < reg
+        return r.reshape(-1)[:n].tolist()
+
+    def coop_rank_big(keys):                         # 256 entries at a time, the whole list streamed 32 keys per step
+        n, out = len(keys), []
+        for base in range(0, n, 256):
+            reg = np.full(256, PAD, np.uint32); m = min(256, n - base); reg[:m] = keys[base:base + m]
+            r = np.zeros(256, np.int64)
+            for j0 in range(0, n, 32):
+                cur = np.full(32, PAD, np.uint32); k = min(32, n - j0); cur[:k] = keys[j0:j0 + k]
+                for l in range(32):
+                    r += cur[l] < reg
+            out += r[:m].tolist()
+        return out
+
+    for n in (1, 3, 4, 5, 8, 9, 12, 13, 16, 17, 24, 25, 32, 33, 64, 65, 128, 129, 200, 256, 257, 300, 700):
+        ranks = np.sort(rng.choice(2_000_000, size=n, replace=False)).astype(np.uint32)     # unique depth ranks of the chunk
+        ids = rng.integers(0, 1 << 31, size=n, dtype=np.int64)
+        order = rng.permutation(n)                                                          # as the placement left them
+        keys, vals = ranks[order], ids[order]
+        if n <= 32:
+            T = next(t for t in (4, 8, 12, 16, 24, 32) if n <= t)
+            r = rank_tier(keys, T)
+        elif n <= 256:
+            r = coop_rank(keys, next(s for s in (2, 4, 8) if n <= 32 * s))
+        else:
+            r = coop_rank_big(keys)
+        assert sorted(r) == list(range(n)), n                                              # a permutation: no two entries collide
+        fixed = np.empty(n, np.int64); fixed[np.asarray(r)] = vals
+        assert np.array_equal(fixed, ids), n
