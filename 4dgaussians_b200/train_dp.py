@@ -317,7 +317,7 @@ class DPTrainer:
 
     def _launch_allreduce(self):
         st = self.state
-        if self.dist.get_backend() != "nccl":
+        if st.device.type == "cuda" and self.dist.get_backend() != "nccl":
             # gloo stages CUDA tensors through pinned host memory on its own streams (the CPU-side test configuration): hand it
             # a finished buffer.  NCCL (the production path) is stream-ordered and needs no host synchronisation.
             torch.cuda.current_stream(st.device).synchronize()

@@ -88,3 +88,52 @@ def test_bucket_detects_detached_grads():
     b.zero_(); b.attach()
     (p.sum() * 2).backward()
     assert torch.equal(p.grad, torch.full((3, 2), 2.0)) and p.grad.data_ptr() == b.flat.data_ptr()
+
+
+def _trainer_worker(rank, world, port, q):
+    """DPTrainer's own exchange (train_dp.py): the flat gradient buffer in `comm_chunks` asynchronous slices and the
+    densification statistics reduced on demand -- on CPU tensors over gloo (no kernels are launched)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    td = importlib.import_module("4dgaussians_b200.train_dp")
+    synth = importlib.import_module("4dgaussians_b200.synth")
+    g4d = importlib.import_module("4dgaussians_b200")
+    torch.manual_seed(3)
+    scene = synth.make_scene(300, seed=1, scale_mean=0.05)
+    mod = g4d.deform_network(synth.hidden_args("small128"))
+    gs = td.GaussianSet(scene, mod, device="cpu")
+    tr = td.DPTrainer(gs, td.default_opt(), dist=dist, world_size=world, rank=rank, cameras_extent=2.0, seed=0)
+    st = tr.state
+    base = torch.arange(st.numel, dtype=torch.float32) % 97.0
+    st.grad.copy_(base * (rank + 1))                      # rank r holds (r + 1) * base: the SUM over two ranks is 3 * base
+    works = tr._launch_allreduce()
+    assert len(works) == tr.comm_chunks and works[0][0] == 0 and works[-1][1] == st.numel
+    assert all(b % 4 == 0 for b, _, _ in works)           # slices start on 16-byte boundaries (Adam kernel spans)
+    for _, _, w in works:
+        w.wait()
+    ok_grad = bool(torch.equal(st.grad, 3.0 * base)) and st.attached()
+    n = gs._xyz.shape[0]
+    gs.xyz_gradient_accum.fill_(float(rank + 1)); gs.denom.fill_(1.0)
+    gs.max_radii2D.copy_(torch.arange(n, dtype=torch.float32) * (rank + 1))
+    accum, denom, radii = tr._global_stats()
+    ok_stats = bool(torch.equal(accum, torch.full((n, 1), 3.0)) and torch.equal(denom, torch.full((n, 1), 2.0))
+                    and torch.equal(radii, torch.arange(n, dtype=torch.float32) * 2)
+                    and float(gs.xyz_gradient_accum[0]) == rank + 1)          # the local accumulators stay local
+    q.put((rank, ok_grad, ok_stats))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_trainer_sliced_allreduce_and_global_stats_two_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_trainer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=150) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(30)
+        assert p.exitcode == 0
+    assert res == [(0, True, True), (1, True, True)]
