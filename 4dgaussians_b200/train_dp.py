@@ -293,7 +293,7 @@ class DPTrainer:
             if it % o.densification_interval == 0 or it % o.pruning_interval == 0:
                 if works is not None:                  # a rebuild copies the reduced network gradients: finish the exchange first
                     for _, _, w in works:
-                        w.wait()
+                        self._wait(w)
                 self._densify_and_prune(it, stage)
             if it % o.opacity_reset_interval == 0:
                 self.reset_opacity()
@@ -304,23 +304,35 @@ class DPTrainer:
         if works is None or self._rebuilt_this_step:
             if works is not None:
                 for _, _, w in works:
-                    w.wait()
+                    self._wait(w)
             self.state.adam_step(lrs, grad_scale=1.0 / self.world, only=only)
         else:
             for i, (b, e, w) in enumerate(works):
-                w.wait()                                   # the current stream waits for slice i only
+                self._wait(w)                              # the current stream waits for slice i only
                 self.state.adam_step(lrs, grad_scale=1.0 / self.world, span=(b, e), count_step=(i == 0))
         self._rebuilt_this_step = False
         return self.loss_accum
 
     comm_chunks = 4
 
+    def _host_staged_collectives(self) -> bool:
+        """gloo stages CUDA tensors through pinned host memory on its own streams (the CPU-side test configuration): it is
+        handed finished buffers and its results are awaited on the host.  NCCL (the production path) is stream-ordered and
+        needs no host synchronisation."""
+        return self.state.device.type == "cuda" and self.dist.get_backend() != "nccl"
+
+    def _sync_device(self):
+        torch.cuda.synchronize(self.state.device)
+
+    def _wait(self, work):
+        work.wait()
+        if self._host_staged_collectives():
+            self._sync_device()
+
     def _launch_allreduce(self):
         st = self.state
-        if st.device.type == "cuda" and self.dist.get_backend() != "nccl":
-            # gloo stages CUDA tensors through pinned host memory on its own streams (the CPU-side test configuration): hand it
-            # a finished buffer.  NCCL (the production path) is stream-ordered and needs no host synchronisation.
-            torch.cuda.current_stream(st.device).synchronize()
+        if self._host_staged_collectives():
+            self._sync_device()
         k = max(1, int(self.comm_chunks))
         step = (st.numel // k + 3) // 4 * 4
         works, b = [], 0

@@ -110,8 +110,20 @@ def _trainer_worker(rank, world, port, q):
     assert len(works) == tr.comm_chunks and works[0][0] == 0 and works[-1][1] == st.numel
     assert all(b % 4 == 0 for b, _, _ in works)           # slices start on 16-byte boundaries (Adam kernel spans)
     for _, _, w in works:
-        w.wait()
-    ok_grad = bool(torch.equal(st.grad, 3.0 * base)) and st.attached()
+        tr._wait(w)
+    ok_grad = bool(torch.equal(st.grad, 3.0 * base)) and st.attached() and not tr._host_staged_collectives()
+    # a CUDA buffer over gloo is handed over finished and awaited on the host (stand-in device, counting synchronisation)
+    real_device, calls = st.device, []
+    st.device = torch.device("cuda", 0)
+    tr._sync_device = lambda: calls.append(1)
+
+    class _Done:
+        def wait(self):
+            calls.append(0)
+    ok_grad = ok_grad and tr._host_staged_collectives()
+    tr._wait(_Done())
+    st.device = real_device
+    ok_grad = ok_grad and calls == [0, 1]
     n = gs._xyz.shape[0]
     gs.xyz_gradient_accum.fill_(float(rank + 1)); gs.denom.fill_(1.0)
     gs.max_radii2D.copy_(torch.arange(n, dtype=torch.float32) * (rank + 1))
